@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the encrypted-imputation cloud evaluation (cloud_compute_score) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): iDASH-scale synthetic, 1004 samples x 16184 tag SNPs x 80882 target
+SNPs, neighbors = 5: 48 552 input TRLWE ciphertexts -> 242 646 output ciphertexts per batch of 1004
+samples. One step = one pass of cloud_compute_score over the batch(es). With N GPUs the job is N batches
+(N x 1004 samples, BASELINE configs[4] shape) sharded by contiguous target-SNP range: rank r evaluates
+targets [G r/N, G (r+1)/N) of every batch from the tag-ciphertext slab its band touches; no collective is
+on the data path (weak scaling: per-GPU work is constant).
+
+metric = samples x targets x 3 per second (packed imputed slots/s); `out_ct_per_s` is the same in output
+ciphertexts. `value` is timed with the inputs resident in HBM; `e2e` goes through the host-buffer C-ABI
+call (H2D + kernels + D2H inside the timed region). The reference arm (--impl reference) and the
+`cpu_baseline` object time the reference's own cloud_compute_score (oracle/_ref, compiled from the
+unmodified reference) on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "imputed target-SNP ciphertext slots/sec (samples x targets x 3)"
+UNIT = "slots/s"
+S, T, G, NEIGHBORS = 1004, 16184, 80882, 5
+SEED = 1234
+CT_BYTES = 8192
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--neighbors", type=int, default=NEIGHBORS)
+    ap.add_argument("--targets", type=int, default=G, help="(debug) fewer target SNPs")
+    ap.add_argument("--tags", type=int, default=T)
+    ap.add_argument("--samples", type=int, default=S)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.dev = device_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(self.dev)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in Path(self.f.name).read_text().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            r = [x.strip() for x in r]
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, r[5:9]):
+                if v.lower() == "active":
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(power), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+def build_workload(args):
+    from idash2019_2_b200 import synth
+    tag, tgt = synth.make_positions(args.tags, args.targets, SEED)
+    model = synth.make_model(tag, tgt, args.neighbors, SEED)
+    return model
+
+
+def shard_rows(model, rank, world, n_targets):
+    """Contiguous target-SNP range of this rank; the model is re-based so that its first input ciphertext is 0."""
+    lo, hi = n_targets * rank // world, n_targets * (rank + 1) // world
+    sub = model.rows(3 * lo, 3 * hi)
+    real = sub.col != 0xFFFFFFFF
+    ct_min = int(sub.col[real].min()) if real.any() else 0      # NUM_REGIONS = 1: ct index == input bigIndex
+    ct_max = int(sub.col[real].max()) if real.any() else 0
+    col = sub.col.copy()
+    col[real] -= np.uint32(ct_min)
+    sub.col = col
+    return sub, ct_min, ct_max - ct_min + 1, (lo, hi)
+
+
+# ---------------------------------------------------------------------------------------------------
+def reference_sample_runner(args, model):
+    """Returns (fn(sample_targets) -> seconds of the reference cloud_compute_score, kind, cores)."""
+    from idash2019_2_b200 import synth
+    from oracle import pyoracle as po
+    cores = po.host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    kind = "reference" if po.have_ref() else "port"
+    NRr, RSr = 1024 // args.samples, 1024 // (1024 // args.samples)
+    cache = {}
+
+    def run(sample_targets: int) -> float:
+        if sample_targets not in cache:
+            sub = model.rows(0, 3 * sample_targets)
+            real = sub.col != 0xFFFFFFFF
+            n_in = int(sub.col[real].max()) // NRr + 1
+            cache.clear()
+            cache[sample_targets] = (sub, synth.random_ciphertexts(n_in, SEED), np.full(n_in, 2.0 ** -50),
+                                     np.arange(n_in, dtype=np.uint32))
+        sub, cts, var, idx = cache[sample_targets]
+        if kind == "reference":
+            return po.cloud_ref(args.samples, NRr, RSr, idx, cts, var, sub.out_bidx, sub.row_ptr, sub.col, sub.coef,
+                                want_output=False)[2]
+        t0 = time.perf_counter()
+        po.cloud_port(args.samples, NRr, RSr, idx, cts, var, sub.row_ptr, sub.col, sub.coef, threads=cores)
+        return time.perf_counter() - t0
+
+    return run, kind, cores
+
+
+def pick_sample(run, n_targets, budget_s=2.5):
+    """Bounded sample of the workload: as many leading target SNPs as the reference evaluates in ~budget_s."""
+    probe = min(n_targets, 1500)
+    t = run(probe)
+    if probe == n_targets:
+        return probe
+    est = int(probe * budget_s / max(t, 1e-3))
+    return max(probe, min(n_targets, est))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    model = build_workload(args)
+    run, kind, cores = reference_sample_runner(args, model)
+    sample = pick_sample(run, args.targets)
+    for _ in range(args.warmup):
+        run(sample)
+    times = [run(sample) for _ in range(args.steps)]
+    total = sum(times)
+    value = args.samples * sample * 3 * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "out_ct_per_s": 3 * sample * args.steps / total,
+        "config": {"workload": f"iDASH-scale synthetic {args.samples} samples x {args.tags} tag x {args.targets} target SNPs, "
+                               f"neighbors={args.neighbors} (BASELINE configs[1])", "neighbors": args.neighbors,
+                   "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"first {sample} of {args.targets} target SNPs ({3 * sample} output ciphertexts) per step, "
+                                   f"reference cloud_compute_score 'fhe wall time' with {cores} OpenMP threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:   # convenience: relaunch under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29533", __file__] + sys.argv[1:]
+            os.execv(sys.executable, cmd)
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build_native()
+    if world > 1:
+        dist.barrier()
+    from idash2019_2_b200 import api
+
+    model = build_workload(args)
+    NR = 1024 // args.samples
+    RS = 1024 // NR
+    sub, ct_min, slab, (t_lo, t_hi) = shard_rows(model, rank, world, args.targets) if NR == 1 else (model, 0, 0, (0, args.targets))
+    if NR != 1:
+        slab = (3 * args.tags - 1) // NR + 1
+    n_rows = sub.n_out
+    n_batches = world
+    ctx = api.Context(local_rank)
+    m = api.Model(ctx, args.samples, NR, RS, sub.out_bidx, sub.row_ptr, sub.col, sub.coef)
+    gen = torch.Generator(device="cuda").manual_seed(SEED + rank)
+    ins = [torch.randint(-2 ** 31, 2 ** 31, (slab, 2048), dtype=torch.int32, device="cuda", generator=gen)
+           for _ in range(n_batches)]
+    outs = [torch.empty((n_rows, 2048), dtype=torch.int32, device="cuda") for _ in range(n_batches)]
+
+    def step():
+        for b in range(n_batches):
+            api.cloud_compute_score_device(ctx, m, ins[b], outs[b])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    ctx.check_device_status()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = ctx.kernel_launches()
+    ctx.timing_enable(args.steps * n_batches)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    if sampler:
+        sampler.start()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    kernel_ms = ctx.timing_read(args.steps * n_batches)
+    ctx.timing_enable(0)
+    launches = ctx.kernel_launches() - launches0
+
+    # ---- end to end through the host-buffer entry point (pinned host memory, H2D + D2H per step)
+    e2e_steps = max(1, min(args.e2e_steps, args.steps))
+    h_in = torch.empty((slab, 2048), dtype=torch.int32, pin_memory=True)
+    h_in.copy_(ins[0])
+    h_out = torch.empty((n_rows, 2048), dtype=torch.int32, pin_memory=True)
+    np_in, np_out = h_in.numpy().view(np.uint32), h_out.numpy().view(np.uint32)
+
+    def e2e_step():
+        for _b in range(n_batches):
+            api.cloud_compute_score(ctx, m, np_in, out_ct=np_out)
+
+    e2e_step()                      # warm-up: sizes the library's device staging buffers
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    same = torch.equal(h_out.cuda(), outs[0])   # host path and device path agree on the same input
+
+    t = torch.tensor([ms_total, t_e2e * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        slots_per_step = args.samples * args.targets * 3 * n_batches
+        ct_per_step = args.targets * 3 * n_batches
+        value = slots_per_step * args.steps / (ms_total * 1e-3)
+        k_ms = statistics.mean(kernel_ms) if kernel_ms else float("nan")
+        alg_bytes = CT_BYTES * (slab + n_rows)            # per launch: every input ct read once, every output written once
+        peak, peak_src = measured_peak_gbs()
+        achieved = alg_bytes / (k_ms * 1e-3) * 1e-9
+        h2d = n_batches * (slab * CT_BYTES)
+        d2h = n_batches * (n_rows * (CT_BYTES + 4 + 8))
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "out_ct_per_s": ct_per_step * args.steps / (ms_total * 1e-3),
+            "config": {"workload": f"iDASH-scale synthetic {args.samples} samples x {args.tags} tag x {args.targets} target SNPs, "
+                                   f"neighbors={args.neighbors} (BASELINE configs[1])" +
+                                   (f"; {n_batches} batches sharded by target range over {world} GPUs" if world > 1 else ""),
+                       "neighbors": args.neighbors, "batches": n_batches, "targets_per_gpu": t_hi - t_lo,
+                       "in_ct_per_gpu_batch": slab, "out_ct_per_gpu_batch": n_rows,
+                       "l2": "inputs+outputs per step (2.4 GB) exceed the 126 MB L2; no explicit flush"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "cloud_eval_kernel", "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes,
+                         "peak_source": peak_src, "kernel_share_of_step": k_ms * n_batches / (ms_total / args.steps)},
+            "e2e": {"value": slots_per_step * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
+                    "matches_device_path": bool(same)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                run, kind, cores = reference_sample_runner(args, model)
+                sample = pick_sample(run, args.targets, budget_s=3.0)
+                tt = min(run(sample) for _ in range(2))
+                line["cpu_baseline"] = {"value": args.samples * sample * 3 / tt, "unit": UNIT, "cores": cores, "kind": kind,
+                                        "sample": f"first {sample} of {args.targets} target SNPs ({3 * sample} output "
+                                                  f"ciphertexts), best of 2, cloud_compute_score only ('fhe wall time')",
+                                        "seconds": tt}
+            except Exception as e:  # the checker is optional for the bench line; say why it is missing
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
+        print(json.dumps(line), flush=True)
+    m.free()
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

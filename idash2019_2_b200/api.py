@@ -1,0 +1,246 @@
+"""Python host-side mirror of the reference interface for the hot path, on top of the C ABI.
+
+    Context                       one per GPU (one process per GPU)
+    Model                         Model of eval/idash.h:129-134 compiled + uploaded (idash_b200_model_upload)
+    cloud_compute_score(...)      eval/idash.cpp:763-848, host numpy buffers  (idash_b200_cloud_eval_host)
+    cloud_compute_score_device    same, torch CUDA tensors on the current stream (idash_b200_cloud_eval_device)
+    decrypt_predictions(...)      eval/idash.cpp:681-761, host buffers        (idash_b200_decrypt_host)
+    decrypt_predictions_device    same, torch CUDA tensors
+    compile_layout(...)           the block-banded layout as numpy arrays (no GPU needed)
+
+PyTorch is only plumbing here (device memory, streams); all compute is in libidash_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import (CONSTANT_BIDX, CT_BYTES, CT_WORDS, LAYOUT_PACKED, LAYOUT_RECORDS, N, RECORD_BYTES,  # noqa: F401
+                   IdashB200Error)
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        self.device = device
+        L.check(L.lib().idash_b200_init(C.byref(self._h), device))
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise RuntimeError("Context is closed")
+        return self._h
+
+    def kernel_launches(self) -> int:
+        return int(L.lib().idash_b200_kernel_launches(self.handle))
+
+    def timing_enable(self, max_launches: int) -> None:
+        L.check(L.lib().idash_b200_timing_enable(self.handle, int(max_launches)))
+
+    def timing_read(self, capacity: int = 4096):
+        """Per-launch durations (ms) of the dominant kernels recorded since the last read."""
+        buf = (C.c_float * capacity)()
+        n = C.c_int(capacity)
+        L.check(L.lib().idash_b200_timing_read(self.handle, buf, C.byref(n)))
+        return [float(buf[i]) for i in range(n.value)]
+
+    def check_device_status(self) -> None:
+        L.check(L.lib().idash_b200_check_device_status(self.handle))
+
+    def close(self):
+        if self._h:
+            L.lib().idash_b200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Model:
+    """Device-resident block-banded model."""
+
+    def __init__(self, ctx: Context, S: int, NR: int, RS: int, out_bidx, row_ptr, col, coef):
+        self.ctx = ctx
+        self.S, self.NR, self.RS = int(S), int(NR), int(RS)
+        desc, keep = L.make_desc(S, NR, RS, out_bidx, row_ptr, col, coef)
+        self.out_bidx = keep[0]
+        self._h = C.c_void_p()
+        L.check(L.lib().idash_b200_model_upload(ctx.handle, C.byref(desc), C.byref(self._h)))
+        info = L.ModelInfo()
+        L.check(L.lib().idash_b200_model_get_info(self._h, C.byref(info)))
+        self.info = info.as_dict()
+        self.n_rows = self.info["n_rows"]
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise RuntimeError("Model is freed")
+        return self._h
+
+    def free(self):
+        if self._h:
+            L.lib().idash_b200_model_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def cloud_compute_score(ctx: Context, model: Model, in_ct: np.ndarray, in_index=None, in_var=None, slot_of_row=None,
+                        out_ct: np.ndarray | None = None):
+    """PACKED host path. in_ct [n_in, 2048] uint32. Returns (out_ct [n_rows, 2048], out_bidx, out_var)."""
+    in_ct = np.ascontiguousarray(in_ct, np.uint32).reshape(-1, CT_WORDS)
+    n_in = len(in_ct)
+    idx = None if in_index is None else np.ascontiguousarray(in_index, np.uint32)
+    var = None if in_var is None else np.ascontiguousarray(in_var, np.float64)
+    if idx is not None and len(idx) != n_in:
+        raise ValueError("in_index length mismatch")
+    if var is not None and len(var) != n_in:
+        raise ValueError("in_var length mismatch")
+    n_out = model.n_rows
+    if out_ct is None:
+        out_ct = np.empty((n_out, CT_WORDS), np.uint32)
+    assert out_ct.dtype == np.uint32 and out_ct.flags.c_contiguous and out_ct.size == n_out * CT_WORDS
+    out_idx = np.zeros(n_out, np.uint32)
+    out_var = np.zeros(n_out, np.float64)
+    sor = None if slot_of_row is None else np.ascontiguousarray(slot_of_row, np.uint32)
+    cin = L.Cts(LAYOUT_PACKED, _ptr(in_ct) if n_in else None, n_in, _ptr(idx), _ptr(var))
+    cout = L.Cts(LAYOUT_PACKED, _ptr(out_ct) if n_out else None, n_out, _ptr(out_idx), _ptr(out_var))
+    L.check(L.lib().idash_b200_cloud_eval_host(ctx.handle, model.handle, C.byref(cin), C.byref(cout), _ptr(sor)))
+    return out_ct, out_idx, out_var
+
+
+def cloud_compute_score_records(ctx: Context, model: Model, in_image: np.ndarray, slot_of_row=None,
+                                out_image: np.ndarray | None = None) -> np.ndarray:
+    """RECORDS host path: in_image = the bytes of encrypted_data.bin (uint8, including the 8-byte count);
+    returns the bytes of encrypted_prediction.bin."""
+    in_image = np.ascontiguousarray(in_image, np.uint8)
+    n_in = int(in_image[:8].view("<u8")[0])
+    if in_image.size != 8 + n_in * RECORD_BYTES:
+        raise ValueError("encrypted data image has the wrong size")
+    n_out = model.n_rows
+    if out_image is None:
+        out_image = np.empty(8 + n_out * RECORD_BYTES, np.uint8)
+    out_image[:8].view("<u8")[0] = n_out
+    sor = None if slot_of_row is None else np.ascontiguousarray(slot_of_row, np.uint32)
+    cin = L.Cts(LAYOUT_RECORDS, in_image.ctypes.data + 8 if n_in else None, n_in, None, None)
+    cout = L.Cts(LAYOUT_RECORDS, out_image.ctypes.data + 8 if n_out else None, n_out, None, None)
+    L.check(L.lib().idash_b200_cloud_eval_host(ctx.handle, model.handle, C.byref(cin), C.byref(cout), _ptr(sor)))
+    return out_image
+
+
+def cloud_compute_score_device(ctx: Context, model: Model, in_ct, out_ct, in_index=None, in_var=None, out_index=None,
+                               out_var=None, slot_of_row=None, stream=None) -> None:
+    """PACKED device path on torch CUDA tensors (int32/uint32 words); enqueues on `stream` (default: torch's
+    current stream) and returns without synchronising."""
+    import torch
+    if stream is None:
+        stream = torch.cuda.current_stream().cuda_stream
+    n_in = in_ct.numel() // CT_WORDS
+    n_out = out_ct.numel() // CT_WORDS
+    dp = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+    cin = L.Cts(LAYOUT_PACKED, dp(in_ct) if n_in else None, n_in, dp(in_index), dp(in_var))
+    cout = L.Cts(LAYOUT_PACKED, dp(out_ct) if n_out else None, n_out, dp(out_index), dp(out_var))
+    L.check(L.lib().idash_b200_cloud_eval_device(ctx.handle, model.handle, C.byref(cin), C.byref(cout), dp(slot_of_row),
+                                                 C.c_void_p(stream)))
+
+
+def decrypt_predictions(ctx: Context, key, S: int, ct: np.ndarray, want_phase: bool = False):
+    """PACKED host path. key [1024] in {0,1}; ct [n, 2048]. Returns scores [n, S] float32 (and phase [n, 1024])."""
+    key = np.ascontiguousarray(key, np.int32)
+    ct = np.ascontiguousarray(ct, np.uint32).reshape(-1, CT_WORDS)
+    n = len(ct)
+    scores = np.empty((n, S), np.float32)
+    phase = np.empty((n, N), np.uint32) if want_phase else None
+    cin = L.Cts(LAYOUT_PACKED, _ptr(ct) if n else None, n, None, None)
+    L.check(L.lib().idash_b200_decrypt_host(ctx.handle, _ptr(key), S, C.byref(cin), _ptr(scores), _ptr(phase)))
+    return (scores, phase) if want_phase else scores
+
+
+def decrypt_predictions_records(ctx: Context, key, S: int, image: np.ndarray, want_phase: bool = False):
+    """RECORDS host path on the bytes of encrypted_prediction.bin. Returns (index [n], scores [n, S][, phase])."""
+    key = np.ascontiguousarray(key, np.int32)
+    image = np.ascontiguousarray(image, np.uint8)
+    n = int(image[:8].view("<u8")[0])
+    if image.size != 8 + n * RECORD_BYTES:
+        raise ValueError("encrypted prediction image has the wrong size")
+    scores = np.empty((n, S), np.float32)
+    phase = np.empty((n, N), np.uint32) if want_phase else None
+    cin = L.Cts(LAYOUT_RECORDS, image.ctypes.data + 8 if n else None, n, None, None)
+    L.check(L.lib().idash_b200_decrypt_host(ctx.handle, _ptr(key), S, C.byref(cin), _ptr(scores), _ptr(phase)))
+    index = np.ndarray((n,), "<u4", image, offset=8, strides=(RECORD_BYTES,)).copy() if n else np.zeros(0, np.uint32)
+    return (index, scores, phase) if want_phase else (index, scores)
+
+
+def decrypt_predictions_device(ctx: Context, key, S: int, ct, scores, phase=None, stream=None) -> None:
+    import torch
+    if stream is None:
+        stream = torch.cuda.current_stream().cuda_stream
+    key = np.ascontiguousarray(key, np.int32)
+    n = ct.numel() // CT_WORDS
+    cin = L.Cts(LAYOUT_PACKED, ct.data_ptr() if n else None, n, None, None)
+    L.check(L.lib().idash_b200_decrypt_device(ctx.handle, _ptr(key), S, C.byref(cin),
+                                              None if scores is None else scores.data_ptr(),
+                                              None if phase is None else phase.data_ptr(), C.c_void_p(stream)))
+
+
+@dataclass
+class Layout:
+    info: dict
+    groups: np.ndarray    # GROUP_DTYPE
+    entries: np.ndarray   # ENTRY_DTYPE
+    var_ptr: np.ndarray
+    var_ct: np.ndarray
+    var_w: np.ndarray
+    out_bidx: np.ndarray
+
+
+def compile_layout(S, NR, RS, out_bidx, row_ptr, col, coef) -> Layout:
+    """Runs the host-side model compiler only (no GPU) and copies the layout out as numpy arrays."""
+    lib = L.lib()
+    desc, keep = L.make_desc(S, NR, RS, out_bidx, row_ptr, col, coef)
+    h = C.c_void_p()
+    L.check(lib.idash_b200_layout_compile(C.byref(desc), C.byref(h)))
+    try:
+        info = L.ModelInfo()
+        L.check(lib.idash_b200_layout_get_info(h, C.byref(info)))
+        n = C.c_uint64()
+        gp = lib.idash_b200_layout_groups(h, C.byref(n))
+        groups = np.ctypeslib.as_array(C.cast(gp, C.POINTER(C.c_uint8)), (n.value * 64,)).view(L.GROUP_DTYPE).copy() \
+            if n.value else np.zeros(0, L.GROUP_DTYPE)
+        ep = lib.idash_b200_layout_entries(h, C.byref(n))
+        entries = np.ctypeslib.as_array(C.cast(ep, C.POINTER(C.c_uint8)), (n.value * 32,)).view(L.ENTRY_DTYPE).copy() \
+            if n.value else np.zeros(0, L.ENTRY_DTYPE)
+        n_rows = info.n_rows
+        vp = np.ctypeslib.as_array(C.cast(lib.idash_b200_layout_var_ptr(h), C.POINTER(C.c_uint64)), (n_rows + 1,)).copy()
+        nv = C.c_uint64()
+        vc_p = lib.idash_b200_layout_var_ct(h, C.byref(nv))
+        if nv.value:
+            vc = np.ctypeslib.as_array(C.cast(vc_p, C.POINTER(C.c_uint32)), (nv.value,)).copy()
+            vw = np.ctypeslib.as_array(C.cast(lib.idash_b200_layout_var_w(h), C.POINTER(C.c_double)), (nv.value,)).copy()
+        else:
+            vc, vw = np.zeros(0, np.uint32), np.zeros(0, np.float64)
+        ob = np.ctypeslib.as_array(C.cast(lib.idash_b200_layout_out_bidx(h), C.POINTER(C.c_uint32)), (n_rows,)).copy() \
+            if n_rows else np.zeros(0, np.uint32)
+        return Layout(info.as_dict(), groups, entries, vp, vc, vw, ob)
+    finally:
+        lib.idash_b200_layout_free(h)

@@ -1,0 +1,755 @@
+// libidash_b200.so -- CUDA (sm_100a) implementation of the C ABI in include/idash_b200.h.
+//
+// Kernels
+//   cloud_eval_kernel   K1: out = bias + sum coef * rot(in) mod 2^32 over the block-banded layout
+//                           (restates eval/idash.cpp:763-848 + tlwe-functions.cpp:106-176 +
+//                           toruspolynomial-functions.cpp:97-103,140-160 as one fused pass)
+//   cloud_finalize_kernel   per-row variance (tlwe-functions.cpp:175) and record headers
+//   slot_map_kernel         ciphertext index -> input slot table (EncryptedData::enc_data lookup,
+//                           eval/idash.h:162-166)
+//   decrypt_kernel      K4: phase = b - key*a (exact negacyclic, tlwe-functions.cpp:64-71 with the
+//                           integer product of multiplication.cpp:53-65) fused with the decode of
+//                           eval/idash.cpp:717-719
+// There is no CPU fallback: every entry point fails with IDASH_B200_ERR_CUDA when no device works.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "internal.h"
+
+using namespace idash_b200;
+
+#define CT_WORDS 2048u
+#define POLY_N 1024u
+#define NO_SLOT 0xFFFFFFFFu
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return set_error(IDASH_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                             __FILE__, __LINE__);                                                   \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// device-side views
+// ------------------------------------------------------------------------------------------------
+struct CtView {              // where ciphertext slot s keeps its 2048 words / variance / header
+    uint8_t *words;          // address of word 0 of slot 0 (16-byte aligned)
+    uint64_t stride;         // bytes between slots (8192 packed, 8208 records)
+    uint32_t *index;         // PACKED: index array or null. RECORDS: null (header is words - 8)
+    double *variance;        // PACKED: variance array or null. RECORDS: null (trailer is words + 8192)
+    uint32_t records;        // 1 = RECORDS layout
+    uint64_t count;
+};
+
+struct CloudParams {
+    const idash_b200_group *groups;
+    const idash_b200_entry *entries;
+    uint32_t n_groups;
+    uint32_t groups_per_cta;
+    CtView in, out;
+    const uint32_t *slot_of_ct;   // null: identity
+    uint32_t n_ct_slots;          // size of slot_of_ct (or in.count for identity)
+    const uint32_t *slot_of_row;  // null: identity
+    uint32_t S, RS;
+    int *status;
+};
+
+__device__ __forceinline__ uint4 ldg128(const void *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
+
+// streaming 128-bit store: outputs are written once and never re-read by this kernel
+__device__ __forceinline__ void stg128_stream(void *p, uint4 v) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ uint32_t lookup_slot(const CloudParams &p, uint32_t ct) {
+    if (ct >= p.n_ct_slots) return NO_SLOT;
+    return p.slot_of_ct ? __ldg(p.slot_of_ct + ct) : ct;
+}
+
+// MODE 0: no rotation anywhere in the model (NUM_REGIONS == 1)
+// MODE 1: rotations are multiples of 4 words  -> one 128-bit load, one sign for the 4 words
+// MODE 2: arbitrary rotations (e.g. REGION_SIZE = 341) -> four 32-bit loads
+// Returns X^(-shift) * P restricted to words i0..i0+3 of the polynomial starting at `poly`
+// (torusPolynomialMulByXai with a = 2N - shift, toruspolynomial-functions.cpp:140-160).
+template <int MODE>
+__device__ __forceinline__ uint4 load_rotated(const uint8_t *poly, uint32_t i0, uint32_t shift) {
+    if (MODE == 0) {
+        return ldg128(poly + 4u * i0);
+    } else if (MODE == 1) {
+        uint32_t idx = i0 + shift;
+        const bool neg = idx >= POLY_N;
+        idx &= POLY_N - 1;
+        uint4 v = ldg128(poly + 4u * idx);
+        if (neg) { v.x = 0u - v.x; v.y = 0u - v.y; v.z = 0u - v.z; v.w = 0u - v.w; }
+        return v;
+    } else {
+        uint32_t r[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t idx = i0 + k + shift;
+            const bool neg = idx >= POLY_N;
+            idx &= POLY_N - 1;
+            const uint32_t x = __ldg(reinterpret_cast<const uint32_t *>(poly) + idx);
+            r[k] = neg ? 0u - x : x;
+        }
+        return make_uint4(r[0], r[1], r[2], r[3]);
+    }
+}
+
+#define MAC4(acc, c, x)                      \
+    do {                                     \
+        (acc).x += (uint32_t) (c) * (x).x;   \
+        (acc).y += (uint32_t) (c) * (x).y;   \
+        (acc).z += (uint32_t) (c) * (x).z;   \
+        (acc).w += (uint32_t) (c) * (x).w;   \
+    } while (0)
+
+// One CTA = 128 threads = one 512-word slice of the 2048-word ciphertext axis, walking
+// `groups_per_cta` consecutive groups (consecutive target SNPs, whose tag windows overlap, so the
+// re-read input words hit L1/L2). Each thread owns 4 consecutive words (128-bit accesses) and the
+// 6 x 4 int32 accumulators of the group's rows.
+template <int MODE>
+__global__ void __launch_bounds__(128) cloud_eval_kernel(const CloudParams p) {
+    const uint32_t slice = blockIdx.x & 3u;
+    const uint32_t chunk = blockIdx.x >> 2;
+    const uint32_t w0 = slice * 512u + threadIdx.x * 4u;   // first word of this thread inside a ct
+    const uint32_t poly_off = w0 & POLY_N;                  // 0: polynomial a, 1024: polynomial b
+    const uint32_t i0 = w0 & (POLY_N - 1);
+    const bool is_b = poly_off != 0;
+
+    uint32_t g = chunk * p.groups_per_cta;
+    const uint32_t g_end = min(p.n_groups, g + p.groups_per_cta);
+    for (; g < g_end; ++g) {
+        const uint4 *gp = reinterpret_cast<const uint4 *>(p.groups + g);
+        const uint4 g0 = __ldg(gp);   // entry_begin, n_a, n_ab, n_b
+        uint4 acc[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) acc[r] = make_uint4(0, 0, 0, 0);
+
+        const idash_b200_entry *ep = p.entries + g0.x;
+        // ---- entries used only by target A: rows 0..2
+#pragma unroll 2
+        for (uint32_t k = 0; k < g0.y; ++k, ++ep) {
+            const uint4 h = ldg128(ep);                                       // ct, shift, c0, c1
+            const uint4 t = ldg128(reinterpret_cast<const uint4 *>(ep) + 1);  // c2, c3, c4, c5
+            const uint32_t slot = lookup_slot(p, h.x);
+            if (slot == NO_SLOT) { if (threadIdx.x == 0) atomicOr(p.status, 1); continue; }
+            const uint4 x = load_rotated<MODE>(p.in.words + (uint64_t) slot * p.in.stride + 4u * poly_off, i0, h.y);
+            MAC4(acc[0], h.z, x); MAC4(acc[1], h.w, x); MAC4(acc[2], t.x, x);
+        }
+        // ---- entries shared by A and B: rows 0..5
+#pragma unroll 2
+        for (uint32_t k = 0; k < g0.z; ++k, ++ep) {
+            const uint4 h = ldg128(ep);
+            const uint4 t = ldg128(reinterpret_cast<const uint4 *>(ep) + 1);
+            const uint32_t slot = lookup_slot(p, h.x);
+            if (slot == NO_SLOT) { if (threadIdx.x == 0) atomicOr(p.status, 1); continue; }
+            const uint4 x = load_rotated<MODE>(p.in.words + (uint64_t) slot * p.in.stride + 4u * poly_off, i0, h.y);
+            MAC4(acc[0], h.z, x); MAC4(acc[1], h.w, x); MAC4(acc[2], t.x, x);
+            MAC4(acc[3], t.y, x); MAC4(acc[4], t.z, x); MAC4(acc[5], t.w, x);
+        }
+        // ---- entries used only by target B: rows 3..5
+#pragma unroll 2
+        for (uint32_t k = 0; k < g0.w; ++k, ++ep) {
+            const uint4 h = ldg128(ep);
+            const uint4 t = ldg128(reinterpret_cast<const uint4 *>(ep) + 1);
+            const uint32_t slot = lookup_slot(p, h.x);
+            if (slot == NO_SLOT) { if (threadIdx.x == 0) atomicOr(p.status, 1); continue; }
+            const uint4 x = load_rotated<MODE>(p.in.words + (uint64_t) slot * p.in.stride + 4u * poly_off, i0, h.y);
+            MAC4(acc[3], t.y, x); MAC4(acc[4], t.z, x); MAC4(acc[5], t.w, x);
+        }
+
+        // ---- epilogue: bias on b[0..S) (idash.cpp:805-810), b[RS..N) = 0 (idash.cpp:839-841), store
+        const uint4 rows03 = __ldg(gp + 1);               // row[0..3]
+        const uint4 rows45_b01 = __ldg(gp + 2);           // row[4], row[5], bias[0], bias[1]
+        const uint4 b25 = __ldg(gp + 3);                  // bias[2..5]
+        const uint32_t rows[6] = {rows03.x, rows03.y, rows03.z, rows03.w, rows45_b01.x, rows45_b01.y};
+        const uint32_t bias[6] = {rows45_b01.z, rows45_b01.w, b25.x, b25.y, b25.z, b25.w};
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            if (rows[r] == IDASH_B200_NO_ROW) continue;
+            uint4 v = acc[r];
+            if (is_b) {
+                const uint32_t sb = bias[r] * (uint32_t) IDASH_B200_ONE_IN_T32;
+                v.x = (i0 + 0 >= p.RS) ? 0u : v.x + ((i0 + 0 < p.S) ? sb : 0u);
+                v.y = (i0 + 1 >= p.RS) ? 0u : v.y + ((i0 + 1 < p.S) ? sb : 0u);
+                v.z = (i0 + 2 >= p.RS) ? 0u : v.z + ((i0 + 2 < p.S) ? sb : 0u);
+                v.w = (i0 + 3 >= p.RS) ? 0u : v.w + ((i0 + 3 < p.S) ? sb : 0u);
+            }
+            const uint32_t oslot = p.slot_of_row ? __ldg(p.slot_of_row + rows[r]) : rows[r];
+            stg128_stream(p.out.words + (uint64_t) oslot * p.out.stride + 4u * w0, v);
+        }
+    }
+}
+
+// Per caller row: output variance, record header / index array.
+struct FinalizeParams {
+    uint64_t n_rows;
+    const uint64_t *var_ptr;
+    const uint32_t *var_ct;
+    const double *var_w;
+    const uint32_t *out_bidx;
+    CtView in, out;
+    const uint32_t *slot_of_ct;
+    uint32_t n_ct_slots;
+    const uint32_t *slot_of_row;
+    double default_var;
+};
+
+__global__ void cloud_finalize_kernel(const FinalizeParams p) {
+    const uint64_t r = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.n_rows) return;
+    double var = 0.;
+    for (uint64_t e = p.var_ptr[r]; e < p.var_ptr[r + 1]; ++e) {
+        const uint32_t ct = p.var_ct[e];
+        uint32_t slot = NO_SLOT;
+        if (ct < p.n_ct_slots) slot = p.slot_of_ct ? p.slot_of_ct[ct] : ct;
+        if (slot == NO_SLOT) continue;   // reported by cloud_eval_kernel
+        double vin;
+        if (p.in.records) vin = *reinterpret_cast<const double *>(p.in.words + (uint64_t) slot * p.in.stride + 8192);
+        else vin = p.in.variance ? p.in.variance[slot] : p.default_var;
+        var += p.var_w[e] * vin;
+    }
+    const uint32_t oslot = p.slot_of_row ? p.slot_of_row[r] : (uint32_t) r;
+    if (p.out.records) {
+        uint8_t *rec = p.out.words + (uint64_t) oslot * p.out.stride;
+        reinterpret_cast<uint32_t *>(rec - 8)[0] = p.out_bidx[r];
+        reinterpret_cast<int32_t *>(rec - 8)[1] = IDASH_B200_TLWE_SAMPLE_UID;
+        *reinterpret_cast<double *>(rec + 8192) = var;
+    } else {
+        if (p.out.index) p.out.index[oslot] = p.out_bidx[r];
+        if (p.out.variance) p.out.variance[oslot] = var;
+    }
+}
+
+__global__ void slot_map_kernel(CtView in, uint32_t *slot_of_ct, uint32_t n_ct_slots) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= in.count) return;
+    const uint32_t idx = in.records ? *reinterpret_cast<const uint32_t *>(in.words + i * in.stride - 8) : in.index[i];
+    if (idx < n_ct_slots) slot_of_ct[idx] = (uint32_t) i;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: exact phase + decode
+// ------------------------------------------------------------------------------------------------
+struct KeyBits { uint32_t w[32]; };   // bit i of the binary TRLWE key
+
+// One CTA (128 threads) per ciphertext; thread t owns phase coefficients j = 8t .. 8t+7.
+// ext[d + 1024] = a[d] for d >= 0, -a[d + 1024] for d < 0 (the negacyclic extension), so that
+//     phase[j] = b[j] - sum_{i : key_i = 1} ext[1024 + j - i].
+// The i loop runs in steps of 8 over a 16-word register window that slides down by one aligned
+// 8-word block per step; key bits are warp-uniform, so skipped bits cost one predicate test.
+__global__ void __launch_bounds__(128) decrypt_kernel(CtView in, uint64_t n_ct, KeyBits key, uint32_t S, float *scores, uint32_t *phase) {
+    __shared__ __align__(16) uint32_t ext[2 * POLY_N];
+    const uint32_t t = threadIdx.x;
+    for (uint64_t c = blockIdx.x; c < n_ct; c += gridDim.x) {
+        const uint8_t *a = in.words + c * in.stride;
+        const uint8_t *b = a + 4 * POLY_N;
+        for (uint32_t i = 4 * t; i < POLY_N; i += 4 * 128) {
+            const uint4 v = ldg128(a + 4 * i);
+            *reinterpret_cast<uint4 *>(ext + POLY_N + i) = v;
+            *reinterpret_cast<uint4 *>(ext + i) = make_uint4(0u - v.x, 0u - v.y, 0u - v.z, 0u - v.w);
+        }
+        __syncthreads();
+        const uint32_t j0 = 8 * t;
+        uint32_t acc[8];
+        {
+            const uint4 b0 = ldg128(b + 4 * j0), b1 = ldg128(b + 4 * j0 + 16);
+            acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
+            acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+        }
+        uint32_t W[16];   // W[8..15] = ext[base .. base+7], W[0..7] = ext[base-8 .. base-1], base = 1024 + j0 - 8q
+        {
+            const uint4 h0 = *reinterpret_cast<const uint4 *>(ext + POLY_N + j0);
+            const uint4 h1 = *reinterpret_cast<const uint4 *>(ext + POLY_N + j0 + 4);
+            W[8] = h0.x; W[9] = h0.y; W[10] = h0.z; W[11] = h0.w; W[12] = h1.x; W[13] = h1.y; W[14] = h1.z; W[15] = h1.w;
+        }
+        for (uint32_t q = 0; q < POLY_N / 8; ++q) {
+            const uint32_t base = POLY_N + j0 - 8 * q;
+            const uint4 l0 = *reinterpret_cast<const uint4 *>(ext + base - 8);
+            const uint4 l1 = *reinterpret_cast<const uint4 *>(ext + base - 4);
+            W[0] = l0.x; W[1] = l0.y; W[2] = l0.z; W[3] = l0.w; W[4] = l1.x; W[5] = l1.y; W[6] = l1.z; W[7] = l1.w;
+            const uint32_t bits = (key.w[q >> 2] >> ((q & 3u) * 8u)) & 0xFFu;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                if (bits & (1u << r)) {
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) acc[m] -= W[8 + m - r];
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < 8; ++m) W[8 + m] = W[m];
+        }
+        if (phase) {
+            uint4 *pp = reinterpret_cast<uint4 *>(phase + c * POLY_N + j0);
+            pp[0] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+            pp[1] = make_uint4(acc[4], acc[5], acc[6], acc[7]);
+        }
+        if (scores) {
+            // (float) (double(int32) / 2^32): one rounding of a 32-bit integer to 24 bits, then an exact
+            // power-of-two scale -- identical to idash.cpp:718 + numeric-functions.cpp:36-38
+#pragma unroll
+            for (int m = 0; m < 8; ++m)
+                if (j0 + m < S) scores[c * S + j0 + m] = __int2float_rn((int32_t) acc[m]) * 2.3283064365386963e-10f;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return IDASH_B200_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        CUDA_TRY(cudaMalloc(&p, bytes));
+        cap = bytes;
+        return IDASH_B200_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct idash_b200_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;     // used by the *_host entry points
+    int *d_status = nullptr;
+    int *h_status = nullptr;           // pinned
+    uint64_t launches = 0;
+    std::vector<cudaEvent_t> t_begin, t_end;   // per-launch timing of the dominant kernels (timing_enable)
+    int t_used = 0;
+    DevBuf in_buf, out_buf, slot_buf, row_slot_buf, aux_in_idx, aux_in_var, aux_out_idx, aux_out_var, scores_buf, phase_buf;
+};
+
+struct idash_b200_model {
+    idash_b200_layout *layout = nullptr;
+    int device = 0;
+    idash_b200_group *d_groups = nullptr;
+    idash_b200_entry *d_entries = nullptr;
+    uint64_t *d_var_ptr = nullptr;
+    uint32_t *d_var_ct = nullptr;
+    double *d_var_w = nullptr;
+    uint32_t *d_out_bidx = nullptr;
+};
+
+extern "C" int idash_b200_init(idash_b200_ctx **out, int device) {
+    clear_error();
+    if (!out) return set_error(IDASH_B200_ERR_INVALID, "init: null argument");
+    *out = nullptr;
+    int n = 0;
+    CUDA_TRY(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return set_error(IDASH_B200_ERR_CUDA, "init: device %d not available (%d CUDA devices)", device, n);
+    CUDA_TRY(cudaSetDevice(device));
+    idash_b200_ctx *c = new (std::nothrow) idash_b200_ctx();
+    if (!c) return set_error(IDASH_B200_ERR_NOMEM, "init: out of memory");
+    c->device = device;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaMalloc(&c->d_status, sizeof(int)));
+    CUDA_TRY(cudaMemset(c->d_status, 0, sizeof(int)));
+    CUDA_TRY(cudaMallocHost(&c->h_status, sizeof(int)));
+    *out = c;
+    return IDASH_B200_OK;
+}
+
+extern "C" int idash_b200_destroy(idash_b200_ctx *c) {
+    if (!c) return IDASH_B200_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    DevBuf *bufs[] = {&c->in_buf, &c->out_buf, &c->slot_buf, &c->row_slot_buf, &c->aux_in_idx, &c->aux_in_var,
+                      &c->aux_out_idx, &c->aux_out_var, &c->scores_buf, &c->phase_buf};
+    for (DevBuf *b : bufs) b->release();
+    for (cudaEvent_t e : c->t_begin) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->t_end) cudaEventDestroy(e);
+    if (c->d_status) cudaFree(c->d_status);
+    if (c->h_status) cudaFreeHost(c->h_status);
+    delete c;
+    return IDASH_B200_OK;
+}
+
+extern "C" int idash_b200_timing_enable(idash_b200_ctx *c, int max_launches) {
+    clear_error();
+    if (!c || max_launches < 0) return set_error(IDASH_B200_ERR_INVALID, "timing_enable: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    for (cudaEvent_t e : c->t_begin) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->t_end) cudaEventDestroy(e);
+    c->t_begin.clear(); c->t_end.clear(); c->t_used = 0;
+    for (int i = 0; i < max_launches; ++i) {
+        cudaEvent_t a, b;
+        CUDA_TRY(cudaEventCreate(&a));
+        CUDA_TRY(cudaEventCreate(&b));
+        c->t_begin.push_back(a); c->t_end.push_back(b);
+    }
+    return IDASH_B200_OK;
+}
+
+extern "C" int idash_b200_timing_read(idash_b200_ctx *c, float *ms, int *n) {
+    clear_error();
+    if (!c || !ms || !n) return set_error(IDASH_B200_ERR_INVALID, "timing_read: null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int cnt = std::min(*n, c->t_used);
+    for (int i = 0; i < cnt; ++i) {
+        CUDA_TRY(cudaEventSynchronize(c->t_end[i]));
+        CUDA_TRY(cudaEventElapsedTime(&ms[i], c->t_begin[i], c->t_end[i]));
+    }
+    *n = cnt;
+    c->t_used = 0;
+    return IDASH_B200_OK;
+}
+
+extern "C" uint64_t idash_b200_kernel_launches(const idash_b200_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int idash_b200_host_alloc(void **ptr, size_t bytes) {
+    clear_error();
+    if (!ptr) return set_error(IDASH_B200_ERR_INVALID, "host_alloc: null argument");
+    CUDA_TRY(cudaMallocHost(ptr, bytes ? bytes : 1));
+    return IDASH_B200_OK;
+}
+extern "C" int idash_b200_host_free(void *ptr) {
+    clear_error();
+    if (ptr) CUDA_TRY(cudaFreeHost(ptr));
+    return IDASH_B200_OK;
+}
+
+template <typename T>
+static int upload(T **dst, const T *src, size_t n) {
+    *dst = nullptr;
+    CUDA_TRY(cudaMalloc((void **) dst, std::max<size_t>(n, 1) * sizeof(T)));
+    if (n) CUDA_TRY(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return IDASH_B200_OK;
+}
+
+extern "C" int idash_b200_model_free(idash_b200_model *m) {
+    if (!m) return IDASH_B200_OK;
+    cudaSetDevice(m->device);
+    cudaFree(m->d_groups); cudaFree(m->d_entries); cudaFree(m->d_var_ptr); cudaFree(m->d_var_ct); cudaFree(m->d_var_w);
+    cudaFree(m->d_out_bidx);
+    idash_b200_layout_free(m->layout);
+    delete m;
+    return IDASH_B200_OK;
+}
+
+extern "C" int idash_b200_model_upload(idash_b200_ctx *c, const idash_b200_model_desc *desc, idash_b200_model **out) {
+    clear_error();
+    if (!c || !desc || !out) return set_error(IDASH_B200_ERR_INVALID, "model_upload: null argument");
+    *out = nullptr;
+    idash_b200_layout *L = nullptr;
+    int rc = idash_b200_layout_compile(desc, &L);
+    if (rc) return rc;
+    idash_b200_model *m = new (std::nothrow) idash_b200_model();
+    if (!m) { idash_b200_layout_free(L); return set_error(IDASH_B200_ERR_NOMEM, "model_upload: out of memory"); }
+    m->layout = L;
+    m->device = c->device;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if ((rc = upload(&m->d_groups, L->groups.data(), L->groups.size())) ||
+        (rc = upload(&m->d_entries, L->entries.data(), L->entries.size())) ||
+        (rc = upload(&m->d_var_ptr, L->var_ptr.data(), L->var_ptr.size())) ||
+        (rc = upload(&m->d_var_ct, L->var_ct.data(), L->var_ct.size())) ||
+        (rc = upload(&m->d_var_w, L->var_w.data(), L->var_w.size())) ||
+        (rc = upload(&m->d_out_bidx, L->out_bidx.data(), L->out_bidx.size()))) {
+        idash_b200_model_free(m);
+        return rc;
+    }
+    *out = m;
+    return IDASH_B200_OK;
+}
+
+extern "C" int idash_b200_model_get_info(const idash_b200_model *m, idash_b200_model_info *info) {
+    clear_error();
+    if (!m) return set_error(IDASH_B200_ERR_INVALID, "model_get_info: null argument");
+    return idash_b200_layout_get_info(m->layout, info);
+}
+
+// Builds the device view of a ciphertext array that already lives in device memory.
+static int make_view(const idash_b200_cts *a, bool is_output, CtView *v, const char *what) {
+    if (!a) return set_error(IDASH_B200_ERR_INVALID, "%s: null ciphertext array", what);
+    if (a->count && !a->data) return set_error(IDASH_B200_ERR_INVALID, "%s: null data pointer", what);
+    memset(v, 0, sizeof(*v));
+    v->count = a->count;
+    if (a->layout == IDASH_B200_LAYOUT_PACKED) {
+        if ((uintptr_t) a->data & 15u) return set_error(IDASH_B200_ERR_INVALID, "%s: packed data must be 16-byte aligned", what);
+        v->words = (uint8_t *) a->data;
+        v->stride = IDASH_B200_CT_BYTES;
+        v->index = a->index;
+        v->variance = a->variance;
+        v->records = 0;
+    } else if (a->layout == IDASH_B200_LAYOUT_RECORDS) {
+        if (a->count && ((uintptr_t) a->data & 15u) != 8u)
+            return set_error(IDASH_B200_ERR_INVALID, "%s: record stream must start at an address = 8 mod 16 (file image + 8)", what);
+        if (a->index || a->variance) return set_error(IDASH_B200_ERR_INVALID, "%s: index/variance must be NULL for the RECORDS layout", what);
+        v->words = (uint8_t *) a->data + 8;
+        v->stride = IDASH_B200_RECORD_BYTES;
+        v->records = 1;
+    } else {
+        return set_error(IDASH_B200_ERR_INVALID, "%s: unknown layout %d", what, a->layout);
+    }
+    (void) is_output;
+    return IDASH_B200_OK;
+}
+
+static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtView &in, const CtView &out,
+                        const uint32_t *d_slot_of_row, cudaStream_t st) {
+    const idash_b200_layout *L = m->layout;
+    if (out.count != L->n_rows) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: out->count (%llu) != model rows (%llu)",
+                                                 (unsigned long long) out.count, (unsigned long long) L->n_rows);
+    if (L->n_rows == 0) return IDASH_B200_OK;
+    if (in.count >= NO_SLOT) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: too many input ciphertexts");
+
+    // ciphertext index -> input slot
+    const bool has_entries = L->ct_min <= L->ct_max;
+    const uint32_t *d_slot_of_ct = nullptr;
+    uint32_t n_ct_slots = (uint32_t) in.count;
+    const bool identity = !in.records && in.index == nullptr;
+    if (!identity) {
+        n_ct_slots = has_entries ? L->ct_max + 1 : 1;
+        int rc = c->slot_buf.ensure((size_t) n_ct_slots * 4);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemsetAsync(c->slot_buf.p, 0xFF, (size_t) n_ct_slots * 4, st));
+        if (in.count) {
+            slot_map_kernel<<<(unsigned) ((in.count + 255) / 256), 256, 0, st>>>(in, (uint32_t *) c->slot_buf.p, n_ct_slots);
+            c->launches++;
+        }
+        d_slot_of_ct = (const uint32_t *) c->slot_buf.p;
+    }
+
+    CloudParams p;
+    memset(&p, 0, sizeof(p));
+    p.groups = m->d_groups;
+    p.entries = m->d_entries;
+    p.n_groups = (uint32_t) L->groups.size();
+    p.in = in;
+    p.out = out;
+    p.slot_of_ct = d_slot_of_ct;
+    p.n_ct_slots = n_ct_slots;
+    p.slot_of_row = d_slot_of_row;
+    p.S = L->S;
+    p.RS = L->RS;
+    p.status = c->d_status;
+    // enough CTAs for >= ~8 waves of 8 resident CTAs/SM, at most 16 consecutive groups per CTA
+    uint32_t gpc = 16;
+    while (gpc > 1 && (uint64_t) ((p.n_groups + gpc - 1) / gpc) * 4 < (uint64_t) c->sm_count * 64) gpc >>= 1;
+    p.groups_per_cta = gpc;
+    const unsigned grid = ((p.n_groups + gpc - 1) / gpc) * 4;
+    const int mode = (L->NR == 1) ? 0 : (L->shifts_aligned ? 1 : 2);
+    const bool timed = c->t_used < (int) c->t_begin.size();
+    if (timed) CUDA_TRY(cudaEventRecord(c->t_begin[c->t_used], st));
+    if (mode == 0) cloud_eval_kernel<0><<<grid, 128, 0, st>>>(p);
+    else if (mode == 1) cloud_eval_kernel<1><<<grid, 128, 0, st>>>(p);
+    else cloud_eval_kernel<2><<<grid, 128, 0, st>>>(p);
+    c->launches++;
+    if (timed) CUDA_TRY(cudaEventRecord(c->t_end[c->t_used++], st));
+    CUDA_TRY(cudaGetLastError());
+
+    FinalizeParams f;
+    memset(&f, 0, sizeof(f));
+    f.n_rows = L->n_rows;
+    f.var_ptr = m->d_var_ptr;
+    f.var_ct = m->d_var_ct;
+    f.var_w = m->d_var_w;
+    f.out_bidx = m->d_out_bidx;
+    f.in = in;
+    f.out = out;
+    f.slot_of_ct = d_slot_of_ct;
+    f.n_ct_slots = n_ct_slots;
+    f.slot_of_row = d_slot_of_row;
+    f.default_var = 8.8817841970012523e-16;   // alpha^2 = 2^-50 (eval/idash.cpp:20, tlwe-functions.cpp:38)
+    cloud_finalize_kernel<<<(unsigned) ((L->n_rows + 255) / 256), 256, 0, st>>>(f);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return IDASH_B200_OK;
+}
+
+extern "C" int idash_b200_cloud_eval_device(idash_b200_ctx *c, const idash_b200_model *m, const idash_b200_cts *in,
+                                            const idash_b200_cts *out, const uint32_t *slot_of_row, void *stream) {
+    clear_error();
+    if (!c || !m) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_device: null argument");
+    if (m->device != c->device) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_device: model lives on device %d, ctx on %d", m->device, c->device);
+    CUDA_TRY(cudaSetDevice(c->device));
+    CtView vin, vout;
+    int rc;
+    if ((rc = make_view(in, false, &vin, "cloud_eval_device(in)"))) return rc;
+    if ((rc = make_view(out, true, &vout, "cloud_eval_device(out)"))) return rc;
+    return launch_cloud(c, m, vin, vout, slot_of_row, (cudaStream_t) stream);
+}
+
+extern "C" int idash_b200_check_device_status(idash_b200_ctx *c) {
+    clear_error();
+    if (!c) return set_error(IDASH_B200_ERR_INVALID, "check_device_status: null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int st = 0;
+    CUDA_TRY(cudaMemcpy(&st, c->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st) {
+        CUDA_TRY(cudaMemset(c->d_status, 0, sizeof(int)));
+        return set_error(IDASH_B200_ERR_MISSING_INPUT, "cloud_eval: the model references an input ciphertext that was not supplied");
+    }
+    return IDASH_B200_OK;
+}
+
+// Stages a host ciphertext array into ctx-owned device memory and returns its device view.
+static int stage_in(idash_b200_ctx *c, const idash_b200_cts *a, DevBuf &buf, DevBuf &idx_buf, DevBuf &var_buf, CtView *v,
+                    const char *what) {
+    if (!a) return set_error(IDASH_B200_ERR_INVALID, "%s: null ciphertext array", what);
+    if (a->count && !a->data) return set_error(IDASH_B200_ERR_INVALID, "%s: null data pointer", what);
+    memset(v, 0, sizeof(*v));
+    v->count = a->count;
+    int rc;
+    if (a->layout == IDASH_B200_LAYOUT_PACKED) {
+        const size_t bytes = (size_t) a->count * IDASH_B200_CT_BYTES;
+        if ((rc = buf.ensure(bytes + 16))) return rc;
+        if (bytes) CUDA_TRY(cudaMemcpyAsync(buf.p, a->data, bytes, cudaMemcpyHostToDevice, c->stream));
+        v->words = (uint8_t *) buf.p;
+        v->stride = IDASH_B200_CT_BYTES;
+        if (a->index) {
+            if ((rc = idx_buf.ensure((size_t) a->count * 4 + 4))) return rc;
+            if (a->count) CUDA_TRY(cudaMemcpyAsync(idx_buf.p, a->index, (size_t) a->count * 4, cudaMemcpyHostToDevice, c->stream));
+            v->index = (uint32_t *) idx_buf.p;
+        }
+        if (a->variance) {
+            if ((rc = var_buf.ensure((size_t) a->count * 8 + 8))) return rc;
+            if (a->count) CUDA_TRY(cudaMemcpyAsync(var_buf.p, a->variance, (size_t) a->count * 8, cudaMemcpyHostToDevice, c->stream));
+            v->variance = (double *) var_buf.p;
+        }
+    } else if (a->layout == IDASH_B200_LAYOUT_RECORDS) {
+        if (a->index || a->variance) return set_error(IDASH_B200_ERR_INVALID, "%s: index/variance must be NULL for the RECORDS layout", what);
+        const size_t bytes = (size_t) a->count * IDASH_B200_RECORD_BYTES;
+        if ((rc = buf.ensure(bytes + 32))) return rc;
+        // device image starts at +8 so that the word arrays are 16-byte aligned, as in the file
+        if (bytes) CUDA_TRY(cudaMemcpyAsync((uint8_t *) buf.p + 8, a->data, bytes, cudaMemcpyHostToDevice, c->stream));
+        v->words = (uint8_t *) buf.p + 16;
+        v->stride = IDASH_B200_RECORD_BYTES;
+        v->records = 1;
+    } else {
+        return set_error(IDASH_B200_ERR_INVALID, "%s: unknown layout %d", what, a->layout);
+    }
+    return IDASH_B200_OK;
+}
+
+extern "C" int idash_b200_cloud_eval_host(idash_b200_ctx *c, const idash_b200_model *m, const idash_b200_cts *in,
+                                          const idash_b200_cts *out, const uint32_t *slot_of_row) {
+    clear_error();
+    if (!c || !m || !in || !out) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_host: null argument");
+    if (m->device != c->device) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_host: model lives on device %d, ctx on %d", m->device, c->device);
+    CUDA_TRY(cudaSetDevice(c->device));
+    const idash_b200_layout *L = m->layout;
+    if (out->count != L->n_rows) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_host: out->count (%llu) != model rows (%llu)",
+                                                  (unsigned long long) out->count, (unsigned long long) L->n_rows);
+    if (out->count && !out->data) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_host: null output data pointer");
+    int rc;
+    CtView vin, vout;
+    if ((rc = stage_in(c, in, c->in_buf, c->aux_in_idx, c->aux_in_var, &vin, "cloud_eval_host(in)"))) return rc;
+
+    memset(&vout, 0, sizeof(vout));
+    vout.count = out->count;
+    const uint32_t *d_slot_of_row = nullptr;
+    if (slot_of_row) {
+        for (uint64_t r = 0; r < out->count; ++r)
+            if (slot_of_row[r] >= out->count) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_host: slot_of_row[%llu] out of range", (unsigned long long) r);
+        if ((rc = c->row_slot_buf.ensure((size_t) out->count * 4 + 4))) return rc;
+        if (out->count) CUDA_TRY(cudaMemcpyAsync(c->row_slot_buf.p, slot_of_row, (size_t) out->count * 4, cudaMemcpyHostToDevice, c->stream));
+        d_slot_of_row = (const uint32_t *) c->row_slot_buf.p;
+    }
+    size_t out_bytes;
+    if (out->layout == IDASH_B200_LAYOUT_PACKED) {
+        out_bytes = (size_t) out->count * IDASH_B200_CT_BYTES;
+        if ((rc = c->out_buf.ensure(out_bytes + 16))) return rc;
+        vout.words = (uint8_t *) c->out_buf.p;
+        vout.stride = IDASH_B200_CT_BYTES;
+        if (out->index) { if ((rc = c->aux_out_idx.ensure((size_t) out->count * 4 + 4))) return rc; vout.index = (uint32_t *) c->aux_out_idx.p; }
+        if (out->variance) { if ((rc = c->aux_out_var.ensure((size_t) out->count * 8 + 8))) return rc; vout.variance = (double *) c->aux_out_var.p; }
+    } else if (out->layout == IDASH_B200_LAYOUT_RECORDS) {
+        if (out->index || out->variance) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_host(out): index/variance must be NULL for the RECORDS layout");
+        out_bytes = (size_t) out->count * IDASH_B200_RECORD_BYTES;
+        if ((rc = c->out_buf.ensure(out_bytes + 32))) return rc;
+        vout.words = (uint8_t *) c->out_buf.p + 16;
+        vout.stride = IDASH_B200_RECORD_BYTES;
+        vout.records = 1;
+    } else {
+        return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_host(out): unknown layout %d", out->layout);
+    }
+    if ((rc = launch_cloud(c, m, vin, vout, d_slot_of_row, c->stream))) return rc;
+    if (out->count) {
+        if (vout.records) {
+            CUDA_TRY(cudaMemcpyAsync(out->data, (uint8_t *) c->out_buf.p + 8, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(out->data, c->out_buf.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+            if (out->index) CUDA_TRY(cudaMemcpyAsync(out->index, vout.index, (size_t) out->count * 4, cudaMemcpyDeviceToHost, c->stream));
+            if (out->variance) CUDA_TRY(cudaMemcpyAsync(out->variance, vout.variance, (size_t) out->count * 8, cudaMemcpyDeviceToHost, c->stream));
+        }
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (*c->h_status) {
+        CUDA_TRY(cudaMemset(c->d_status, 0, sizeof(int)));
+        return set_error(IDASH_B200_ERR_MISSING_INPUT, "cloud_eval: the model references an input ciphertext that was not supplied");
+    }
+    return IDASH_B200_OK;
+}
+
+static int pack_key(const int32_t *key, KeyBits *kb) {
+    memset(kb, 0, sizeof(*kb));
+    for (uint32_t i = 0; i < POLY_N; ++i) {
+        if (key[i] != 0 && key[i] != 1) return set_error(IDASH_B200_ERR_INVALID, "decrypt: key coefficient %u is %d, expected a binary key", i, key[i]);
+        if (key[i]) kb->w[i >> 5] |= 1u << (i & 31);
+    }
+    return IDASH_B200_OK;
+}
+
+static int launch_decrypt(idash_b200_ctx *c, const KeyBits &kb, uint32_t S, const CtView &in, float *d_scores, uint32_t *d_phase, cudaStream_t st) {
+    if (in.count == 0) return IDASH_B200_OK;
+    const unsigned grid = (unsigned) std::min<uint64_t>(in.count, (uint64_t) c->sm_count * 16);
+    const bool timed = c->t_used < (int) c->t_begin.size();
+    if (timed) CUDA_TRY(cudaEventRecord(c->t_begin[c->t_used], st));
+    decrypt_kernel<<<grid, 128, 0, st>>>(in, in.count, kb, S, d_scores, d_phase);
+    c->launches++;
+    if (timed) CUDA_TRY(cudaEventRecord(c->t_end[c->t_used++], st));
+    CUDA_TRY(cudaGetLastError());
+    return IDASH_B200_OK;
+}
+
+extern "C" int idash_b200_decrypt_device(idash_b200_ctx *c, const int32_t *key_host, uint32_t S, const idash_b200_cts *in,
+                                         float *scores, uint32_t *phase, void *stream) {
+    clear_error();
+    if (!c || !key_host || !in) return set_error(IDASH_B200_ERR_INVALID, "decrypt_device: null argument");
+    if (S > POLY_N) return set_error(IDASH_B200_ERR_INVALID, "decrypt_device: num_samples %u > 1024", S);
+    if (phase && ((uintptr_t) phase & 15u)) return set_error(IDASH_B200_ERR_INVALID, "decrypt_device: phase must be 16-byte aligned");
+    CUDA_TRY(cudaSetDevice(c->device));
+    KeyBits kb;
+    int rc;
+    if ((rc = pack_key(key_host, &kb))) return rc;
+    CtView vin;
+    if ((rc = make_view(in, false, &vin, "decrypt_device(in)"))) return rc;
+    return launch_decrypt(c, kb, S, vin, scores, phase, (cudaStream_t) stream);
+}
+
+extern "C" int idash_b200_decrypt_host(idash_b200_ctx *c, const int32_t *key, uint32_t S, const idash_b200_cts *in,
+                                       float *scores, uint32_t *phase) {
+    clear_error();
+    if (!c || !key || !in) return set_error(IDASH_B200_ERR_INVALID, "decrypt_host: null argument");
+    if (S > POLY_N) return set_error(IDASH_B200_ERR_INVALID, "decrypt_host: num_samples %u > 1024", S);
+    CUDA_TRY(cudaSetDevice(c->device));
+    KeyBits kb;
+    int rc;
+    if ((rc = pack_key(key, &kb))) return rc;
+    CtView vin;
+    if ((rc = stage_in(c, in, c->in_buf, c->aux_in_idx, c->aux_in_var, &vin, "decrypt_host(in)"))) return rc;
+    float *d_scores = nullptr;
+    uint32_t *d_phase = nullptr;
+    const size_t sbytes = (size_t) in->count * S * sizeof(float), pbytes = (size_t) in->count * POLY_N * 4;
+    if (scores) { if ((rc = c->scores_buf.ensure(sbytes + 16))) return rc; d_scores = (float *) c->scores_buf.p; }
+    if (phase) { if ((rc = c->phase_buf.ensure(pbytes + 16))) return rc; d_phase = (uint32_t *) c->phase_buf.p; }
+    if ((rc = launch_decrypt(c, kb, S, vin, d_scores, d_phase, c->stream))) return rc;
+    if (scores && sbytes) CUDA_TRY(cudaMemcpyAsync(scores, d_scores, sbytes, cudaMemcpyDeviceToHost, c->stream));
+    if (phase && pbytes) CUDA_TRY(cudaMemcpyAsync(phase, d_phase, pbytes, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return IDASH_B200_OK;
+}

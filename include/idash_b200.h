@@ -1,0 +1,148 @@
+/* idash_b200.h -- C ABI of libidash_b200.so: the B200 (sm_100a) evaluator for the encrypted
+ * genotype-imputation path of ssmiler/idash2019_2.
+ *
+ * The reference has no plugin/FFI layer; its boundary for this path is three C++ functions of
+ * eval/idash.h compiled into the cloud / decrypt binaries:
+ *     void cloud_compute_score(EncryptedPredictions&, const EncryptedData&, const Model&,
+ *                              const IdashParams&);                     eval/idash.h:251-252
+ *     void decrypt_predictions(DecryptedPredictions&, const EncryptedPredictions&,
+ *                              const IdashKey&);                        eval/idash.h:254
+ *     void read_model(Model&, const IdashParams&, const std::string&);  eval/idash.h:229
+ * The entry points below are what new bodies of those functions bind (see INTEGRATION.md for the
+ * exact glue): plain pointers and sizes, no C++ or torch types, int return codes, never abort().
+ *
+ * Conventions
+ *   - one idash_b200_ctx per GPU (one process per GPU); a ctx is not thread-safe.
+ *   - a TRLWE ciphertext ("ct") is 2048 uint32 words: polynomial a[1024] then b[1024]
+ *     (tfhe/src/libtfhe/tlwe.cpp:42-52, k = 1, N = 1024, eval/idash.h:49-50).
+ *   - all torus arithmetic is mod 2^32; results are bit-identical to the reference.
+ *   - *_host entry points take HOST pointers (pinned recommended) and do the H2D/D2H copies;
+ *     *_device entry points take DEVICE pointers, enqueue on the given cudaStream_t and return
+ *     without synchronising.
+ */
+#ifndef IDASH_B200_H
+#define IDASH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IDASH_B200_N 1024u               /* IdashParams::N, eval/idash.h:49 */
+#define IDASH_B200_CT_WORDS 2048u        /* (k+1)*N */
+#define IDASH_B200_CT_BYTES 8192u
+#define IDASH_B200_RECORD_BYTES 8208u    /* u32 index, i32 84, 2048 words, f64 variance: eval/idash.cpp:551-552,
+                                            tfhe/src/libtfhe/tfhe_io.cpp:315-323 */
+#define IDASH_B200_TLWE_SAMPLE_UID 84    /* tfhe/src/include/tfhe_generic_streams.h:16 */
+#define IDASH_B200_CONSTANT_BIDX 0xFFFFFFFFu /* IdashParams::constant_bigIndex(), eval/idash.h:93 */
+#define IDASH_B200_ONE_IN_T32 262144     /* dtot32(1/16384), eval/idash.cpp:29-39 */
+
+enum {
+    IDASH_B200_OK = 0,
+    IDASH_B200_ERR_INVALID = -1,       /* bad argument / inconsistent model */
+    IDASH_B200_ERR_CUDA = -2,          /* CUDA runtime error (no device, launch failure, ...) */
+    IDASH_B200_ERR_MISSING_INPUT = -3, /* model references a ciphertext that was not supplied
+                                          (the reference aborts: eval/idash.h:164) */
+    IDASH_B200_ERR_NOMEM = -4
+};
+
+enum {
+    /* data = uint32[count][2048]; index / variance are separate arrays */
+    IDASH_B200_LAYOUT_PACKED = 0,
+    /* data = the record stream of encrypted_data.bin / encrypted_prediction.bin, i.e. file image + 8:
+       count records of 8208 bytes {u32 index, i32 84, u32 a[1024], u32 b[1024], f64 variance}
+       (eval/idash.cpp:540-556, 596-613). `data` itself is 8 mod 16, so the word arrays are 16-byte
+       aligned; index / variance live inside the records and the two pointers below must be NULL. */
+    IDASH_B200_LAYOUT_RECORDS = 1
+};
+
+/* A view of `count` ciphertexts (host or device memory, depending on the entry point). */
+typedef struct idash_b200_cts {
+    int32_t layout;
+    void *data;
+    uint64_t count;
+    /* PACKED only. Inputs: ciphertext index (EncryptedData key = bigIndex / NUM_REGIONS,
+       eval/idash.h:87,137) of every slot, NULL = slot i holds index i. Outputs: receives the output
+       bigIndex of every slot, may be NULL. */
+    uint32_t *index;
+    /* PACKED only. TLweSample::current_variance of every slot. Inputs: NULL = alpha^2 = 2^-50 (what
+       encrypt writes, eval/idash.cpp:20,625). Outputs: may be NULL. */
+    double *variance;
+} idash_b200_cts;
+
+/* The Model of eval/idash.h:129-134 flattened to CSR; rows in any order, out_bidx unique. */
+typedef struct idash_b200_model_desc {
+    uint32_t num_samples;   /* IdashParams::NUM_SAMPLES  */
+    uint32_t num_regions;   /* IdashParams::NUM_REGIONS  */
+    uint32_t region_size;   /* IdashParams::REGION_SIZE  */
+    uint64_t n_rows;        /* output features            */
+    const uint32_t *out_bidx; /* [n_rows] output bigIndex */
+    const uint64_t *row_ptr;  /* [n_rows+1]               */
+    const uint32_t *col;      /* [nnz] input bigIndex or IDASH_B200_CONSTANT_BIDX */
+    const int32_t *coef;      /* [nnz]                    */
+} idash_b200_model_desc;
+
+typedef struct idash_b200_model_info {
+    uint64_t n_rows, nnz;
+    uint64_t n_groups;        /* device row groups (two target SNPs x three variants each) */
+    uint64_t n_entries;       /* distinct (ciphertext, rotation) pairs summed over groups */
+    uint32_t ct_min, ct_max;  /* range of input ciphertext indices the model touches (ct_min > ct_max: none) */
+    uint32_t max_entries_per_group;
+    uint32_t shifts_aligned;  /* 1 if every rotation is a multiple of 4 words (128-bit path) */
+    uint64_t device_bytes;    /* size of the device-resident layout */
+} idash_b200_model_info;
+
+typedef struct idash_b200_ctx idash_b200_ctx;
+typedef struct idash_b200_model idash_b200_model;
+
+/* ---- context --------------------------------------------------------------------------------- */
+int idash_b200_init(idash_b200_ctx **ctx, int device);
+int idash_b200_destroy(idash_b200_ctx *ctx);
+/* text of the last error on the calling thread ("" if none) */
+const char *idash_b200_last_error(void);
+/* number of kernels this ctx has launched so far */
+uint64_t idash_b200_kernel_launches(const idash_b200_ctx *ctx);
+/* Per-launch device timing of the dominant kernel (cloud_eval_kernel / decrypt_kernel): when enabled,
+ * every launch is bracketed by cudaEvents on its own stream (up to max_launches, then it stops
+ * recording). timing_read() synchronises those events and returns the durations in milliseconds in
+ * launch order; *n is in: capacity of ms[], out: launches recorded. timing_enable(ctx, 0) disables. */
+int idash_b200_timing_enable(idash_b200_ctx *ctx, int max_launches);
+int idash_b200_timing_read(idash_b200_ctx *ctx, float *ms, int *n);
+/* pinned host memory for the *_host entry points */
+int idash_b200_host_alloc(void **ptr, size_t bytes);
+int idash_b200_host_free(void *ptr);
+
+/* ---- model: replaces the per-call deep copy of Model (eval/idash.cpp:772) by a one-time compile of
+ *      the coefficient maps into a device-resident block-banded layout ---------------------------- */
+int idash_b200_model_upload(idash_b200_ctx *ctx, const idash_b200_model_desc *desc, idash_b200_model **model);
+int idash_b200_model_free(idash_b200_model *model);
+int idash_b200_model_get_info(const idash_b200_model *model, idash_b200_model_info *info);
+
+/* ---- cloud_compute_score (eval/idash.cpp:763-848) --------------------------------------------
+ * out->count must equal the model's n_rows. Row r of the model (order of desc->out_bidx) is written
+ * to output slot slot_of_row[r], or to slot r if slot_of_row is NULL. For RECORDS output the record
+ * header {out_bidx, 84} and the variance are written too, so with the reference's record order in
+ * slot_of_row the buffer is the image of encrypted_prediction.bin (after its 8-byte count). */
+int idash_b200_cloud_eval_host(idash_b200_ctx *ctx, const idash_b200_model *model, const idash_b200_cts *in,
+                               const idash_b200_cts *out, const uint32_t *slot_of_row);
+int idash_b200_cloud_eval_device(idash_b200_ctx *ctx, const idash_b200_model *model, const idash_b200_cts *in,
+                                 const idash_b200_cts *out, const uint32_t *slot_of_row, void *cuda_stream);
+/* After a *_device call and a stream synchronise: IDASH_B200_ERR_MISSING_INPUT if a kernel met a model
+ * entry whose ciphertext was not supplied, else IDASH_B200_OK. Clears the flag. */
+int idash_b200_check_device_status(idash_b200_ctx *ctx);
+
+/* ---- decrypt_predictions (eval/idash.cpp:681-761): phase = b - key*a mod (X^1024+1, 2^32), exact;
+ *      scores[i][j] = (float)((double)(int32)phase[i][j] / 2^32) for j < num_samples ---------------
+ * key: 1024 int32 in {0,1} (TLweKey::key[0].coefs, tfhe_io.cpp:409-416). scores: [count][num_samples]
+ * floats. phase: optional [count][1024] words (NULL to skip). */
+int idash_b200_decrypt_host(idash_b200_ctx *ctx, const int32_t *key, uint32_t num_samples, const idash_b200_cts *in,
+                            float *scores, uint32_t *phase);
+int idash_b200_decrypt_device(idash_b200_ctx *ctx, const int32_t *key_host, uint32_t num_samples,
+                              const idash_b200_cts *in, float *scores, uint32_t *phase, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IDASH_B200_H */

@@ -1,0 +1,92 @@
+"""Test helpers: seeded cases, golden loading, and a numpy INTERPRETER of the device layout.
+
+The interpreter executes idash_b200_group / idash_b200_entry arrays exactly as cloud_eval_kernel is
+specified to (include/idash_b200_layout.h), so the host-side model compiler can be checked against
+the oracle on a CPU-only box.
+"""
+from __future__ import annotations
+
+from pathlib import Path
+
+import numpy as np
+
+from idash2019_2_b200 import formats, synth
+from idash2019_2_b200._lib import NO_ROW, ONE_IN_T32
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+GOLDEN_CASES = ["s1004_nr1", "s400_nr2", "s335_nr3", "s16_nr64"]
+N = 1024
+ALPHA2 = 2.0 ** -50
+
+
+def rot(poly: np.ndarray, shift: int) -> np.ndarray:
+    """X^(-shift) * poly mod X^1024 + 1 on uint32 words."""
+    if shift == 0:
+        return poly
+    out = np.empty_like(poly)
+    out[: N - shift] = poly[shift:]
+    out[N - shift:] = (0 - poly[:shift].astype(np.int64)).astype(np.uint32)
+    return out
+
+
+def interpret_layout(layout, S, RS, in_ct, in_var, slot_of_ct=None):
+    """-> (out_ct [n_rows, 2048] in caller row order, out_var [n_rows])."""
+    n_rows = layout.info["n_rows"]
+    out = np.zeros((n_rows, 2048), np.uint32)
+    seen = np.zeros(n_rows, bool)
+    for G in layout.groups:
+        acc = np.zeros((6, 2048), np.uint32)
+        e = int(G["entry_begin"])
+        for cls, cnt in ((0, int(G["n_a"])), (1, int(G["n_ab"])), (2, int(G["n_b"]))):
+            rows = {0: (0, 1, 2), 1: (0, 1, 2, 3, 4, 5), 2: (3, 4, 5)}[cls]
+            for _ in range(cnt):
+                E = layout.entries[e]
+                e += 1
+                ct = int(E["ct"])
+                slot = ct if slot_of_ct is None else slot_of_ct[ct]
+                x = np.concatenate([rot(in_ct[slot, :N], int(E["shift"])), rot(in_ct[slot, N:], int(E["shift"]))])
+                for r in range(6):
+                    c = np.uint32(int(E["coef"][r]) & 0xFFFFFFFF)
+                    if r in rows:
+                        acc[r] += c * x
+                    else:
+                        assert E["coef"][r] == 0
+        for r in range(6):
+            row = int(G["row"][r])
+            if row == NO_ROW:
+                continue
+            v = acc[r].copy()
+            sb = np.uint32((int(G["bias"][r]) * ONE_IN_T32) & 0xFFFFFFFF)
+            v[N:N + S] += sb
+            v[N + RS:] = 0
+            assert not seen[row]
+            seen[row] = True
+            out[row] = v
+    assert seen.all()
+    var = np.zeros(n_rows)
+    for r in range(n_rows):
+        for e in range(int(layout.var_ptr[r]), int(layout.var_ptr[r + 1])):
+            ct = int(layout.var_ct[e])
+            slot = ct if slot_of_ct is None else slot_of_ct[ct]
+            var[r] += layout.var_w[e] * in_var[slot]
+    return out, var
+
+
+def make_case(S, T, G, n, seed, coef_range=200, bias_range=500):
+    """Seeded synthetic problem: geometry, CSR model, random ciphertext words, 2^-50 variances."""
+    geo = synth.Geometry(S, T, G)
+    tag, tgt = synth.make_positions(T, G, seed)
+    model = synth.make_model(tag, tgt, n, seed, coef_range=coef_range, bias_range=bias_range)
+    n_in = geo.n_in_ct_used
+    cts = synth.random_ciphertexts(n_in, seed)
+    var = np.full(n_in, ALPHA2)
+    return geo, model, cts, var
+
+
+def load_golden(name):
+    d = GOLDEN / name
+    params, key, props = formats.read_key(d / "keys.bin")
+    enc = formats.read_ct_image(d / "encrypted_data.bin")
+    pred = formats.read_ct_image(d / "encrypted_prediction.bin")
+    ref = np.load(d / "ref.npz")
+    return d, params, key, enc, pred, ref

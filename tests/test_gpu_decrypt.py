@@ -1,0 +1,59 @@
+"""Parity of the CUDA decrypt/decode kernel with the exact oracle and the reference's golden output."""
+import numpy as np
+import pytest
+
+from idash2019_2_b200 import api, formats
+from oracle import pyoracle as po
+
+from helpers import GOLDEN_CASES, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("S", [1004, 1024, 400, 335, 16, 1])
+def test_decrypt_matches_exact_oracle(gpu_ctx, S):
+    rng = np.random.default_rng(S)
+    key = rng.integers(0, 2, 1024).astype(np.int32)
+    ct = rng.integers(0, 2 ** 32, size=(37, 2048), dtype=np.uint32)
+    scores, phase = api.decrypt_predictions(gpu_ctx, key, S, ct, want_phase=True)
+    ref_phase = po.phase_exact_port(key, ct)
+    assert np.array_equal(phase, ref_phase)                       # bit-exact, every coefficient
+    assert np.array_equal(scores, po.decode_port(S, ref_phase))   # decoded floats bit-equal
+
+
+@pytest.mark.parametrize("key_kind", ["zeros", "ones", "single"])
+def test_decrypt_edge_keys(gpu_ctx, key_kind):
+    rng = np.random.default_rng(1)
+    key = {"zeros": np.zeros(1024, np.int32), "ones": np.ones(1024, np.int32),
+           "single": np.eye(1, 1024, 1023, dtype=np.int32)[0]}[key_kind]
+    ct = rng.integers(0, 2 ** 32, size=(5, 2048), dtype=np.uint32)
+    _, phase = api.decrypt_predictions(gpu_ctx, key, 1004, ct, want_phase=True)
+    assert np.array_equal(phase, po.phase_exact_port(key, ct))
+
+
+def test_decrypt_rejects_non_binary_key(gpu_ctx):
+    key = np.zeros(1024, np.int32)
+    key[3] = 2
+    with pytest.raises(api.IdashB200Error):
+        api.decrypt_predictions(gpu_ctx, key, 16, np.zeros((1, 2048), np.uint32))
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_decrypt_golden_prediction_file(gpu_ctx, name):
+    """encrypted_prediction.bin of the reference -> phases equal TFHE's exact Karatsuba product, within 1 LSB of
+    the reference's FFT decrypt; decoded scores equal the reference's except where that LSB shows."""
+    d, params, key, enc, pred, ref = load_golden(name)
+    S = params.NUM_SAMPLES
+    index, scores, phase = api.decrypt_predictions_records(gpu_ctx, key, S, pred, want_phase=True)
+    order = np.argsort(index)
+    assert np.array_equal(index[order], ref["pred_index_sorted"])
+    assert np.array_equal(phase[order], ref["phase_exact"])
+    diff = (phase[order].astype(np.int64) - ref["phase_fft"].astype(np.int64) + 2 ** 31) % 2 ** 32 - 2 ** 31
+    assert np.abs(diff).max() <= 1
+    assert np.array_equal(scores[order], po.decode_port(S, ref["phase_exact"]))
+    assert np.abs(scores[order] - ref["scores"]).max() <= 2.0 ** -32 * 1.0001
+
+
+def test_decrypt_empty(gpu_ctx):
+    s = api.decrypt_predictions(gpu_ctx, np.zeros(1024, np.int32), 16, np.zeros((0, 2048), np.uint32))
+    assert s.shape == (0, 16)
