@@ -18,8 +18,8 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib as L
-from ._lib import (CONSTANT_BIDX, CT_BYTES, CT_WORDS, LAYOUT_PACKED, LAYOUT_RECORDS, N, RECORD_BYTES,  # noqa: F401
-                   IdashB200Error)
+from ._lib import (CONSTANT_BIDX, CT_BYTES, CT_WORDS, KERNEL_AUTO, KERNEL_IMAD, KERNEL_TENSOR,  # noqa: F401
+                   LAYOUT_PACKED, LAYOUT_RECORDS, N, RECORD_BYTES, IdashB200Error)
 
 
 class Context:
@@ -36,6 +36,13 @@ class Context:
 
     def kernel_launches(self) -> int:
         return int(L.lib().idash_b200_kernel_launches(self.handle))
+
+    def set_kernel(self, which: int) -> None:
+        """KERNEL_AUTO / KERNEL_IMAD / KERNEL_TENSOR (idash_b200_set_kernel)."""
+        L.check(L.lib().idash_b200_set_kernel(self.handle, int(which)))
+
+    def last_kernel(self) -> int:
+        return int(L.lib().idash_b200_last_kernel(self.handle))
 
     def timing_enable(self, max_launches: int) -> None:
         L.check(L.lib().idash_b200_timing_enable(self.handle, int(max_launches)))
@@ -119,12 +126,14 @@ def cloud_compute_score(ctx: Context, model: Model, in_ct: np.ndarray, in_index=
     n_out = model.n_rows
     if out_ct is None:
         out_ct = np.empty((n_out, CT_WORDS), np.uint32)
-    assert out_ct.dtype == np.uint32 and out_ct.flags.c_contiguous and out_ct.size == n_out * CT_WORDS
-    out_idx = np.zeros(n_out, np.uint32)
-    out_var = np.zeros(n_out, np.float64)
+    if out_ct.dtype != np.uint32 or not out_ct.flags.c_contiguous or out_ct.size % CT_WORDS:
+        raise ValueError("out_ct must be a C-contiguous uint32 array of whole ciphertexts")
+    n_buf = out_ct.size // CT_WORDS            # the library checks it against the model's row count
+    out_idx = np.zeros(n_buf, np.uint32)
+    out_var = np.zeros(n_buf, np.float64)
     sor = None if slot_of_row is None else np.ascontiguousarray(slot_of_row, np.uint32)
     cin = L.Cts(LAYOUT_PACKED, _ptr(in_ct) if n_in else None, n_in, _ptr(idx), _ptr(var))
-    cout = L.Cts(LAYOUT_PACKED, _ptr(out_ct) if n_out else None, n_out, _ptr(out_idx), _ptr(out_var))
+    cout = L.Cts(LAYOUT_PACKED, _ptr(out_ct) if n_buf else None, n_buf, _ptr(out_idx), _ptr(out_var))
     L.check(L.lib().idash_b200_cloud_eval_host(ctx.handle, model.handle, C.byref(cin), C.byref(cout), _ptr(sor)))
     return out_ct, out_idx, out_var
 
@@ -212,6 +221,11 @@ class Layout:
     var_ct: np.ndarray
     var_w: np.ndarray
     out_bidx: np.ndarray
+    tiles: np.ndarray       # TILE_DTYPE; empty when the model is not eligible for the tensor-core kernel
+    tile_rows: np.ndarray   # [n_tiles * 64] caller row or NO_ROW
+    tile_bias: np.ndarray   # [n_tiles * 64]
+    tile_coef: np.ndarray   # uint8 coefficient images
+    tile_used: np.ndarray   # uint32 masks
 
 
 def compile_layout(S, NR, RS, out_bidx, row_ptr, col, coef) -> Layout:
@@ -241,6 +255,20 @@ def compile_layout(S, NR, RS, out_bidx, row_ptr, col, coef) -> Layout:
             vc, vw = np.zeros(0, np.uint32), np.zeros(0, np.float64)
         ob = np.ctypeslib.as_array(C.cast(lib.idash_b200_layout_out_bidx(h), C.POINTER(C.c_uint32)), (n_rows,)).copy() \
             if n_rows else np.zeros(0, np.uint32)
-        return Layout(info.as_dict(), groups, entries, vp, vc, vw, ob)
+        def arr(ptr, ctype, count, dtype):
+            if not count:
+                return np.zeros(0, dtype)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), (count,)).view(dtype).copy()
+        nt = C.c_uint64()
+        tiles = arr(lib.idash_b200_layout_tiles(h, C.byref(nt)), C.c_uint8, nt.value * 32, L.TILE_DTYPE)
+        t_rows = arr(lib.idash_b200_layout_tile_rows(h), C.c_uint32, nt.value * L.TILE_ROWS, np.uint32)
+        t_bias = arr(lib.idash_b200_layout_tile_bias(h), C.c_int32, nt.value * L.TILE_ROWS, np.int32)
+        nb = C.c_uint64()
+        cp = lib.idash_b200_layout_tile_coef(h, C.byref(nb))
+        t_coef = arr(cp, C.c_uint8, nb.value, np.uint8)
+        nu = C.c_uint64()
+        up = lib.idash_b200_layout_tile_used(h, C.byref(nu))
+        t_used = arr(up, C.c_uint32, nu.value, np.uint32)
+        return Layout(info.as_dict(), groups, entries, vp, vc, vw, ob, tiles, t_rows, t_bias, t_coef, t_used)
     finally:
         lib.idash_b200_layout_free(h)

@@ -186,6 +186,8 @@ __global__ void __launch_bounds__(128) cloud_eval_kernel(const CloudParams p) {
     }
 }
 
+#include "cloud_tc.cuh"
+
 // Per caller row: output variance, record header / index array.
 struct FinalizeParams {
     uint64_t n_rows;
@@ -324,6 +326,8 @@ struct idash_b200_ctx {
     int *d_status = nullptr;
     int *h_status = nullptr;           // pinned
     uint64_t launches = 0;
+    int kernel_choice = IDASH_B200_KERNEL_AUTO;
+    int last_kernel = 0;               // which cloud kernel the last launch used
     std::vector<cudaEvent_t> t_begin, t_end;   // per-launch timing of the dominant kernels (timing_enable)
     int t_used = 0;
     DevBuf in_buf, out_buf, slot_buf, row_slot_buf, aux_in_idx, aux_in_var, aux_out_idx, aux_out_var, scores_buf, phase_buf;
@@ -338,6 +342,11 @@ struct idash_b200_model {
     uint32_t *d_var_ct = nullptr;
     double *d_var_w = nullptr;
     uint32_t *d_out_bidx = nullptr;
+    idash_b200_tile *d_tiles = nullptr;      // tensor-core layout (null when not eligible)
+    uint32_t *d_tile_rows = nullptr;
+    int32_t *d_tile_bias = nullptr;
+    uint8_t *d_tile_coef = nullptr;
+    uint32_t *d_tile_used = nullptr;
 };
 
 extern "C" int idash_b200_init(idash_b200_ctx **out, int device) {
@@ -358,6 +367,10 @@ extern "C" int idash_b200_init(idash_b200_ctx **out, int device) {
     CUDA_TRY(cudaMalloc(&c->d_status, sizeof(int)));
     CUDA_TRY(cudaMemset(c->d_status, 0, sizeof(int)));
     CUDA_TRY(cudaMallocHost(&c->h_status, sizeof(int)));
+    const int tc_smem_max = (int) tc_smem_bytes(IDASH_B200_TILE_KMAX);
+    CUDA_TRY(cudaFuncSetAttribute(cloud_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_max));
+    CUDA_TRY(cudaFuncSetAttribute(cloud_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_max));
+    CUDA_TRY(cudaFuncSetAttribute(cloud_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_max));
     *out = c;
     return IDASH_B200_OK;
 }
@@ -409,6 +422,14 @@ extern "C" int idash_b200_timing_read(idash_b200_ctx *c, float *ms, int *n) {
 
 extern "C" uint64_t idash_b200_kernel_launches(const idash_b200_ctx *c) { return c ? c->launches : 0; }
 
+extern "C" int idash_b200_set_kernel(idash_b200_ctx *c, int which) {
+    clear_error();
+    if (!c || which < IDASH_B200_KERNEL_AUTO || which > IDASH_B200_KERNEL_TENSOR) return set_error(IDASH_B200_ERR_INVALID, "set_kernel: bad argument");
+    c->kernel_choice = which;
+    return IDASH_B200_OK;
+}
+extern "C" int idash_b200_last_kernel(const idash_b200_ctx *c) { return c ? c->last_kernel : 0; }
+
 extern "C" int idash_b200_host_alloc(void **ptr, size_t bytes) {
     clear_error();
     if (!ptr) return set_error(IDASH_B200_ERR_INVALID, "host_alloc: null argument");
@@ -434,6 +455,7 @@ extern "C" int idash_b200_model_free(idash_b200_model *m) {
     cudaSetDevice(m->device);
     cudaFree(m->d_groups); cudaFree(m->d_entries); cudaFree(m->d_var_ptr); cudaFree(m->d_var_ct); cudaFree(m->d_var_w);
     cudaFree(m->d_out_bidx);
+    cudaFree(m->d_tiles); cudaFree(m->d_tile_rows); cudaFree(m->d_tile_bias); cudaFree(m->d_tile_coef); cudaFree(m->d_tile_used);
     idash_b200_layout_free(m->layout);
     delete m;
     return IDASH_B200_OK;
@@ -457,6 +479,15 @@ extern "C" int idash_b200_model_upload(idash_b200_ctx *c, const idash_b200_model
         (rc = upload(&m->d_var_ct, L->var_ct.data(), L->var_ct.size())) ||
         (rc = upload(&m->d_var_w, L->var_w.data(), L->var_w.size())) ||
         (rc = upload(&m->d_out_bidx, L->out_bidx.data(), L->out_bidx.size()))) {
+        idash_b200_model_free(m);
+        return rc;
+    }
+    if (!L->tiles.empty() &&
+        ((rc = upload(&m->d_tiles, L->tiles.data(), L->tiles.size())) ||
+         (rc = upload(&m->d_tile_rows, L->tile_rows.data(), L->tile_rows.size())) ||
+         (rc = upload(&m->d_tile_bias, L->tile_bias.data(), L->tile_bias.size())) ||
+         (rc = upload(&m->d_tile_coef, L->tile_coef.data(), L->tile_coef.size())) ||
+         (rc = upload(&m->d_tile_used, L->tile_used.data(), L->tile_used.size())))) {
         idash_b200_model_free(m);
         return rc;
     }
@@ -522,30 +553,55 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
         d_slot_of_ct = (const uint32_t *) c->slot_buf.p;
     }
 
-    CloudParams p;
-    memset(&p, 0, sizeof(p));
-    p.groups = m->d_groups;
-    p.entries = m->d_entries;
-    p.n_groups = (uint32_t) L->groups.size();
-    p.in = in;
-    p.out = out;
-    p.slot_of_ct = d_slot_of_ct;
-    p.n_ct_slots = n_ct_slots;
-    p.slot_of_row = d_slot_of_row;
-    p.S = L->S;
-    p.RS = L->RS;
-    p.status = c->d_status;
-    // enough CTAs for >= ~8 waves of 8 resident CTAs/SM, at most 16 consecutive groups per CTA
-    uint32_t gpc = 16;
-    while (gpc > 1 && (uint64_t) ((p.n_groups + gpc - 1) / gpc) * 4 < (uint64_t) c->sm_count * 64) gpc >>= 1;
-    p.groups_per_cta = gpc;
-    const unsigned grid = ((p.n_groups + gpc - 1) / gpc) * 4;
     const int mode = (L->NR == 1) ? 0 : (L->shifts_aligned ? 1 : 2);
+    const bool tc_ok = !L->tiles.empty();
+    if (c->kernel_choice == IDASH_B200_KERNEL_TENSOR && !tc_ok)
+        return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: the tensor-core kernel was requested but the model is not eligible "
+                                                 "(a coefficient outside int16 or a band wider than %u features)", IDASH_B200_TILE_KMAX);
+    const bool use_tc = tc_ok && c->kernel_choice != IDASH_B200_KERNEL_IMAD;
     const bool timed = c->t_used < (int) c->t_begin.size();
     if (timed) CUDA_TRY(cudaEventRecord(c->t_begin[c->t_used], st));
-    if (mode == 0) cloud_eval_kernel<0><<<grid, 128, 0, st>>>(p);
-    else if (mode == 1) cloud_eval_kernel<1><<<grid, 128, 0, st>>>(p);
-    else cloud_eval_kernel<2><<<grid, 128, 0, st>>>(p);
+    if (use_tc) {
+        TcParams p;
+        memset(&p, 0, sizeof(p));
+        p.tiles = m->d_tiles; p.tile_rows = m->d_tile_rows; p.tile_bias = m->d_tile_bias; p.tile_coef = m->d_tile_coef;
+        p.tile_used = m->d_tile_used;
+        p.n_tiles = (uint32_t) L->tiles.size();
+        p.in = in; p.out = out;
+        p.slot_of_ct = d_slot_of_ct; p.n_ct_slots = n_ct_slots; p.slot_of_row = d_slot_of_row;
+        p.S = L->S; p.NR = L->NR; p.RS = L->RS;
+        p.status = c->d_status;
+        if ((uint64_t) p.n_tiles * 16 > 0x7FFFFFFFull) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: too many tiles");
+        const unsigned grid = p.n_tiles * 16u;
+        const size_t smem = tc_smem_bytes(L->tile_kmax);
+        if (mode == 0) cloud_tc_kernel<0><<<grid, TC_THREADS, smem, st>>>(p);
+        else if (mode == 1) cloud_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(p);
+        else cloud_tc_kernel<2><<<grid, TC_THREADS, smem, st>>>(p);
+        c->last_kernel = IDASH_B200_KERNEL_TENSOR;
+    } else {
+        CloudParams p;
+        memset(&p, 0, sizeof(p));
+        p.groups = m->d_groups;
+        p.entries = m->d_entries;
+        p.n_groups = (uint32_t) L->groups.size();
+        p.in = in;
+        p.out = out;
+        p.slot_of_ct = d_slot_of_ct;
+        p.n_ct_slots = n_ct_slots;
+        p.slot_of_row = d_slot_of_row;
+        p.S = L->S;
+        p.RS = L->RS;
+        p.status = c->d_status;
+        // enough CTAs for >= ~8 waves of 8 resident CTAs/SM, at most 16 consecutive groups per CTA
+        uint32_t gpc = 16;
+        while (gpc > 1 && (uint64_t) ((p.n_groups + gpc - 1) / gpc) * 4 < (uint64_t) c->sm_count * 64) gpc >>= 1;
+        p.groups_per_cta = gpc;
+        const unsigned grid = ((p.n_groups + gpc - 1) / gpc) * 4;
+        if (mode == 0) cloud_eval_kernel<0><<<grid, 128, 0, st>>>(p);
+        else if (mode == 1) cloud_eval_kernel<1><<<grid, 128, 0, st>>>(p);
+        else cloud_eval_kernel<2><<<grid, 128, 0, st>>>(p);
+        c->last_kernel = IDASH_B200_KERNEL_IMAD;
+    }
     c->launches++;
     if (timed) CUDA_TRY(cudaEventRecord(c->t_end[c->t_used++], st));
     CUDA_TRY(cudaGetLastError());

@@ -25,6 +25,13 @@ struct idash_b200_layout {
     std::vector<uint64_t> var_ptr;    // per caller row (+1)
     std::vector<uint32_t> var_ct;
     std::vector<double> var_w;
+    // band tiles (tensor-core kernel); empty when the model is not eligible
+    std::vector<idash_b200_tile> tiles;
+    std::vector<uint32_t> tile_rows;
+    std::vector<int32_t> tile_bias;
+    std::vector<uint8_t> tile_coef;
+    std::vector<uint32_t> tile_used;
+    uint32_t tile_kmax = 0;           // widest band over all tiles
     uint32_t ct_min = 1, ct_max = 0;
     uint32_t max_entries_per_group = 0;
     bool shifts_aligned = true;

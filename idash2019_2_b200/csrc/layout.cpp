@@ -182,6 +182,61 @@ extern "C" int idash_b200_layout_compile(const idash_b200_model_desc *d, idash_b
             }
             L->max_entries_per_group = std::max<uint32_t>(L->max_entries_per_group, (uint32_t) m);
         }
+
+        // ---- band tiles for the tensor-core kernel (include/idash_b200_layout.h) ----
+        {
+            const uint32_t TN = IDASH_B200_TILE_ROWS;
+            const uint64_t n_tiles = (n_rows + TN - 1) / TN;
+            bool ok = true;
+            L->tiles.resize(n_tiles);
+            L->tile_rows.assign(n_tiles * TN, IDASH_B200_NO_ROW);
+            L->tile_bias.assign(n_tiles * TN, 0);
+            for (uint64_t t = 0; t < n_tiles && ok; ++t) {
+                const uint64_t r0 = t * TN, r1 = std::min<uint64_t>(n_rows, r0 + TN);
+                uint32_t fmin = 0xFFFFFFFFu, fmax = 0;
+                for (uint64_t i = r0; i < r1 && ok; ++i)
+                    for (const Feat &f : feats[order[i]]) {
+                        if (f.coef == 0) continue;
+                        if (f.coef < -32768 || f.coef > 32767) { ok = false; break; }
+                        fmin = std::min(fmin, f.bidx);
+                        fmax = std::max(fmax, f.bidx);
+                    }
+                if (!ok) break;
+                if (fmin > fmax) fmin = fmax = 0;   // bias-only tile
+                const uint64_t width = (uint64_t) fmax - fmin + 1;
+                const uint64_t K = (width + 31) / 32 * 32;
+                if (K > IDASH_B200_TILE_KMAX || (uint64_t) fmin + K > 0xFFFFFFFFull) { ok = false; break; }
+                idash_b200_tile &T = L->tiles[t];
+                memset(&T, 0, sizeof(T));
+                T.f_base = fmin;
+                T.K = (uint32_t) K;
+                T.b_off = L->tile_coef.size();
+                T.used_off = (uint32_t) L->tile_used.size();
+                T.n_valid = (uint32_t) (r1 - r0);
+                L->tile_kmax = std::max<uint32_t>(L->tile_kmax, T.K);
+                L->tile_coef.resize(L->tile_coef.size() + 2 * K * TN, 0);
+                L->tile_used.resize(L->tile_used.size() + K / 32, 0);
+                uint8_t *lo = L->tile_coef.data() + T.b_off, *hi = lo + K * TN;
+                uint32_t *used = L->tile_used.data() + T.used_off;
+                for (uint64_t i = r0; i < r1; ++i) {
+                    const uint32_t r = order[i], n = (uint32_t) (i - r0);
+                    L->tile_rows[t * TN + n] = r;
+                    L->tile_bias[t * TN + n] = bias[r];
+                    for (const Feat &f : feats[r]) {
+                        if (f.coef == 0) continue;
+                        const uint32_t k = f.bidx - fmin;
+                        const size_t o = (size_t) (k / 16) * (TN * 16) + (size_t) n * 16 + (k % 16);
+                        lo[o] = (uint8_t) ((uint32_t) f.coef & 0xFFu);
+                        hi[o] = (uint8_t) (((uint32_t) f.coef >> 8) & 0xFFu);   // two's complement: signed high byte
+                        used[k / 32] |= 1u << (k % 32);
+                    }
+                }
+            }
+            if (!ok) {
+                L->tiles.clear(); L->tile_rows.clear(); L->tile_bias.clear(); L->tile_coef.clear(); L->tile_used.clear();
+                L->tile_kmax = 0;
+            }
+        }
     } catch (const std::bad_alloc &) {
         delete L;
         return set_error(IDASH_B200_ERR_NOMEM, "layout_compile: out of memory");
@@ -206,7 +261,10 @@ extern "C" int idash_b200_layout_get_info(const idash_b200_layout *L, idash_b200
     info->ct_max = L->ct_max;
     info->max_entries_per_group = L->max_entries_per_group;
     info->shifts_aligned = L->shifts_aligned ? 1u : 0u;
-    info->device_bytes = L->groups.size() * sizeof(idash_b200_group) + L->entries.size() * sizeof(idash_b200_entry) +
+    info->n_tiles = L->tiles.size();
+    info->tile_kmax = L->tile_kmax;
+    info->device_bytes = L->tiles.size() * sizeof(idash_b200_tile) + L->tile_rows.size() * 4 + L->tile_bias.size() * 4 +
+                         L->tile_coef.size() + L->tile_used.size() * 4 + L->groups.size() * sizeof(idash_b200_group) + L->entries.size() * sizeof(idash_b200_entry) +
                          L->var_ptr.size() * 8 + L->var_ct.size() * 4 + L->var_w.size() * 8 + L->out_bidx.size() * 4;
     return IDASH_B200_OK;
 }
@@ -226,3 +284,17 @@ extern "C" const uint32_t *idash_b200_layout_var_ct(const idash_b200_layout *L, 
 }
 extern "C" const double *idash_b200_layout_var_w(const idash_b200_layout *L) { return L->var_w.data(); }
 extern "C" const uint32_t *idash_b200_layout_out_bidx(const idash_b200_layout *L) { return L->out_bidx.data(); }
+extern "C" const idash_b200_tile *idash_b200_layout_tiles(const idash_b200_layout *L, uint64_t *n) {
+    if (n) *n = L->tiles.size();
+    return L->tiles.data();
+}
+extern "C" const uint32_t *idash_b200_layout_tile_rows(const idash_b200_layout *L) { return L->tile_rows.data(); }
+extern "C" const int32_t *idash_b200_layout_tile_bias(const idash_b200_layout *L) { return L->tile_bias.data(); }
+extern "C" const uint8_t *idash_b200_layout_tile_coef(const idash_b200_layout *L, uint64_t *n) {
+    if (n) *n = L->tile_coef.size();
+    return L->tile_coef.data();
+}
+extern "C" const uint32_t *idash_b200_layout_tile_used(const idash_b200_layout *L, uint64_t *n) {
+    if (n) *n = L->tile_used.size();
+    return L->tile_used.data();
+}

@@ -47,6 +47,30 @@ typedef struct idash_b200_group {
  * var_out[row] = sum over e in [var_ptr[row], var_ptr[row+1]) of var_w[e] * var_in[var_ct[e]],
  * var_w = (double)(int32)(coef*coef). Stored as CSR over caller rows. */
 
+/* ---- band tiles: the operand layout of the tcgen05 (int8 tensor-core) kernel ----------------------
+ * Rows sorted by output bigIndex are cut into TILES of IDASH_B200_TILE_ROWS consecutive rows. A tile's
+ * rows only use input features (bigIndex) inside one contiguous band [f_base, f_base + K), K a multiple
+ * of 32, so the tile is a dense (rows x K) coefficient block times the (K x 2048 words) block of
+ * (rotated) input ciphertexts:  out[row][word] = sum_k coef[row][k] * X[f_base + k][word]  mod 2^32.
+ * The kernel evaluates it with u8 limbs on the tensor cores: X = sum_j 2^(8j) X_j (4 unsigned limbs,
+ * split on the fly), coef = c_lo + 256 * c_hi (c_lo unsigned, c_hi signed; needs -32768 <= coef <= 32767),
+ *     out = sum_{w=0..3} 2^(8w) * P_w,    P_w = X_w * c_lo + X_(w-1) * c_hi     (int32 accumulators).
+ * The coefficient image of a tile is stored ready to be copied into shared memory as the K-major,
+ * no-swizzle tcgen05 operand: limb i (0 = c_lo, 1 = c_hi) at b_off + i * K * TILE_ROWS, and inside a
+ * limb byte (k / 16) * (TILE_ROWS * 16) + n * 16 + (k % 16) holds limb i of coef[row n][feature f_base + k].
+ * The "Constant" (bias) is NOT part of the band: the kernel adds bias * 2^18 to b[0..S) in its epilogue. */
+#define IDASH_B200_TILE_ROWS 64u
+#define IDASH_B200_TILE_KMAX 256u   /* widest band (features) a tile may have; wider models use the IMAD kernel */
+
+typedef struct idash_b200_tile {
+    uint32_t f_base;    /* first input bigIndex of the band */
+    uint32_t K;         /* band width in features, multiple of 32, <= IDASH_B200_TILE_KMAX */
+    uint64_t b_off;     /* byte offset of the tile's coefficient image (16-byte aligned) */
+    uint32_t used_off;  /* offset (uint32 words) of the K/32-word mask of features with a non-zero coefficient */
+    uint32_t n_valid;   /* rows of the tile that exist (the last tile may be partial) */
+    uint32_t pad[2];
+} idash_b200_tile;      /* 32 bytes */
+
 typedef struct idash_b200_layout idash_b200_layout;
 
 int idash_b200_layout_compile(const idash_b200_model_desc *desc, idash_b200_layout **layout);
@@ -60,6 +84,14 @@ const uint32_t *idash_b200_layout_var_ct(const idash_b200_layout *layout, uint64
 const double *idash_b200_layout_var_w(const idash_b200_layout *layout);
 /* output bigIndex per caller row (copy of desc->out_bidx) */
 const uint32_t *idash_b200_layout_out_bidx(const idash_b200_layout *layout);
+/* band tiles. *n_tiles = 0 when the model is not eligible for the tensor-core kernel (a coefficient outside
+ * int16, or a tile whose band is wider than IDASH_B200_TILE_KMAX). tile_rows / tile_bias: [n_tiles * TILE_ROWS]
+ * caller row (IDASH_B200_NO_ROW = padding) and Constant of every tile row. */
+const idash_b200_tile *idash_b200_layout_tiles(const idash_b200_layout *layout, uint64_t *n_tiles);
+const uint32_t *idash_b200_layout_tile_rows(const idash_b200_layout *layout);
+const int32_t *idash_b200_layout_tile_bias(const idash_b200_layout *layout);
+const uint8_t *idash_b200_layout_tile_coef(const idash_b200_layout *layout, uint64_t *n_bytes);
+const uint32_t *idash_b200_layout_tile_used(const idash_b200_layout *layout, uint64_t *n_words);
 
 #ifdef __cplusplus
 }

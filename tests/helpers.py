@@ -72,6 +72,55 @@ def interpret_layout(layout, S, RS, in_ct, in_var, slot_of_ct=None):
     return out, var
 
 
+def interpret_tiles(layout, S, NR, RS, in_ct, slot_of_ct=None):
+    """Executes the band-tile layout the way cloud_tc_kernel is specified to (include/idash_b200_layout.h):
+    u8 limb planes of the rotated inputs times the (c_lo u8, c_hi s8) coefficient images, four int32
+    accumulators P_w recombined with shifts. -> out_ct [n_rows, 2048] in caller row order."""
+    from idash2019_2_b200._lib import TILE_ROWS
+    TN = TILE_ROWS
+    n_rows = layout.info["n_rows"]
+    out = np.zeros((n_rows, 2048), np.uint32)
+    seen = np.zeros(n_rows, bool)
+    n_slots = len(in_ct)
+    for t, T in enumerate(layout.tiles):
+        K, f_base, b_off = int(T["K"]), int(T["f_base"]), int(T["b_off"])
+        img = layout.tile_coef[b_off:b_off + 2 * K * TN].reshape(2, K // 16, TN, 16)
+        c_lo = img[0].transpose(1, 0, 2).reshape(TN, K).astype(np.int64)                    # [row][k] unsigned
+        c_hi = img[1].transpose(1, 0, 2).reshape(TN, K).view(np.int8).astype(np.int64)      # signed
+        used = layout.tile_used[int(T["used_off"]):int(T["used_off"]) + K // 32]
+        X = np.zeros((K, 2048), np.uint32)
+        for k in range(K):
+            f = f_base + k
+            ct, shift = f // NR, (f % NR) * RS
+            slot = (ct if ct < n_slots else None) if slot_of_ct is None else slot_of_ct.get(ct)
+            if slot is None:
+                assert not (int(used[k // 32]) >> (k % 32)) & 1, "tile uses a missing ciphertext"
+                continue
+            X[k] = np.concatenate([rot(in_ct[slot, :N], shift), rot(in_ct[slot, N:], shift)])
+        limbs = [((X >> (8 * j)) & 0xFF).astype(np.int64) for j in range(4)]               # [j][k][word]
+        acc = np.zeros((TN, 2048), np.int64)
+        for w in range(4):
+            P = c_lo @ limbs[w]
+            if w:
+                P = P + c_hi @ limbs[w - 1]
+            assert np.abs(P).max() < 2 ** 31                                                # int32 accumulators never overflow
+            acc += P << (8 * w)
+        acc = (acc & 0xFFFFFFFF).astype(np.uint32)
+        for n in range(TN):
+            row = int(layout.tile_rows[t * TN + n])
+            if row == NO_ROW:
+                assert n >= int(T["n_valid"])
+                continue
+            v = acc[n].copy()
+            v[N:N + S] += np.uint32((int(layout.tile_bias[t * TN + n]) * ONE_IN_T32) & 0xFFFFFFFF)
+            v[N + RS:] = 0
+            assert not seen[row]
+            seen[row] = True
+            out[row] = v
+    assert seen.all()
+    return out
+
+
 def make_case(S, T, G, n, seed, coef_range=200, bias_range=500):
     """Seeded synthetic problem: geometry, CSR model, random ciphertext words, 2^-50 variances."""
     geo = synth.Geometry(S, T, G)

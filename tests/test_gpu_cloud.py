@@ -10,6 +10,17 @@ from helpers import ALPHA2, GOLDEN_CASES, load_golden, make_case
 
 pytestmark = pytest.mark.gpu
 
+KERNELS = {"imad": _lib.KERNEL_IMAD, "tensor": _lib.KERNEL_TENSOR}
+
+
+@pytest.fixture(params=["imad", "tensor"])
+def kctx(request, gpu_ctx):
+    """The shared context with the cloud kernel forced to the IMAD or the tcgen05 (tensor-core) one."""
+    gpu_ctx.set_kernel(KERNELS[request.param])
+    yield gpu_ctx
+    assert gpu_ctx.last_kernel() == KERNELS[request.param]
+    gpu_ctx.set_kernel(_lib.KERNEL_AUTO)
+
 
 def _oracle(S, geo, model, cts, var, idx=None):
     idx = np.arange(len(cts), dtype=np.uint32) if idx is None else idx
@@ -18,10 +29,10 @@ def _oracle(S, geo, model, cts, var, idx=None):
 
 @pytest.mark.parametrize("S,n,cr", [(1004, 5, 200), (1024, 2, 8191), (1004, 50, 200), (513, 5, 200), (512, 5, 8191),
                                     (400, 20, 200), (335, 5, 8191), (335, 20, 200), (100, 4, 200), (16, 5, 8191), (1, 2, 50)])
-def test_cloud_packed_matches_oracle(gpu_ctx, S, n, cr):
+def test_cloud_packed_matches_oracle(kctx, S, n, cr):
     geo, model, cts, var = make_case(S, T=60, G=101, n=n, seed=S + n, coef_range=cr, bias_range=cr)
-    m = api.Model(gpu_ctx, S, geo.NR, geo.RS, model.out_bidx, model.row_ptr, model.col, model.coef)
-    out, idx, ovar = api.cloud_compute_score(gpu_ctx, m, cts, in_var=var)
+    m = api.Model(kctx, S, geo.NR, geo.RS, model.out_bidx, model.row_ptr, model.col, model.coef)
+    out, idx, ovar = api.cloud_compute_score(kctx, m, cts, in_var=var)
     ref_out, ref_var = _oracle(S, geo, model, cts, var)
     assert np.array_equal(out, ref_out)
     assert np.array_equal(ovar, ref_var)
@@ -30,21 +41,21 @@ def test_cloud_packed_matches_oracle(gpu_ctx, S, n, cr):
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
-def test_cloud_records_reproduces_reference_file(gpu_ctx, name):
+def test_cloud_records_reproduces_reference_file(kctx, name):
     """encrypted_data.bin image in, encrypted_prediction.bin image out: byte-identical to the file the
     reference `cloud` binary wrote (same record order via slot_of_row)."""
     d, params, key, enc, pred, ref = load_golden(name)
     ob, rp, col, coef = formats.read_model(params, d / "model")
-    m = api.Model(gpu_ctx, params.NUM_SAMPLES, params.NUM_REGIONS, params.REGION_SIZE, ob, rp, col, coef)
+    m = api.Model(kctx, params.NUM_SAMPLES, params.NUM_REGIONS, params.REGION_SIZE, ob, rp, col, coef)
     p_idx, _, _ = formats.image_views(pred)
     slot_of_bidx = {int(b): s for s, b in enumerate(p_idx)}
     slot_of_row = np.array([slot_of_bidx[int(b)] for b in ob], np.uint32)
-    out_img = api.cloud_compute_score_records(gpu_ctx, m, enc, slot_of_row, formats.aligned_image(len(ob)))
+    out_img = api.cloud_compute_score_records(kctx, m, enc, slot_of_row, formats.aligned_image(len(ob)))
     assert out_img.tobytes() == pred.tobytes()
     m.free()
 
 
-def test_cloud_permuted_input_slots_and_scattered_outputs(gpu_ctx):
+def test_cloud_permuted_input_slots_and_scattered_outputs(kctx):
     S = 400
     geo, model, cts, var = make_case(S, T=50, G=80, n=5, seed=21)
     rng = np.random.default_rng(3)
@@ -52,8 +63,8 @@ def test_cloud_permuted_input_slots_and_scattered_outputs(gpu_ctx):
     var = var * rng.integers(1, 5, size=len(cts))
     cts_p, var_p = np.ascontiguousarray(cts[perm]), np.ascontiguousarray(var[perm])
     slot_of_row = rng.permutation(model.n_out).astype(np.uint32)
-    m = api.Model(gpu_ctx, S, geo.NR, geo.RS, model.out_bidx, model.row_ptr, model.col, model.coef)
-    out, idx, ovar = api.cloud_compute_score(gpu_ctx, m, cts_p, in_index=perm, in_var=var_p, slot_of_row=slot_of_row)
+    m = api.Model(kctx, S, geo.NR, geo.RS, model.out_bidx, model.row_ptr, model.col, model.coef)
+    out, idx, ovar = api.cloud_compute_score(kctx, m, cts_p, in_index=perm, in_var=var_p, slot_of_row=slot_of_row)
     ref_out, ref_var = _oracle(S, geo, model, cts_p, var_p, perm)
     assert np.array_equal(out[slot_of_row], ref_out)
     assert np.array_equal(ovar[slot_of_row], ref_var)
@@ -62,6 +73,8 @@ def test_cloud_permuted_input_slots_and_scattered_outputs(gpu_ctx):
 
 
 def test_cloud_int32_range_coefficients_wrap(gpu_ctx):
+    """Coefficients outside int16 are not eligible for the tensor-core kernel: AUTO must pick the IMAD one,
+    forcing TENSOR must fail loudly."""
     S = 335
     geo, model, cts, var = make_case(S, T=30, G=40, n=5, seed=31)
     rng = np.random.default_rng(4)
@@ -71,13 +84,42 @@ def test_cloud_int32_range_coefficients_wrap(gpu_ctx):
     ref_out, ref_var = po.cloud_port(S, geo.NR, geo.RS, np.arange(len(cts), dtype=np.uint32), cts, var, model.row_ptr,
                                      model.col, coef)
     assert np.array_equal(out, ref_out) and np.array_equal(ovar, ref_var)
+    assert gpu_ctx.last_kernel() == _lib.KERNEL_IMAD and m.info["n_tiles"] == 0
+    gpu_ctx.set_kernel(_lib.KERNEL_TENSOR)
+    with pytest.raises(api.IdashB200Error):
+        api.cloud_compute_score(gpu_ctx, m, cts, in_var=var)
+    gpu_ctx.set_kernel(_lib.KERNEL_AUTO)
     m.free()
 
 
-def test_cloud_sparse_unbanded_shuffled_rows(gpu_ctx):
+def test_cloud_auto_picks_tensor_kernel_for_idash_models(gpu_ctx):
+    geo, model, cts, var = make_case(1004, T=60, G=101, n=5, seed=2)
+    m = api.Model(gpu_ctx, 1004, 1, 1024, model.out_bidx, model.row_ptr, model.col, model.coef)
+    out, _, _ = api.cloud_compute_score(gpu_ctx, m, cts, in_var=var)
+    assert gpu_ctx.last_kernel() == _lib.KERNEL_TENSOR
+    assert np.array_equal(out, _oracle(1004, geo, model, cts, var)[0])
+    m.free()
+
+
+def test_cloud_tensor_kernel_extreme_int16_coefficients_and_wide_band(kctx):
+    """+-32767/-32768 coefficients (signed high limb), all-ones words (max limb products), a 40-neighbour band."""
+    S = 1004
+    geo, model, cts, var = make_case(S, T=120, G=150, n=40, seed=9, coef_range=200, bias_range=500)
+    rng = np.random.default_rng(5)
+    coef = rng.choice(np.array([-32768, -32767, -1, 1, 255, 256, 32767, -256, -255], np.int32), size=model.nnz)
+    cts = cts.copy()
+    cts[::3] = 0xFFFFFFFF
+    m = api.Model(kctx, S, 1, 1024, model.out_bidx, model.row_ptr, model.col, coef)
+    out, _, ovar = api.cloud_compute_score(kctx, m, cts, in_var=var)
+    ref_out, ref_var = po.cloud_port(S, 1, 1024, np.arange(len(cts), dtype=np.uint32), cts, var, model.row_ptr, model.col, coef)
+    assert np.array_equal(out, ref_out) and np.array_equal(ovar, ref_var)
+    m.free()
+
+
+def test_cloud_sparse_unbanded_shuffled_rows(kctx):
     rng = np.random.default_rng(8)
     S, NR, RS = 16, 64, 16
-    n_ct = 12
+    n_ct = 4                        # 256 input features: the widest band a tensor-core tile takes
     cts = synth.random_ciphertexts(n_ct, 8)
     var = np.full(n_ct, ALPHA2)
     out_bidx = rng.permutation(np.array([0, 1, 2, 4, 5, 6, 7, 8, 40, 41, 300, 302, 303], np.uint32))
@@ -90,21 +132,21 @@ def test_cloud_sparse_unbanded_shuffled_rows(gpu_ctx):
             col.append(int(f)); coef.append(int(rng.integers(-300, 300)))
         row_ptr.append(len(col))
     row_ptr, col, coef = np.array(row_ptr, np.uint64), np.array(col, np.uint32), np.array(coef, np.int32)
-    m = api.Model(gpu_ctx, S, NR, RS, out_bidx, row_ptr, col, coef)
-    out, idx, ovar = api.cloud_compute_score(gpu_ctx, m, cts, in_var=var)
+    m = api.Model(kctx, S, NR, RS, out_bidx, row_ptr, col, coef)
+    out, idx, ovar = api.cloud_compute_score(kctx, m, cts, in_var=var)
     ref_out, ref_var = po.cloud_port(S, NR, RS, np.arange(n_ct, dtype=np.uint32), cts, var, row_ptr, col, coef)
     assert np.array_equal(out, ref_out) and np.array_equal(ovar, ref_var) and np.array_equal(idx, out_bidx)
     m.free()
 
 
-def test_cloud_missing_input_is_an_error_not_garbage(gpu_ctx):
+def test_cloud_missing_input_is_an_error_not_garbage(kctx):
     geo, model, cts, var = make_case(1004, T=20, G=30, n=5, seed=41)
-    m = api.Model(gpu_ctx, 1004, 1, 1024, model.out_bidx, model.row_ptr, model.col, model.coef)
+    m = api.Model(kctx, 1004, 1, 1024, model.out_bidx, model.row_ptr, model.col, model.coef)
     with pytest.raises(api.IdashB200Error) as e:
-        api.cloud_compute_score(gpu_ctx, m, cts[:-5], in_var=var[:-5])
+        api.cloud_compute_score(kctx, m, cts[:-5], in_var=var[:-5])
     assert e.value.code == _lib.ERR_MISSING_INPUT
     # and the context keeps working afterwards
-    out, _, _ = api.cloud_compute_score(gpu_ctx, m, cts, in_var=var)
+    out, _, _ = api.cloud_compute_score(kctx, m, cts, in_var=var)
     assert np.array_equal(out, _oracle(1004, geo, model, cts, var)[0])
     m.free()
 
@@ -122,16 +164,16 @@ def test_cloud_empty_model_and_row_count_mismatch(gpu_ctx):
     m.free()
 
 
-def test_cloud_default_variance_is_alpha_squared(gpu_ctx):
+def test_cloud_default_variance_is_alpha_squared(kctx):
     geo, model, cts, var = make_case(1004, T=10, G=6, n=3, seed=6)
-    m = api.Model(gpu_ctx, 1004, 1, 1024, model.out_bidx, model.row_ptr, model.col, model.coef)
-    _, _, v0 = api.cloud_compute_score(gpu_ctx, m, cts)
-    _, _, v1 = api.cloud_compute_score(gpu_ctx, m, cts, in_var=np.full(len(cts), ALPHA2))
+    m = api.Model(kctx, 1004, 1, 1024, model.out_bidx, model.row_ptr, model.col, model.coef)
+    _, _, v0 = api.cloud_compute_score(kctx, m, cts)
+    _, _, v1 = api.cloud_compute_score(kctx, m, cts, in_var=np.full(len(cts), ALPHA2))
     assert np.array_equal(v0, v1) and (v0 > 0).all()
     m.free()
 
 
-def test_cloud_device_path_linearity_at_scale(gpu_ctx):
+def test_cloud_device_path_linearity_at_scale(kctx):
     """Size-independent property at a larger size: eval(x + y) == eval(x) + eval(y) - eval(0) mod 2^32 (the
     map is affine: bias + linear), through the device-resident entry point on torch tensors."""
     import torch
@@ -139,7 +181,7 @@ def test_cloud_device_path_linearity_at_scale(gpu_ctx):
     geo = synth.Geometry(S, T, G)
     tag, tgt = synth.make_positions(T, G, 77)
     model = synth.make_model(tag, tgt, n, 77)
-    m = api.Model(gpu_ctx, S, 1, 1024, model.out_bidx, model.row_ptr, model.col, model.coef)
+    m = api.Model(kctx, S, 1, 1024, model.out_bidx, model.row_ptr, model.col, model.coef)
     g = torch.Generator(device="cuda").manual_seed(1)
     n_in = geo.n_in_ct_used
     x = torch.randint(-2 ** 31, 2 ** 31, (n_in, 2048), dtype=torch.int32, device="cuda", generator=g)
@@ -148,10 +190,10 @@ def test_cloud_device_path_linearity_at_scale(gpu_ctx):
     outs = []
     for inp in (x, y, x + y, z):
         o = torch.empty((model.n_out, 2048), dtype=torch.int32, device="cuda")
-        api.cloud_compute_score_device(gpu_ctx, m, inp, o)
+        api.cloud_compute_score_device(kctx, m, inp, o)
         outs.append(o)
     torch.cuda.synchronize()
-    gpu_ctx.check_device_status()
+    kctx.check_device_status()
     assert torch.equal(outs[2], outs[0] + outs[1] - outs[3])
     # spot-check 64 rows against the oracle
     rows = np.random.default_rng(0).choice(model.n_out, 64, replace=False)

@@ -51,7 +51,13 @@ def test_decrypt_golden_prediction_file(gpu_ctx, name):
     diff = (phase[order].astype(np.int64) - ref["phase_fft"].astype(np.int64) + 2 ** 31) % 2 ** 32 - 2 ** 31
     assert np.abs(diff).max() <= 1
     assert np.array_equal(scores[order], po.decode_port(S, ref["phase_exact"]))
-    assert np.abs(scores[order] - ref["scores"]).max() <= 2.0 ** -32 * 1.0001
+    # vs the reference binary's floats: identical where the FFT phase is exact, else the float of a phase 1 LSB away
+    ref_sc = ref["scores"]
+    same_phase = (diff == 0)[:, :S]
+    assert np.array_equal(scores[order][same_phase], ref_sc[same_phase])
+    lo = po.decode_port(S, (phase[order].astype(np.int64) - 1).astype(np.uint32))
+    hi = po.decode_port(S, (phase[order].astype(np.int64) + 1).astype(np.uint32))
+    assert ((ref_sc == scores[order]) | (ref_sc == lo) | (ref_sc == hi)).all()
 
 
 def test_decrypt_empty(gpu_ctx):

@@ -11,7 +11,7 @@ import pytest
 from idash2019_2_b200 import _lib, api, formats, synth
 from oracle import pyoracle as po
 
-from helpers import ALPHA2, GOLDEN_CASES, interpret_layout, load_golden, make_case
+from helpers import ALPHA2, GOLDEN_CASES, interpret_layout, interpret_tiles, load_golden, make_case
 
 ROOT = Path(__file__).resolve().parent.parent
 
@@ -49,6 +49,39 @@ def test_layout_interpreter_matches_oracle(built_lib, S, n):
         assert len(keys) == cnt
         assert (lay.entries[e0:e0 + int(G["n_a"])]["coef"][:, 3:] == 0).all()
         assert (lay.entries[e0 + int(G["n_a"] + G["n_ab"]):e0 + cnt]["coef"][:, :3] == 0).all()
+
+
+@pytest.mark.parametrize("S,n,cr", [(1004, 5, 200), (1024, 1, 32767), (512, 5, 8191), (400, 20, 200), (335, 5, 8191), (64, 3, 200),
+                                    (16, 5, 8191)])
+def test_tile_interpreter_matches_oracle(built_lib, S, n, cr):
+    """The tensor-core operand layout (band tiles, limb-split coefficients) reproduces the oracle."""
+    geo, model, cts, var = make_case(S, T=45, G=70, n=n, seed=7 * S + n, coef_range=cr, bias_range=cr)
+    lay = api.compile_layout(S, geo.NR, geo.RS, model.out_bidx, model.row_ptr, model.col, model.coef)
+    assert lay.info["n_tiles"] == (model.n_out + 63) // 64 and lay.info["tile_kmax"] % 32 == 0
+    out = interpret_tiles(lay, S, geo.NR, geo.RS, cts)
+    ref_out, _ = po.cloud_port(S, geo.NR, geo.RS, np.arange(len(cts), dtype=np.uint32), cts, var, model.row_ptr,
+                               model.col, model.coef)
+    assert np.array_equal(out, ref_out)
+    for T in lay.tiles:
+        assert T["K"] % 32 == 0 and 32 <= T["K"] <= _lib.TILE_KMAX and T["b_off"] % 16 == 0
+
+
+def test_tiles_absent_when_model_not_eligible(built_lib):
+    geo, model, cts, var = make_case(1004, T=20, G=30, n=5, seed=3)
+    coef = model.coef.copy()
+    coef[5] = 40000                                                   # outside int16
+    lay = api.compile_layout(1004, 1, 1024, model.out_bidx, model.row_ptr, model.col, coef)
+    assert lay.info["n_tiles"] == 0 and len(lay.tiles) == 0 and lay.info["n_groups"] > 0
+    lay = api.compile_layout(1004, 1, 1024, model.out_bidx, model.row_ptr, model.col, model.coef)
+    assert lay.info["n_tiles"] > 0
+    # a band wider than TILE_KMAX features
+    ob = np.array([0], np.uint32)
+    lay = api.compile_layout(1004, 1, 1024, ob, np.array([0, 2], np.uint64), np.array([0, 300], np.uint32),
+                             np.array([1, 1], np.int32))
+    assert lay.info["n_tiles"] == 0
+    lay = api.compile_layout(1004, 1, 1024, ob, np.array([0, 2], np.uint64), np.array([0, 255], np.uint32),
+                             np.array([1, -1], np.int32))
+    assert lay.info["n_tiles"] == 1 and lay.info["tile_kmax"] == 256
 
 
 def test_layout_band_is_compact_at_idash_shape(built_lib):
@@ -107,6 +140,7 @@ def test_layout_on_golden_model_files(built_lib, name):
     p_idx, p_words, p_var = formats.image_views(pred)
     order = np.argsort(p_idx)
     assert np.array_equal(out, p_words[order]) and np.array_equal(ovar, p_var[order])
+    assert np.array_equal(interpret_tiles(lay, S, NR, RS, in_words, slot_of_ct), p_words[order])
 
 
 def test_layout_rejects_bad_models(built_lib):
