@@ -53,8 +53,9 @@ def parse_args():
     ap.add_argument("--samples", type=int, default=S)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "imad", "tensor"],
-                    help="cloud kernel: auto (tensor-core when the model is eligible), imad, tensor")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "imad", "tensor", "tile", "ring"],
+                    help="cloud kernel: auto (tensor-core when the model is eligible), imad, tensor (ring if eligible, "
+                         "else tile), tile (one CTA per tile), ring (persistent)")
     return ap.parse_args()
 
 
@@ -241,7 +242,8 @@ def run_b200(args):
     n_rows = sub.n_out
     n_batches = world
     ctx = api.Context(local_rank)
-    ctx.set_kernel({"auto": api.KERNEL_AUTO, "imad": api.KERNEL_IMAD, "tensor": api.KERNEL_TENSOR}[args.kernel])
+    ctx.set_kernel({"auto": api.KERNEL_AUTO, "imad": api.KERNEL_IMAD, "tensor": api.KERNEL_TENSOR,
+                    "tile": api.KERNEL_TENSOR_TILE, "ring": api.KERNEL_TENSOR_RING}[args.kernel])
     m = api.Model(ctx, args.samples, NR, RS, sub.out_bidx, sub.row_ptr, sub.col, sub.coef)
     gen = torch.Generator(device="cuda").manual_seed(SEED + rank)
     ins = [torch.randint(-2 ** 31, 2 ** 31, (slab, 2048), dtype=torch.int32, device="cuda", generator=gen)
@@ -330,7 +332,8 @@ def run_b200(args):
                        "l2": "inputs+outputs per step (2.4 GB) exceed the 126 MB L2; no explicit flush"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None,
-                         "kernel": {api.KERNEL_IMAD: "cloud_eval_kernel", api.KERNEL_TENSOR: "cloud_tc_kernel"}.get(kernel_used, "?"), "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes,
+                         "kernel": {api.KERNEL_IMAD: "cloud_eval_kernel", api.KERNEL_TENSOR_TILE: "cloud_tc_kernel",
+                                    api.KERNEL_TENSOR_RING: "cloud_ring_kernel"}.get(kernel_used, "?"), "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes,
                          "peak_source": peak_src, "kernel_share_of_step": k_ms * n_batches / (ms_total / args.steps)},
             "e2e": {"value": slots_per_step * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,

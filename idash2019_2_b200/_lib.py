@@ -47,7 +47,7 @@ class ModelInfo(C.Structure):
     _fields_ = [("n_rows", C.c_uint64), ("nnz", C.c_uint64), ("n_groups", C.c_uint64), ("n_entries", C.c_uint64),
                 ("ct_min", C.c_uint32), ("ct_max", C.c_uint32), ("max_entries_per_group", C.c_uint32),
                 ("shifts_aligned", C.c_uint32), ("device_bytes", C.c_uint64), ("n_tiles", C.c_uint64),
-                ("tile_kmax", C.c_uint32), ("pad", C.c_uint32)]
+                ("tile_kmax", C.c_uint32), ("ring_ok", C.c_uint32)]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
@@ -57,10 +57,10 @@ ENTRY_DTYPE = np.dtype([("ct", "<u4"), ("shift", "<u4"), ("coef", "<i4", (6,))])
 GROUP_DTYPE = np.dtype([("entry_begin", "<u4"), ("n_a", "<u4"), ("n_ab", "<u4"), ("n_b", "<u4"), ("row", "<u4", (6,)),
                         ("bias", "<i4", (6,))])
 TILE_DTYPE = np.dtype([("f_base", "<u4"), ("K", "<u4"), ("b_off", "<u8"), ("used_off", "<u4"), ("n_valid", "<u4"),
-                       ("pad", "<u4", (2,))])
+                       ("flags", "<u4"), ("pad", "<u4")])
 assert ENTRY_DTYPE.itemsize == 32 and GROUP_DTYPE.itemsize == 64 and TILE_DTYPE.itemsize == 32
 TILE_ROWS, TILE_KMAX = 64, 256
-KERNEL_AUTO, KERNEL_IMAD, KERNEL_TENSOR = 0, 1, 2
+KERNEL_AUTO, KERNEL_IMAD, KERNEL_TENSOR, KERNEL_TENSOR_TILE, KERNEL_TENSOR_RING = 0, 1, 2, 3, 4
 
 # every symbol include/idash_b200.h and include/idash_b200_layout.h declare
 EXPORTS = {
@@ -98,6 +98,7 @@ EXPORTS = {
     "idash_b200_layout_tile_bias": (C.c_void_p, [C.c_void_p]),
     "idash_b200_layout_tile_coef": (C.c_void_p, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "idash_b200_layout_tile_used": (C.c_void_p, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "idash_b200_layout_feat_used": (C.c_void_p, [C.c_void_p, C.POINTER(C.c_uint64)]),
 }
 
 _lib = None

@@ -19,7 +19,7 @@ import numpy as np
 
 from . import _lib as L
 from ._lib import (CONSTANT_BIDX, CT_BYTES, CT_WORDS, KERNEL_AUTO, KERNEL_IMAD, KERNEL_TENSOR,  # noqa: F401
-                   LAYOUT_PACKED, LAYOUT_RECORDS, N, RECORD_BYTES, IdashB200Error)
+                   KERNEL_TENSOR_RING, KERNEL_TENSOR_TILE, LAYOUT_PACKED, LAYOUT_RECORDS, N, RECORD_BYTES, IdashB200Error)
 
 
 class Context:

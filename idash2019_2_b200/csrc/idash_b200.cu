@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(128) cloud_eval_kernel(const CloudParams p) {
 }
 
 #include "cloud_tc.cuh"
+#include "cloud_ring.cuh"
 
 // Per caller row: output variance, record header / index array.
 struct FinalizeParams {
@@ -347,6 +348,7 @@ struct idash_b200_model {
     int32_t *d_tile_bias = nullptr;
     uint8_t *d_tile_coef = nullptr;
     uint32_t *d_tile_used = nullptr;
+    uint32_t *d_feat_used = nullptr;         // ring variant only
 };
 
 extern "C" int idash_b200_init(idash_b200_ctx **out, int device) {
@@ -371,6 +373,8 @@ extern "C" int idash_b200_init(idash_b200_ctx **out, int device) {
     CUDA_TRY(cudaFuncSetAttribute(cloud_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_max));
     CUDA_TRY(cudaFuncSetAttribute(cloud_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_max));
     CUDA_TRY(cudaFuncSetAttribute(cloud_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_max));
+    CUDA_TRY(cudaFuncSetAttribute(cloud_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int) ring_smem_bytes(RG_MAX_SLOTS, IDASH_B200_RING_KMAX)));
     *out = c;
     return IDASH_B200_OK;
 }
@@ -424,7 +428,7 @@ extern "C" uint64_t idash_b200_kernel_launches(const idash_b200_ctx *c) { return
 
 extern "C" int idash_b200_set_kernel(idash_b200_ctx *c, int which) {
     clear_error();
-    if (!c || which < IDASH_B200_KERNEL_AUTO || which > IDASH_B200_KERNEL_TENSOR) return set_error(IDASH_B200_ERR_INVALID, "set_kernel: bad argument");
+    if (!c || which < IDASH_B200_KERNEL_AUTO || which > IDASH_B200_KERNEL_TENSOR_RING) return set_error(IDASH_B200_ERR_INVALID, "set_kernel: bad argument");
     c->kernel_choice = which;
     return IDASH_B200_OK;
 }
@@ -456,6 +460,7 @@ extern "C" int idash_b200_model_free(idash_b200_model *m) {
     cudaFree(m->d_groups); cudaFree(m->d_entries); cudaFree(m->d_var_ptr); cudaFree(m->d_var_ct); cudaFree(m->d_var_w);
     cudaFree(m->d_out_bidx);
     cudaFree(m->d_tiles); cudaFree(m->d_tile_rows); cudaFree(m->d_tile_bias); cudaFree(m->d_tile_coef); cudaFree(m->d_tile_used);
+    cudaFree(m->d_feat_used);
     idash_b200_layout_free(m->layout);
     delete m;
     return IDASH_B200_OK;
@@ -487,7 +492,8 @@ extern "C" int idash_b200_model_upload(idash_b200_ctx *c, const idash_b200_model
          (rc = upload(&m->d_tile_rows, L->tile_rows.data(), L->tile_rows.size())) ||
          (rc = upload(&m->d_tile_bias, L->tile_bias.data(), L->tile_bias.size())) ||
          (rc = upload(&m->d_tile_coef, L->tile_coef.data(), L->tile_coef.size())) ||
-         (rc = upload(&m->d_tile_used, L->tile_used.data(), L->tile_used.size())))) {
+         (rc = upload(&m->d_tile_used, L->tile_used.data(), L->tile_used.size())) ||
+         (L->ring_ok && (rc = upload(&m->d_feat_used, L->feat_used.data(), L->feat_used.size()))))) {
         idash_b200_model_free(m);
         return rc;
     }
@@ -555,13 +561,34 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
 
     const int mode = (L->NR == 1) ? 0 : (L->shifts_aligned ? 1 : 2);
     const bool tc_ok = !L->tiles.empty();
-    if (c->kernel_choice == IDASH_B200_KERNEL_TENSOR && !tc_ok)
+    if (c->kernel_choice >= IDASH_B200_KERNEL_TENSOR && !tc_ok)
         return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: the tensor-core kernel was requested but the model is not eligible "
                                                  "(a coefficient outside int16 or a band wider than %u features)", IDASH_B200_TILE_KMAX);
+    if (c->kernel_choice == IDASH_B200_KERNEL_TENSOR_RING && !L->ring_ok)
+        return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: the persistent ring kernel was requested but the model is not eligible "
+                                                 "(needs NUM_REGIONS == 1, forward-moving bands of at most %u features)", IDASH_B200_RING_KMAX);
     const bool use_tc = tc_ok && c->kernel_choice != IDASH_B200_KERNEL_IMAD;
+    const bool use_ring = use_tc && L->ring_ok && c->kernel_choice != IDASH_B200_KERNEL_TENSOR_TILE && c->sm_count >= 16;
     const bool timed = c->t_used < (int) c->t_begin.size();
     if (timed) CUDA_TRY(cudaEventRecord(c->t_begin[c->t_used], st));
-    if (use_tc) {
+    if (use_ring) {
+        RingParams p;
+        memset(&p, 0, sizeof(p));
+        p.tiles = m->d_tiles; p.tile_rows = m->d_tile_rows; p.tile_bias = m->d_tile_bias; p.tile_coef = m->d_tile_coef;
+        p.feat_used = m->d_feat_used;
+        p.n_feat_words = (uint32_t) L->feat_used.size();
+        p.n_tiles = (uint32_t) L->tiles.size();
+        p.n_chunks = (uint32_t) c->sm_count / 16u;
+        const uint32_t max_nb = L->tile_kmax / 32u;
+        p.n_slots = std::min<uint32_t>(RG_MAX_SLOTS, max_nb + 2u);
+        p.b_buf_bytes = 2u * L->tile_kmax * TC_TN;
+        p.in = in; p.out = out;
+        p.slot_of_ct = d_slot_of_ct; p.n_ct_slots = n_ct_slots; p.slot_of_row = d_slot_of_row;
+        p.S = L->S;
+        p.status = c->d_status;
+        cloud_ring_kernel<<<16u * p.n_chunks, RG_THREADS, ring_smem_bytes(p.n_slots, L->tile_kmax), st>>>(p);
+        c->last_kernel = IDASH_B200_KERNEL_TENSOR_RING;
+    } else if (use_tc) {
         TcParams p;
         memset(&p, 0, sizeof(p));
         p.tiles = m->d_tiles; p.tile_rows = m->d_tile_rows; p.tile_bias = m->d_tile_bias; p.tile_coef = m->d_tile_coef;
@@ -577,7 +604,7 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
         if (mode == 0) cloud_tc_kernel<0><<<grid, TC_THREADS, smem, st>>>(p);
         else if (mode == 1) cloud_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(p);
         else cloud_tc_kernel<2><<<grid, TC_THREADS, smem, st>>>(p);
-        c->last_kernel = IDASH_B200_KERNEL_TENSOR;
+        c->last_kernel = IDASH_B200_KERNEL_TENSOR_TILE;
     } else {
         CloudParams p;
         memset(&p, 0, sizeof(p));

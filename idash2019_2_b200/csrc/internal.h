@@ -32,6 +32,8 @@ struct idash_b200_layout {
     std::vector<uint8_t> tile_coef;
     std::vector<uint32_t> tile_used;
     uint32_t tile_kmax = 0;           // widest band over all tiles
+    bool ring_ok = false;             // eligible for the persistent ring kernel
+    std::vector<uint32_t> feat_used;  // ring_ok only: bit f = some row uses input feature f
     uint32_t ct_min = 1, ct_max = 0;
     uint32_t max_entries_per_group = 0;
     bool shifts_aligned = true;

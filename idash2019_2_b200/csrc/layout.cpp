@@ -202,7 +202,10 @@ extern "C" int idash_b200_layout_compile(const idash_b200_model_desc *d, idash_b
                         fmax = std::max(fmax, f.bidx);
                     }
                 if (!ok) break;
-                if (fmin > fmax) fmin = fmax = 0;   // bias-only tile
+                if (fmin > fmax) fmin = fmax = (t ? L->tiles[t - 1].f_base : 0);   // bias-only tile: stay in place
+                // NUM_REGIONS == 1: bands start on a 32-feature block so that consecutive tiles share whole
+                // staged blocks (persistent ring kernel); otherwise the band starts at its first feature
+                if (NR == 1) fmin &= ~31u;
                 const uint64_t width = (uint64_t) fmax - fmin + 1;
                 const uint64_t K = (width + 31) / 32 * 32;
                 if (K > IDASH_B200_TILE_KMAX || (uint64_t) fmin + K > 0xFFFFFFFFull) { ok = false; break; }
@@ -213,6 +216,11 @@ extern "C" int idash_b200_layout_compile(const idash_b200_model_desc *d, idash_b
                 T.b_off = L->tile_coef.size();
                 T.used_off = (uint32_t) L->tile_used.size();
                 T.n_valid = (uint32_t) (r1 - r0);
+                {   // bit 0 of flags: a full tile whose caller rows are consecutive integers (fast store addressing)
+                    bool contiguous = (r1 - r0 == TN);
+                    for (uint64_t i = r0; i < r1 && contiguous; ++i) contiguous = order[i] == order[r0] + (i - r0);
+                    T.flags = contiguous ? 1u : 0u;
+                }
                 L->tile_kmax = std::max<uint32_t>(L->tile_kmax, T.K);
                 L->tile_coef.resize(L->tile_coef.size() + 2 * K * TN, 0);
                 L->tile_used.resize(L->tile_used.size() + K / 32, 0);
@@ -235,6 +243,22 @@ extern "C" int idash_b200_layout_compile(const idash_b200_model_desc *d, idash_b
             if (!ok) {
                 L->tiles.clear(); L->tile_rows.clear(); L->tile_bias.clear(); L->tile_coef.clear(); L->tile_used.clear();
                 L->tile_kmax = 0;
+            }
+            // persistent ring kernel: NUM_REGIONS == 1, block-aligned bands that only move forward, at most
+            // IDASH_B200_RING_KMAX features wide; feat_used = features some row multiplies by a non-zero coefficient
+            L->ring_ok = ok && NR == 1 && !L->tiles.empty() && L->tile_kmax <= IDASH_B200_RING_KMAX;
+            uint64_t f_end = 0;
+            for (uint64_t t = 0; t < L->tiles.size() && L->ring_ok; ++t) {
+                const idash_b200_tile &T = L->tiles[t];
+                if (t && (T.f_base < L->tiles[t - 1].f_base || T.f_base + T.K < L->tiles[t - 1].f_base + L->tiles[t - 1].K))
+                    L->ring_ok = false;
+                f_end = std::max<uint64_t>(f_end, (uint64_t) T.f_base + T.K);
+            }
+            if (f_end > (1ull << 30)) L->ring_ok = false;
+            if (L->ring_ok) {
+                L->feat_used.assign(f_end / 32, 0);
+                for (const idash_b200_tile &T : L->tiles)
+                    for (uint32_t w = 0; w < T.K / 32; ++w) L->feat_used[T.f_base / 32 + w] |= L->tile_used[T.used_off + w];
             }
         }
     } catch (const std::bad_alloc &) {
@@ -262,6 +286,7 @@ extern "C" int idash_b200_layout_get_info(const idash_b200_layout *L, idash_b200
     info->max_entries_per_group = L->max_entries_per_group;
     info->shifts_aligned = L->shifts_aligned ? 1u : 0u;
     info->n_tiles = L->tiles.size();
+    info->ring_ok = L->ring_ok ? 1u : 0u;
     info->tile_kmax = L->tile_kmax;
     info->device_bytes = L->tiles.size() * sizeof(idash_b200_tile) + L->tile_rows.size() * 4 + L->tile_bias.size() * 4 +
                          L->tile_coef.size() + L->tile_used.size() * 4 + L->groups.size() * sizeof(idash_b200_group) + L->entries.size() * sizeof(idash_b200_entry) +
@@ -297,4 +322,8 @@ extern "C" const uint8_t *idash_b200_layout_tile_coef(const idash_b200_layout *L
 extern "C" const uint32_t *idash_b200_layout_tile_used(const idash_b200_layout *L, uint64_t *n) {
     if (n) *n = L->tile_used.size();
     return L->tile_used.data();
+}
+extern "C" const uint32_t *idash_b200_layout_feat_used(const idash_b200_layout *L, uint64_t *n) {
+    if (n) *n = L->ring_ok ? L->feat_used.size() : 0;
+    return L->feat_used.data();
 }

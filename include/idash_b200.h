@@ -94,7 +94,7 @@ typedef struct idash_b200_model_info {
     uint64_t device_bytes;    /* size of the device-resident layout */
     uint64_t n_tiles;         /* band tiles of the tensor-core kernel; 0 = model not eligible (see idash_b200_layout.h) */
     uint32_t tile_kmax;       /* widest tile band (features) */
-    uint32_t pad;
+    uint32_t ring_ok;         /* 1 if the persistent ring variant of the tensor-core kernel applies */
 } idash_b200_model_info;
 
 typedef struct idash_b200_ctx idash_b200_ctx;
@@ -113,11 +113,15 @@ uint64_t idash_b200_kernel_launches(const idash_b200_ctx *ctx);
  * launch order; *n is in: capacity of ms[], out: launches recorded. timing_enable(ctx, 0) disables. */
 int idash_b200_timing_enable(idash_b200_ctx *ctx, int max_launches);
 int idash_b200_timing_read(idash_b200_ctx *ctx, float *ms, int *n);
-/* Which cloud kernel idash_b200_cloud_eval_* launches. AUTO = the tensor-core kernel (tcgen05 int8 limb-split
+/* Which cloud kernel idash_b200_cloud_eval_* launches. AUTO = a tensor-core kernel (tcgen05 int8 limb-split
  * GEMM over band tiles) when the model is eligible -- every coefficient fits int16 and every 64-row tile's band
- * is at most 256 features wide -- else the IMAD kernel. Both are bit-exact; forcing TENSOR on an ineligible
- * model makes cloud_eval fail with IDASH_B200_ERR_INVALID. last_kernel() reports what the last launch used. */
-enum { IDASH_B200_KERNEL_AUTO = 0, IDASH_B200_KERNEL_IMAD = 1, IDASH_B200_KERNEL_TENSOR = 2 };
+ * is at most 256 features wide -- else the IMAD kernel. TENSOR picks between its two schedules: TENSOR_RING
+ * (persistent CTAs, shared-memory ring of staged input blocks; needs NUM_REGIONS == 1 and forward-moving bands
+ * of at most 224 features) and TENSOR_TILE (one CTA per tile x slice; any NUM_REGIONS). All are bit-exact;
+ * forcing a kernel on an ineligible model makes cloud_eval fail with IDASH_B200_ERR_INVALID. last_kernel()
+ * reports what the last launch used (IMAD, TENSOR_TILE or TENSOR_RING). */
+enum { IDASH_B200_KERNEL_AUTO = 0, IDASH_B200_KERNEL_IMAD = 1, IDASH_B200_KERNEL_TENSOR = 2,
+       IDASH_B200_KERNEL_TENSOR_TILE = 3, IDASH_B200_KERNEL_TENSOR_RING = 4 };
 int idash_b200_set_kernel(idash_b200_ctx *ctx, int which);
 int idash_b200_last_kernel(const idash_b200_ctx *ctx);
 /* pinned host memory for the *_host entry points */

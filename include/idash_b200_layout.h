@@ -61,6 +61,10 @@ typedef struct idash_b200_group {
  * The "Constant" (bias) is NOT part of the band: the kernel adds bias * 2^18 to b[0..S) in its epilogue. */
 #define IDASH_B200_TILE_ROWS 64u
 #define IDASH_B200_TILE_KMAX 256u   /* widest band (features) a tile may have; wider models use the IMAD kernel */
+/* With NUM_REGIONS == 1 every band starts on a multiple of 32 features (a "block"). When, in addition, bands
+ * only move forward from tile to tile and are at most RING_KMAX wide, the persistent kernel keeps the staged
+ * blocks of consecutive tiles in a shared-memory ring and stages every input block once per CTA. */
+#define IDASH_B200_RING_KMAX 224u
 
 typedef struct idash_b200_tile {
     uint32_t f_base;    /* first input bigIndex of the band */
@@ -68,7 +72,8 @@ typedef struct idash_b200_tile {
     uint64_t b_off;     /* byte offset of the tile's coefficient image (16-byte aligned) */
     uint32_t used_off;  /* offset (uint32 words) of the K/32-word mask of features with a non-zero coefficient */
     uint32_t n_valid;   /* rows of the tile that exist (the last tile may be partial) */
-    uint32_t pad[2];
+    uint32_t flags;     /* bit 0: full tile whose caller rows are consecutive integers starting at tile_rows[64 t] */
+    uint32_t pad;
 } idash_b200_tile;      /* 32 bytes */
 
 typedef struct idash_b200_layout idash_b200_layout;
@@ -92,6 +97,8 @@ const uint32_t *idash_b200_layout_tile_rows(const idash_b200_layout *layout);
 const int32_t *idash_b200_layout_tile_bias(const idash_b200_layout *layout);
 const uint8_t *idash_b200_layout_tile_coef(const idash_b200_layout *layout, uint64_t *n_bytes);
 const uint32_t *idash_b200_layout_tile_used(const idash_b200_layout *layout, uint64_t *n_words);
+/* ring variant: bit f of the mask = some row has a non-zero coefficient on input feature f (*n_words = 0: not eligible) */
+const uint32_t *idash_b200_layout_feat_used(const idash_b200_layout *layout, uint64_t *n_words);
 
 #ifdef __cplusplus
 }

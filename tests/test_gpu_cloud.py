@@ -10,16 +10,36 @@ from helpers import ALPHA2, GOLDEN_CASES, load_golden, make_case
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = {"imad": _lib.KERNEL_IMAD, "tensor": _lib.KERNEL_TENSOR}
+KERNELS = {"imad": _lib.KERNEL_IMAD, "tile": _lib.KERNEL_TENSOR_TILE, "ring": _lib.KERNEL_TENSOR_RING}
 
 
-@pytest.fixture(params=["imad", "tensor"])
+@pytest.fixture(params=["imad", "tile", "ring"])
 def kctx(request, gpu_ctx):
-    """The shared context with the cloud kernel forced to the IMAD or the tcgen05 (tensor-core) one."""
-    gpu_ctx.set_kernel(KERNELS[request.param])
+    """The shared context with the cloud kernel forced to the IMAD one or to one of the two tcgen05 (tensor-core)
+    schedules. Tests call _model(kctx, ...) which skips models the forced kernel cannot take."""
+    gpu_ctx.requested = KERNELS[request.param]
+    gpu_ctx.set_kernel(gpu_ctx.requested)
     yield gpu_ctx
-    assert gpu_ctx.last_kernel() == KERNELS[request.param]
     gpu_ctx.set_kernel(_lib.KERNEL_AUTO)
+    gpu_ctx.requested = None
+
+
+def _model(ctx, S, NR, RS, out_bidx, row_ptr, col, coef):
+    m = api.Model(ctx, S, NR, RS, out_bidx, row_ptr, col, coef)
+    req = getattr(ctx, "requested", None)
+    if req == _lib.KERNEL_TENSOR_RING and not m.info["ring_ok"]:
+        m.free()
+        pytest.skip("model not eligible for the persistent ring kernel (needs NUM_REGIONS == 1)")
+    if req == _lib.KERNEL_TENSOR_TILE and not m.info["n_tiles"]:
+        m.free()
+        pytest.skip("model not eligible for the tensor-core kernels")
+    return m
+
+
+def _used(ctx):
+    req = getattr(ctx, "requested", None)
+    if req is not None:
+        assert ctx.last_kernel() == req
 
 
 def _oracle(S, geo, model, cts, var, idx=None):
@@ -31,12 +51,13 @@ def _oracle(S, geo, model, cts, var, idx=None):
                                     (400, 20, 200), (335, 5, 8191), (335, 20, 200), (100, 4, 200), (16, 5, 8191), (1, 2, 50)])
 def test_cloud_packed_matches_oracle(kctx, S, n, cr):
     geo, model, cts, var = make_case(S, T=60, G=101, n=n, seed=S + n, coef_range=cr, bias_range=cr)
-    m = api.Model(kctx, S, geo.NR, geo.RS, model.out_bidx, model.row_ptr, model.col, model.coef)
+    m = _model(kctx, S, geo.NR, geo.RS, model.out_bidx, model.row_ptr, model.col, model.coef)
     out, idx, ovar = api.cloud_compute_score(kctx, m, cts, in_var=var)
     ref_out, ref_var = _oracle(S, geo, model, cts, var)
     assert np.array_equal(out, ref_out)
     assert np.array_equal(ovar, ref_var)
     assert np.array_equal(idx, model.out_bidx)
+    _used(kctx)
     m.free()
 
 
@@ -46,12 +67,13 @@ def test_cloud_records_reproduces_reference_file(kctx, name):
     reference `cloud` binary wrote (same record order via slot_of_row)."""
     d, params, key, enc, pred, ref = load_golden(name)
     ob, rp, col, coef = formats.read_model(params, d / "model")
-    m = api.Model(kctx, params.NUM_SAMPLES, params.NUM_REGIONS, params.REGION_SIZE, ob, rp, col, coef)
+    m = _model(kctx, params.NUM_SAMPLES, params.NUM_REGIONS, params.REGION_SIZE, ob, rp, col, coef)
     p_idx, _, _ = formats.image_views(pred)
     slot_of_bidx = {int(b): s for s, b in enumerate(p_idx)}
     slot_of_row = np.array([slot_of_bidx[int(b)] for b in ob], np.uint32)
     out_img = api.cloud_compute_score_records(kctx, m, enc, slot_of_row, formats.aligned_image(len(ob)))
     assert out_img.tobytes() == pred.tobytes()
+    _used(kctx)
     m.free()
 
 
@@ -63,12 +85,13 @@ def test_cloud_permuted_input_slots_and_scattered_outputs(kctx):
     var = var * rng.integers(1, 5, size=len(cts))
     cts_p, var_p = np.ascontiguousarray(cts[perm]), np.ascontiguousarray(var[perm])
     slot_of_row = rng.permutation(model.n_out).astype(np.uint32)
-    m = api.Model(kctx, S, geo.NR, geo.RS, model.out_bidx, model.row_ptr, model.col, model.coef)
+    m = _model(kctx, S, geo.NR, geo.RS, model.out_bidx, model.row_ptr, model.col, model.coef)
     out, idx, ovar = api.cloud_compute_score(kctx, m, cts_p, in_index=perm, in_var=var_p, slot_of_row=slot_of_row)
     ref_out, ref_var = _oracle(S, geo, model, cts_p, var_p, perm)
     assert np.array_equal(out[slot_of_row], ref_out)
     assert np.array_equal(ovar[slot_of_row], ref_var)
     assert np.array_equal(idx[slot_of_row], model.out_bidx)
+    _used(kctx)
     m.free()
 
 
@@ -96,7 +119,7 @@ def test_cloud_auto_picks_tensor_kernel_for_idash_models(gpu_ctx):
     geo, model, cts, var = make_case(1004, T=60, G=101, n=5, seed=2)
     m = api.Model(gpu_ctx, 1004, 1, 1024, model.out_bidx, model.row_ptr, model.col, model.coef)
     out, _, _ = api.cloud_compute_score(gpu_ctx, m, cts, in_var=var)
-    assert gpu_ctx.last_kernel() == _lib.KERNEL_TENSOR
+    assert gpu_ctx.last_kernel() == _lib.KERNEL_TENSOR_RING and m.info["ring_ok"] == 1
     assert np.array_equal(out, _oracle(1004, geo, model, cts, var)[0])
     m.free()
 
@@ -109,10 +132,11 @@ def test_cloud_tensor_kernel_extreme_int16_coefficients_and_wide_band(kctx):
     coef = rng.choice(np.array([-32768, -32767, -1, 1, 255, 256, 32767, -256, -255], np.int32), size=model.nnz)
     cts = cts.copy()
     cts[::3] = 0xFFFFFFFF
-    m = api.Model(kctx, S, 1, 1024, model.out_bidx, model.row_ptr, model.col, coef)
+    m = _model(kctx, S, 1, 1024, model.out_bidx, model.row_ptr, model.col, coef)
     out, _, ovar = api.cloud_compute_score(kctx, m, cts, in_var=var)
     ref_out, ref_var = po.cloud_port(S, 1, 1024, np.arange(len(cts), dtype=np.uint32), cts, var, model.row_ptr, model.col, coef)
     assert np.array_equal(out, ref_out) and np.array_equal(ovar, ref_var)
+    _used(kctx)
     m.free()
 
 
@@ -132,22 +156,24 @@ def test_cloud_sparse_unbanded_shuffled_rows(kctx):
             col.append(int(f)); coef.append(int(rng.integers(-300, 300)))
         row_ptr.append(len(col))
     row_ptr, col, coef = np.array(row_ptr, np.uint64), np.array(col, np.uint32), np.array(coef, np.int32)
-    m = api.Model(kctx, S, NR, RS, out_bidx, row_ptr, col, coef)
+    m = _model(kctx, S, NR, RS, out_bidx, row_ptr, col, coef)
     out, idx, ovar = api.cloud_compute_score(kctx, m, cts, in_var=var)
     ref_out, ref_var = po.cloud_port(S, NR, RS, np.arange(n_ct, dtype=np.uint32), cts, var, row_ptr, col, coef)
     assert np.array_equal(out, ref_out) and np.array_equal(ovar, ref_var) and np.array_equal(idx, out_bidx)
+    _used(kctx)
     m.free()
 
 
 def test_cloud_missing_input_is_an_error_not_garbage(kctx):
     geo, model, cts, var = make_case(1004, T=20, G=30, n=5, seed=41)
-    m = api.Model(kctx, 1004, 1, 1024, model.out_bidx, model.row_ptr, model.col, model.coef)
+    m = _model(kctx, 1004, 1, 1024, model.out_bidx, model.row_ptr, model.col, model.coef)
     with pytest.raises(api.IdashB200Error) as e:
         api.cloud_compute_score(kctx, m, cts[:-5], in_var=var[:-5])
     assert e.value.code == _lib.ERR_MISSING_INPUT
     # and the context keeps working afterwards
     out, _, _ = api.cloud_compute_score(kctx, m, cts, in_var=var)
     assert np.array_equal(out, _oracle(1004, geo, model, cts, var)[0])
+    _used(kctx)
     m.free()
 
 
@@ -166,10 +192,11 @@ def test_cloud_empty_model_and_row_count_mismatch(gpu_ctx):
 
 def test_cloud_default_variance_is_alpha_squared(kctx):
     geo, model, cts, var = make_case(1004, T=10, G=6, n=3, seed=6)
-    m = api.Model(kctx, 1004, 1, 1024, model.out_bidx, model.row_ptr, model.col, model.coef)
+    m = _model(kctx, 1004, 1, 1024, model.out_bidx, model.row_ptr, model.col, model.coef)
     _, _, v0 = api.cloud_compute_score(kctx, m, cts)
     _, _, v1 = api.cloud_compute_score(kctx, m, cts, in_var=np.full(len(cts), ALPHA2))
     assert np.array_equal(v0, v1) and (v0 > 0).all()
+    _used(kctx)
     m.free()
 
 
@@ -181,7 +208,7 @@ def test_cloud_device_path_linearity_at_scale(kctx):
     geo = synth.Geometry(S, T, G)
     tag, tgt = synth.make_positions(T, G, 77)
     model = synth.make_model(tag, tgt, n, 77)
-    m = api.Model(kctx, S, 1, 1024, model.out_bidx, model.row_ptr, model.col, model.coef)
+    m = _model(kctx, S, 1, 1024, model.out_bidx, model.row_ptr, model.col, model.coef)
     g = torch.Generator(device="cuda").manual_seed(1)
     n_in = geo.n_in_ct_used
     x = torch.randint(-2 ** 31, 2 ** 31, (n_in, 2048), dtype=torch.int32, device="cuda", generator=g)
@@ -206,4 +233,5 @@ def test_cloud_device_path_linearity_at_scale(kctx):
     ref_out, _ = po.cloud_port(S, 1, 1024, np.arange(n_in, dtype=np.uint32), xin, np.full(n_in, ALPHA2),
                                np.array(rp, np.uint64), np.array(col, np.uint32), np.array(coef, np.int32))
     assert np.array_equal(outs[0].cpu().numpy().view(np.uint32)[rows], ref_out)
+    _used(kctx)
     m.free()

@@ -6,11 +6,11 @@ TAG=${1:-quick}; shift || true
 KERNELS=${*:-tensor}
 OUT=gpurun_out/$TAG
 mkdir -p "$OUT"
-timeout 900 python -m pytest tests -m gpu -x -q > "$OUT/pytest_gpu.log" 2>&1; echo "pytest rc=$?" | tee -a "$OUT/pytest_gpu.log"
+timeout ${PYTEST_TIMEOUT:-400} python -m pytest tests -m gpu -x -q ${PYTEST_ARGS:-} > "$OUT/pytest_gpu.log" 2>&1; echo "pytest rc=$?" | tee -a "$OUT/pytest_gpu.log"
 tail -25 "$OUT/pytest_gpu.log"
 for k in $KERNELS; do
   for n in ${NEIGHBORS:-5}; do
-    timeout 600 python bench.py --steps 20 --warmup 3 --kernel $k --neighbors $n --no-cpu-baseline --e2e-steps 2 > "$OUT/bench_${k}_n$n.json" 2> "$OUT/bench_${k}_n$n.err"
+    timeout 240 python bench.py --steps 20 --warmup 3 --kernel $k --neighbors $n --no-cpu-baseline --e2e-steps 2 > "$OUT/bench_${k}_n$n.json" 2> "$OUT/bench_${k}_n$n.err"
     echo "bench $k n=$n rc=$?"; python - "$OUT/bench_${k}_n$n.json" <<'PY'
 import json,sys
 try:
