@@ -26,6 +26,7 @@
 #define TC_A_LBO (8u * TC_A_SBO)     // bytes between 8-feature groups
 #define TC_B_SBO 128u                // 8 rows x 16 bytes
 #define TC_B_LBO (TC_TN * 16u)       // bytes between 16-feature chunks
+#define TC_B_CHUNK (2u * 32u * TC_TN)  // coefficient image of one 32-feature K step: c_lo (2048 B) then c_hi
 #define TC_THREADS 256
 
 struct TcParams {
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3) cloud_tc_kernel(const TcParams 
                     for (uint32_t i = 0; i < 2; ++i) {
                         if (i + j > 3) continue;
                         const uint64_t da = tc_desc(a0 + j * plane_bytes + ks * 4u * TC_A_LBO, TC_A_LBO, TC_A_SBO);
-                        const uint64_t db = tc_desc(b0 + i * K * TC_TN + ks * 2u * TC_B_LBO, TC_B_LBO, TC_B_SBO);
+                        const uint64_t db = tc_desc(b0 + ks * TC_B_CHUNK + i * (TC_B_CHUNK / 2u), TC_B_LBO, TC_B_SBO);
                         const uint32_t first = (ks == 0) && (i == 1 || j == 0);
                         tc_mma(tmem + (i + j) * TC_TN, da, db, tc_idesc(i), first ? 0u : 1u);
                     }

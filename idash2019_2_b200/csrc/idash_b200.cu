@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -374,7 +375,7 @@ extern "C" int idash_b200_init(idash_b200_ctx **out, int device) {
     CUDA_TRY(cudaFuncSetAttribute(cloud_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_max));
     CUDA_TRY(cudaFuncSetAttribute(cloud_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_max));
     CUDA_TRY(cudaFuncSetAttribute(cloud_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int) ring_smem_bytes(RG_MAX_SLOTS, IDASH_B200_RING_KMAX)));
+                                  (int) RG_SMEM_MAX));
     *out = c;
     return IDASH_B200_OK;
 }
@@ -581,12 +582,27 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
         p.n_chunks = (uint32_t) c->sm_count / 16u;
         const uint32_t max_nb = L->tile_kmax / 32u;
         p.n_slots = std::min<uint32_t>(RG_MAX_SLOTS, max_nb + 2u);
-        p.b_buf_bytes = 2u * L->tile_kmax * TC_TN;
+        p.n_bslots = std::min<uint32_t>(RG_MAX_BSLOTS, (RG_SMEM_MAX - p.n_slots * RG_BLOCK_BYTES) / TC_B_CHUNK);
         p.in = in; p.out = out;
         p.slot_of_ct = d_slot_of_ct; p.n_ct_slots = n_ct_slots; p.slot_of_row = d_slot_of_row;
         p.S = L->S;
         p.status = c->d_status;
-        cloud_ring_kernel<<<16u * p.n_chunks, RG_THREADS, ring_smem_bytes(p.n_slots, L->tile_kmax), st>>>(p);
+        if (const char *ko = getenv("IDASH_B200_KNOCKOUT")) p.knockout = (uint32_t) atoi(ko);
+        if (const char *tr = getenv("IDASH_B200_TRACE")) p.trace_cta = (uint32_t) atoi(tr) + 1u;
+        cloud_ring_kernel<<<16u * p.n_chunks, RG_THREADS, ring_smem_bytes(p.n_slots, p.n_bslots), st>>>(p);
+        if (p.trace_cta) {   // debugging only: dump the timeline of the traced CTA to the file named by IDASH_B200_TRACE_FILE
+            static unsigned long long h[RG_TRACE_TILES * RG_TRACE_EVENTS];
+            CUDA_TRY(cudaStreamSynchronize(st));
+            CUDA_TRY(cudaMemcpyFromSymbol(h, g_ring_trace, sizeof(h)));
+            const char *fn = getenv("IDASH_B200_TRACE_FILE");
+            if (FILE *f = fopen(fn ? fn : "ring_trace.txt", "w")) {
+                for (int i = 0; i < RG_TRACE_TILES; ++i) {
+                    for (int e = 0; e < RG_TRACE_EVENTS; ++e) fprintf(f, "%llu ", h[i * RG_TRACE_EVENTS + e]);
+                    fprintf(f, "\n");
+                }
+                fclose(f);
+            }
+        }
         c->last_kernel = IDASH_B200_KERNEL_TENSOR_RING;
     } else if (use_tc) {
         TcParams p;

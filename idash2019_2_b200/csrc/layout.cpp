@@ -224,7 +224,7 @@ extern "C" int idash_b200_layout_compile(const idash_b200_model_desc *d, idash_b
                 L->tile_kmax = std::max<uint32_t>(L->tile_kmax, T.K);
                 L->tile_coef.resize(L->tile_coef.size() + 2 * K * TN, 0);
                 L->tile_used.resize(L->tile_used.size() + K / 32, 0);
-                uint8_t *lo = L->tile_coef.data() + T.b_off, *hi = lo + K * TN;
+                uint8_t *img = L->tile_coef.data() + T.b_off;
                 uint32_t *used = L->tile_used.data() + T.used_off;
                 for (uint64_t i = r0; i < r1; ++i) {
                     const uint32_t r = order[i], n = (uint32_t) (i - r0);
@@ -233,9 +233,10 @@ extern "C" int idash_b200_layout_compile(const idash_b200_model_desc *d, idash_b
                     for (const Feat &f : feats[r]) {
                         if (f.coef == 0) continue;
                         const uint32_t k = f.bidx - fmin;
-                        const size_t o = (size_t) (k / 16) * (TN * 16) + (size_t) n * 16 + (k % 16);
-                        lo[o] = (uint8_t) ((uint32_t) f.coef & 0xFFu);
-                        hi[o] = (uint8_t) (((uint32_t) f.coef >> 8) & 0xFFu);   // two's complement: signed high byte
+                        // chunk of 32 features = 4096 bytes: c_lo image (2048) then c_hi image (2048)
+                        const size_t o = (size_t) (k / 32) * (2 * 32 * TN) + (size_t) ((k % 32) / 16) * (TN * 16) + (size_t) n * 16 + (k % 16);
+                        img[o] = (uint8_t) ((uint32_t) f.coef & 0xFFu);
+                        img[o + 32 * TN] = (uint8_t) (((uint32_t) f.coef >> 8) & 0xFFu);   // two's complement: signed high byte
                         used[k / 32] |= 1u << (k % 32);
                     }
                 }

@@ -56,8 +56,9 @@ typedef struct idash_b200_group {
  * split on the fly), coef = c_lo + 256 * c_hi (c_lo unsigned, c_hi signed; needs -32768 <= coef <= 32767),
  *     out = sum_{w=0..3} 2^(8w) * P_w,    P_w = X_w * c_lo + X_(w-1) * c_hi     (int32 accumulators).
  * The coefficient image of a tile is stored ready to be copied into shared memory as the K-major,
- * no-swizzle tcgen05 operand: limb i (0 = c_lo, 1 = c_hi) at b_off + i * K * TILE_ROWS, and inside a
- * limb byte (k / 16) * (TILE_ROWS * 16) + n * 16 + (k % 16) holds limb i of coef[row n][feature f_base + k].
+ * no-swizzle tcgen05 operand, one 4096-byte CHUNK per 32 features (= one MMA K step): chunk k / 32 at
+ * b_off + 4096 * (k / 32) holds the c_lo image (2048 bytes) then the c_hi image, and inside an image byte
+ * ((k % 32) / 16) * (TILE_ROWS * 16) + n * 16 + (k % 16) is the limb of coef[row n][feature f_base + k].
  * The "Constant" (bias) is NOT part of the band: the kernel adds bias * 2^18 to b[0..S) in its epilogue. */
 #define IDASH_B200_TILE_ROWS 64u
 #define IDASH_B200_TILE_KMAX 256u   /* widest band (features) a tile may have; wider models use the IMAD kernel */
