@@ -10,22 +10,30 @@
 //     from global memory, split into byte planes and stored ONCE per CTA -- the north-star's "stage each
 //     overlapping tag window once and reuse it across consecutive target SNPs".
 //   * roles: warps 0-7 epilogue (TMEM lane quadrant = warp id % 4, rows 32 (warp id / 4) .. +31 of the tile),
-//     warp 8 MMA issuer (+ TMEM owner), warp 9 coefficient loader (cp.async.bulk, one 4 KB chunk per
-//     32-feature K step into its own ring), warps 10-13 block producers. mbarrier pipelines: a_full/a_empty
-//     per input-block slot, b_full/b_empty per coefficient-chunk slot, t_full/t_empty x2 TMEM stages
-//     (2 x 4 accumulators x 64 columns = all 512 TMEM columns), so the MMAs of tile t+1 overlap the
-//     epilogue of tile t, the coefficient loader runs several tiles ahead and the producers a ring ahead.
+//     warp 8 MMA issuer (+ TMEM owner), warp 9 coefficient loader (one cp.async.bulk per tile into a ring of
+//     tile-sized stages), warps 10-13 block producers, warp 14 progress publisher.
+//   * synchronisation is built so that the MMA warp -- the one serial instruction stream every tile passes
+//     through -- does as little as possible per tile: its waits (TMEM stage free, coefficient stage full, new
+//     input blocks full) are taken by different lanes at the same time, and it issues ONE tcgen05.commit per
+//     tile (t_full). Everything that has to know "the MMAs of tile t are complete" (the coefficient loader and
+//     the block producers, to reuse ring space) reads two monotonic shared-memory counters that the
+//     publisher warp advances after it has seen t_full complete. (Measured: a tcgen05.commit costs the
+//     issuing thread ~150 cycles and an mbarrier wait ~120 even when satisfied; with per-slot commits and
+//     serial waits the MMA warp, not HBM, set the tile rate.)
+//   * TMEM: 2 stages x 4 accumulators x 64 columns = all 512 columns, so the MMAs of tile t+1 overlap the
+//     epilogue of tile t.
 #pragma once
 
-#define RG_THREADS 448
+#define RG_THREADS 480
 #define RG_EPI_WARPS 8
 #define RG_WARP_MMA 8
 #define RG_WARP_BLOAD 9
 #define RG_WARP_PROD 10
+#define RG_WARP_PUB 14
 #define RG_BLOCK_BYTES (16u * TC_A_LBO)          // 4 planes x 4 feature groups x 1152 B = 18432
 #define RG_PLANE_BYTES (4u * TC_A_LBO)
 #define RG_MAX_SLOTS 9
-#define RG_MAX_BSLOTS 16
+#define RG_MAX_BSTAGES 8
 #define RG_SMEM_MAX (226u * 1024u)               // dynamic shared memory budget of the one resident CTA
 
 struct RingParams {
@@ -38,7 +46,8 @@ struct RingParams {
     uint32_t n_tiles;
     uint32_t n_chunks;             // gridDim.x = 16 * n_chunks
     uint32_t n_slots;              // input-block ring slots (>= widest tile in blocks, + prefetch)
-    uint32_t n_bslots;             // coefficient-chunk ring slots
+    uint32_t n_bstages;            // coefficient ring stages (one tile each)
+    uint32_t b_stage_bytes;        // bytes of one coefficient stage = widest tile's image
     CtView in, out;
     const uint32_t *slot_of_ct;
     uint32_t n_ct_slots;
@@ -47,10 +56,12 @@ struct RingParams {
     int *status;
     uint32_t trace_cta;            // 0 = off, else 1 + index of the CTA whose timeline is recorded
     uint32_t knockout;             // profiling aid (IDASH_B200_KNOCKOUT, results are wrong when non-zero):
-                                   // 1 no MMAs, 2 no output stores, 4 no epilogue TMEM loads, 8 no input loads, 16 no coefficient copies
+                                   // 1 no MMAs, 2 no output stores, 4 no epilogue TMEM loads, 8 no input loads
 };
 
-__host__ __device__ constexpr uint32_t ring_smem_bytes(uint32_t n_slots, uint32_t n_bslots) { return n_slots * RG_BLOCK_BYTES + n_bslots * TC_B_CHUNK; }
+__host__ __device__ constexpr uint32_t ring_smem_bytes(uint32_t n_slots, uint32_t n_bstages, uint32_t b_stage_bytes) {
+    return n_slots * RG_BLOCK_BYTES + n_bstages * b_stage_bytes;
+}
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -62,6 +73,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
                      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     }
 }
+// non-blocking probe (no hardware suspend): 1 if the phase with this parity has completed
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar_addr, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred q;\n\tmbarrier.test_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.u32 %0, 1, 0, q;\n\t}\n"
+                 : "=r"(done) : "r"(bar_addr), "r"(parity) : "memory");
+    return done;
+}
+__device__ __forceinline__ void mbar_spin(uint64_t *bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    while (!mbar_test(a, parity)) __nanosleep(40);
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -70,6 +92,18 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 }
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// monotonic progress counters in shared memory
+__device__ __forceinline__ void progress_publish(uint32_t *ctr, uint32_t v) {
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(ctr)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void progress_wait(const uint32_t *ctr, uint32_t at_least) {
+    uint32_t v;
+    for (;;) {
+        asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(ctr)) : "memory");
+        if ((int32_t) (v - at_least) >= 0) break;
+        __nanosleep(64);      // the waiters are far ahead of the data path: do not spin hot next to the MMA warp
+    }
 }
 
 // tracing aid (IDASH_B200_TRACE=<cta>): per-tile SM-clock timestamps of one CTA, see tools/trace_ring.py
@@ -108,6 +142,24 @@ struct RingTileQueue {
 #pragma unroll
         for (uint32_t i = 0; i + 1 < RG_AHEAD; ++i) q[i] = q[i + 1];
         q[RG_AHEAD - 1] = ring_tile(p, min(t + RG_AHEAD, t_end - 1));
+    }
+};
+
+// The walk over the tiles of a chunk that every role repeats identically: which input blocks a tile adds to the
+// ring (staged in order, one slot each) and which it lets go of once its MMAs are complete.
+struct RingWalk {
+    uint32_t staged_upto, rel_upto;   // blocks < staged_upto have been staged, blocks < rel_upto released
+    __device__ __forceinline__ void init(uint32_t a0) { staged_upto = rel_upto = a0; }
+    // new blocks of tile T: [first_new, T.a + T.nb)
+    __device__ __forceinline__ uint32_t first_new(const RingTile &T) const { return max(T.a, staged_upto); }
+    // blocks tile T releases, given the next tile (or none): [rel_begin, rel_end)
+    __device__ __forceinline__ void advance(const RingTile &T, const RingTile &Tn, bool has_next, uint32_t &rel_begin, uint32_t &rel_end) {
+        const uint32_t bt = T.a + T.nb;
+        staged_upto = max(staged_upto, bt);
+        rel_begin = max(rel_upto, T.a);
+        rel_end = has_next ? min(Tn.a, bt) : bt;
+        rel_end = max(rel_end, rel_begin);
+        rel_upto = max(rel_upto, rel_end);
     }
 };
 
@@ -150,8 +202,10 @@ __device__ __forceinline__ void ring_epilogue(uint32_t taddr, uint8_t *base_lane
 
 __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t a_full[RG_MAX_SLOTS], a_empty[RG_MAX_SLOTS], b_full[RG_MAX_BSLOTS], b_empty[RG_MAX_BSLOTS], t_full[2], t_empty[2];
+    __shared__ __align__(8) uint64_t a_full[RG_MAX_SLOTS], b_full[RG_MAX_BSTAGES], t_full[2], t_empty[2];
     __shared__ uint32_t tmem_base_s;
+    __shared__ uint32_t tiles_done_s;       // tiles of this CTA whose MMAs are complete
+    __shared__ uint32_t blocks_freed_s;     // input blocks (in staging order) that no pending MMA reads any more
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t slice = blockIdx.x & 15u, chunk = blockIdx.x >> 4;
@@ -165,9 +219,11 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
     const uint32_t i_slice = w_slice & (POLY_N - 1);
 
     if (tid == 0) {
-        for (uint32_t s = 0; s < p.n_slots; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
-        for (uint32_t s = 0; s < p.n_bslots; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (uint32_t s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], RG_EPI_WARPS); }
+        for (uint32_t s = 0; s < p.n_slots; ++s) mbar_init(&a_full[s], 4);
+        for (uint32_t s = 0; s < p.n_bstages; ++s) mbar_init(&b_full[s], 1);
+        for (uint32_t s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], RG_EPI_WARPS + 1); }   // 8 epilogue warps + the publisher
+        tiles_done_s = 0;
+        blocks_freed_s = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == RG_WARP_MMA) {
@@ -218,8 +274,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                 ptr_own = (uint64_t) (p.out.words + (uint64_t) (p.slot_of_row ? __ldg(p.slot_of_row + row) : row) * p.out.stride + 4u * w_slice);
             }
             const uint32_t st = it & 1u;
-            if (tid == 0) RG_TRACE(5, it);
-            mbar_wait(&t_full[st], (it >> 1) & 1u);
+            mbar_spin(&t_full[st], (it >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (tid == 0) RG_TRACE(6, it);
             const uint32_t taddr = tmem + ((quad * 32u) << 16) + st * 4u * TC_TN + col_base;
@@ -241,117 +296,132 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
         }
     } else if (warp == RG_WARP_MMA) {
         // ================= MMA issuer =================
-        // Ring positions are tracked incrementally (no divisions); descriptors are a precomputed constant plus
-        // a 16-byte-unit offset, so one k-step (7 MMAs) is a few dozen instructions for the issuing lane.
-        const uint32_t n_slots = p.n_slots, n_bslots = p.n_bslots;
+        const uint32_t n_slots = p.n_slots, n_bstages = p.n_bstages;
         const uint64_t da_base = tc_desc(smem_u32(sA), TC_A_LBO, TC_A_SBO);
         const uint64_t db_base = tc_desc(smem_u32(sB), TC_B_LBO, TC_B_SBO);
         uint32_t it = 0;
         uint32_t next_slot = 0, next_par = 0;       // slot / phase parity of the next input block to be staged
         uint32_t first_slot = 0;                    // slot of block T.a
-        uint32_t bslot = 0, bpar = 0;               // coefficient-chunk ring position
+        uint32_t bstage = 0, bpar = 0;              // coefficient ring position
         RingTileQueue tq;
         tq.init(p, t_begin, t_end);
-        uint32_t staged_upto = tq.q[0].a, rel_upto = tq.q[0].a;
+        RingWalk walk;
+        walk.init(tq.q[0].a);
         for (uint32_t t = t_begin; t < t_end; ++t, ++it) {
             const RingTile T = tq.q[0], Tn = tq.q[1];
             const bool has_next = t + 1 < t_end;
             tq.pop(p, t);
-            const uint32_t bt = T.a + T.nb;
             const uint32_t st = it & 1u;
+            const uint32_t n_new = T.a + T.nb - walk.first_new(T);
             if (lane == 0) RG_TRACE(0, it);
-            mbar_wait(&t_empty[st], ((it >> 1) & 1u) ^ 1u);
-            if (lane == 0) RG_TRACE(1, it);
-            // input blocks this tile adds to the ring
-            for (uint32_t kb = max(T.a, staged_upto); kb < bt; ++kb) {
-                mbar_wait(&a_full[next_slot], next_par);
-                if (++next_slot == n_slots) { next_slot = 0; next_par ^= 1u; }
-            }
-            staged_upto = max(staged_upto, bt);
-            if (lane == 0) RG_TRACE(2, it);
-            // coefficient chunks of this tile
+            // all waits of this tile at once, one barrier per lane: lane 0 the TMEM stage, lane 1 the coefficient
+            // stage, lanes 2.. the input blocks this tile adds to the ring
             {
-                uint32_t s = bslot, par = bpar;
-                for (uint32_t ks = 0; ks < T.nb; ++ks) {
-                    mbar_wait(&b_full[s], par);
-                    if (++s == n_bslots) { s = 0; par ^= 1u; }
+                uint64_t *bar = nullptr;
+                uint32_t par = 0;
+                if (lane == 0) { bar = &t_empty[st]; par = ((it >> 1) & 1u) ^ 1u; }
+                else if (lane == 1) { bar = &b_full[bstage]; par = bpar; }
+                else if (lane - 2u < n_new) {
+                    uint32_t s = next_slot + (lane - 2u);
+                    par = next_par;
+                    if (s >= n_slots) { s -= n_slots; par ^= 1u; }
+                    bar = &a_full[s];
                 }
+                // warp-uniform polling loop: lanes without a barrier count as done
+                const uint32_t bar_addr = bar ? smem_u32(bar) : 0u;
+                uint32_t done = bar ? 0u : 1u;
+                for (;;) {
+                    if (!done) done = mbar_test(bar_addr, par);
+                    if (__all_sync(0xFFFFFFFFu, done)) break;
+                    __nanosleep(40);      // polling hot next to running MMAs slows them down (measured)
+                }
+                if (lane == 0) RG_TRACE(1, it);
             }
+            next_slot += n_new;
+            if (next_slot >= n_slots) { next_slot -= n_slots; next_par ^= 1u; }
+            if (lane == 0) RG_TRACE(2, it);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t rel_end = has_next ? min(Tn.a, bt) : bt;
             if (lane == 0) RG_TRACE(3, it);
             if (lane == 0) {
                 const uint32_t d0 = tmem + st * 4u * TC_TN;
+                const uint64_t db = db_base + (uint64_t) ((bstage * p.b_stage_bytes) >> 4);
                 uint32_t aslot = first_slot;
-                for (uint32_t ks = 0; ks < T.nb; ++ks) {
-                    const uint64_t da = da_base + (uint64_t) ((aslot * RG_BLOCK_BYTES) >> 4);
-                    const uint64_t db = db_base + (uint64_t) ((bslot * TC_B_CHUNK) >> 4);
-                    const uint32_t acc = ks ? 1u : 0u;
-                    if (!(p.knockout & 1u)) {
-                    tc_mma(d0 + 0 * TC_TN, da + 0 * (RG_PLANE_BYTES >> 4), db, tc_idesc(0), acc);                            // P0  = X0 c_lo
-                    tc_mma(d0 + 1 * TC_TN, da + 0 * (RG_PLANE_BYTES >> 4), db + (TC_B_CHUNK >> 5), tc_idesc(1), acc);        // P1  = X0 c_hi
-                    tc_mma(d0 + 1 * TC_TN, da + 1 * (RG_PLANE_BYTES >> 4), db, tc_idesc(0), 1u);                             // P1 += X1 c_lo
-                    tc_mma(d0 + 2 * TC_TN, da + 1 * (RG_PLANE_BYTES >> 4), db + (TC_B_CHUNK >> 5), tc_idesc(1), acc);        // P2  = X1 c_hi
-                    tc_mma(d0 + 2 * TC_TN, da + 2 * (RG_PLANE_BYTES >> 4), db, tc_idesc(0), 1u);                             // P2 += X2 c_lo
-                    tc_mma(d0 + 3 * TC_TN, da + 2 * (RG_PLANE_BYTES >> 4), db + (TC_B_CHUNK >> 5), tc_idesc(1), acc);        // P3  = X2 c_hi
-                    tc_mma(d0 + 3 * TC_TN, da + 3 * (RG_PLANE_BYTES >> 4), db, tc_idesc(0), 1u);                             // P3 += X3 c_lo
+                if (!(p.knockout & 1u)) {
+                    for (uint32_t ks = 0; ks < T.nb; ++ks) {
+                        tc_mma_kstep(d0, da_base + (uint64_t) ((aslot * RG_BLOCK_BYTES) >> 4), RG_PLANE_BYTES >> 4,
+                                     db + (uint64_t) ((ks * TC_B_CHUNK) >> 4), ks == 0);
+                        if (++aslot == n_slots) aslot = 0;
                     }
-                    tc_commit(&b_empty[bslot]);
-                    if (++aslot == n_slots) aslot = 0;
-                    if (++bslot == n_bslots) { bslot = 0; bpar ^= 1u; }
                 }
-                tc_commit(&t_full[st]);
-                // input blocks no later tile needs go back to the producers
-                uint32_t rslot = first_slot + (max(rel_upto, T.a) - T.a);
-                if (rslot >= n_slots) rslot -= n_slots;
-                for (uint32_t kb = max(rel_upto, T.a); kb < rel_end; ++kb) {
-                    tc_commit(&a_empty[rslot]);
-                    if (++rslot == n_slots) rslot = 0;
-                }
+                tc_commit(&t_full[st]);     // the only commit of the tile: epilogue and publisher wait on it
                 RG_TRACE(4, it);
             }
-            bslot = __shfl_sync(0xFFFFFFFFu, bslot, 0);
-            bpar = __shfl_sync(0xFFFFFFFFu, bpar, 0);
-            rel_upto = max(rel_upto, rel_end);
+            __syncwarp();
+            if (++bstage == n_bstages) { bstage = 0; bpar ^= 1u; }
+            uint32_t rb, re;
+            walk.advance(T, Tn, has_next, rb, re);
             // slot of the next tile's first block
             if (has_next) {
-                if (Tn.a >= staged_upto) first_slot = next_slot;              // gap: its blocks are all new
+                if (Tn.a >= walk.staged_upto) first_slot = next_slot;              // gap: its blocks are all new
                 else { first_slot += Tn.a - T.a; while (first_slot >= n_slots) first_slot -= n_slots; }
             }
         }
     } else if (warp == RG_WARP_BLOAD) {
-        // ================= coefficient-chunk loader =================
+        // ================= coefficient loader: one bulk copy per tile =================
         if (lane == 0) {
-            uint32_t bslot = 0, bpar = 0;
+            uint32_t bstage = 0, it = 0;
             RingTileQueue tq;
             tq.init(p, t_begin, t_end);
-            for (uint32_t t = t_begin; t < t_end; ++t) {
+            for (uint32_t t = t_begin; t < t_end; ++t, ++it) {
                 const RingTile T = tq.q[0];
                 tq.pop(p, t);
-                for (uint32_t ks = 0; ks < T.nb; ++ks) {
-                    mbar_wait(&b_empty[bslot], bpar ^ 1u);
-                    if (p.knockout & 16u) { mbar_arrive(&b_full[bslot]); if (++bslot == p.n_bslots) { bslot = 0; bpar ^= 1u; } continue; }
-                    mbar_arrive_expect_tx(&b_full[bslot], TC_B_CHUNK);
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(smem_u32(sB + bslot * TC_B_CHUNK)), "l"(p.tile_coef + T.b_off + (uint64_t) ks * TC_B_CHUNK), "r"(TC_B_CHUNK),
-                                   "r"(smem_u32(&b_full[bslot])) : "memory");
-                    if (++bslot == p.n_bslots) { bslot = 0; bpar ^= 1u; }
-                }
+                // the stage was last used by tile it - n_bstages: its MMAs must be complete
+                if (it >= p.n_bstages) progress_wait(&tiles_done_s, it - p.n_bstages + 1u);
+                const uint32_t bytes = T.nb * TC_B_CHUNK;
+                RG_TRACE(5, it);
+                mbar_arrive_expect_tx(&b_full[bstage], bytes);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_u32(sB + bstage * p.b_stage_bytes)), "l"(p.tile_coef + T.b_off), "r"(bytes), "r"(smem_u32(&b_full[bstage]))
+                             : "memory");
+                if (++bstage == p.n_bstages) bstage = 0;
+            }
+        }
+    } else if (warp == RG_WARP_PUB) {
+        // ================= progress publisher =================
+        // Sees each tile's t_full complete (= its MMAs are done) and advances the two counters the loader and
+        // the producers poll, so that the MMA thread needs no per-slot / per-stage tcgen05.commit.
+        if (lane == 0) {
+            RingTileQueue tq;
+            tq.init(p, t_begin, t_end);
+            RingWalk walk;
+            walk.init(tq.q[0].a);
+            uint32_t freed = 0, it = 0;
+            for (uint32_t t = t_begin; t < t_end; ++t, ++it) {
+                const RingTile T = tq.q[0], Tn = tq.q[1];
+                tq.pop(p, t);
+                uint32_t rb, re;
+                walk.advance(T, Tn, t + 1 < t_end, rb, re);
+                freed += re - rb;
+                mbar_spin(&t_full[it & 1u], (it >> 1) & 1u);
+                progress_publish(&blocks_freed_s, freed);
+                progress_publish(&tiles_done_s, it + 1u);
+                mbar_arrive(&t_empty[it & 1u]);     // the stage's next phase cannot complete before this one was seen here
             }
         }
     } else {
         // ================= block producers (4 warps, 128 threads) =================
         const uint32_t ptid = tid - RG_WARP_PROD * 32u;
         const uint32_t mg = ptid & 7u, k0 = ptid >> 3;          // this thread stages features k0 and k0 + 16 of a block
-        uint32_t slot = 0, par = 0, staged_upto = 0;
+        uint32_t slot = 0, seq = 0;
         RingTileQueue tq;
         tq.init(p, t_begin, t_end);
+        RingWalk walk;
+        walk.init(tq.q[0].a);
         for (uint32_t t = t_begin; t < t_end; ++t) {
-            const RingTile T = tq.q[0];
+            const RingTile T = tq.q[0], Tn = tq.q[1];
             tq.pop(p, t);
-            if (t == t_begin) staged_upto = T.a;
             const uint32_t bt = T.a + T.nb;
-            for (uint32_t kb = max(T.a, staged_upto); kb < bt; ++kb) {
+            for (uint32_t kb = walk.first_new(T); kb < bt; ++kb, ++seq) {
                 // issue the global loads before waiting for the slot: they do not depend on it
                 uint4 w[2][4];
                 const uint32_t used_word = kb < p.n_feat_words ? __ldg(p.feat_used + kb) : 0u;
@@ -372,7 +442,8 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                         for (int q = 0; q < 4; ++q) w[h][q] = ldg128(src + 16 * q);
                     }
                 }
-                mbar_wait(&a_empty[slot], par ^ 1u);
+                // the slot's previous block (staged n_slots blocks ago) must have been released
+                if (seq >= p.n_slots) progress_wait(&blocks_freed_s, seq - p.n_slots + 1u);
                 uint8_t *blk = sA + slot * RG_BLOCK_BYTES;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -395,9 +466,10 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_full[slot]);      // one arrival per producer warp
-                if (++slot == p.n_slots) { slot = 0; par ^= 1u; }
+                if (++slot == p.n_slots) slot = 0;
             }
-            staged_upto = max(staged_upto, bt);
+            uint32_t rb, re;
+            walk.advance(T, Tn, t + 1 < t_end, rb, re);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -6,10 +6,12 @@
 //     D[word][row] = sum_k X[f_base + k][word] * coef[row][k]        M = 128 words, N = 64 rows, K = band
 // restating the coefficient loop of cloud_compute_score (eval/idash.cpp:800-819, tLweAddMulTo ->
 // torusPolynomialAddMulZTo, toruspolynomial-functions.cpp:97-103) as a limb-split integer GEMM:
-//     X = sum_j 2^(8j) X_j (u8), coef = c_lo (u8) + 256 c_hi (s8)
+//     X = sum_j 2^(8j) X_j (u8), coef = c_lo + 256 c_hi (balanced s8 limbs)
 //     P_w = X_w c_lo + X_(w-1) c_hi  (w = 0..3, int32 in TMEM),   out = sum_w 2^(8w) P_w  mod 2^32
-// Products with weight 2^32 and above vanish mod 2^32, so 7 u8 MMAs per 32 features give the exact
-// Torus32 result. Phases of a CTA:
+// Products with weight 2^32 and above vanish mod 2^32. The coefficient operand is the 128-row matrix
+// [c_lo | c_hi], so ONE N = 128 MMA of plane X_j adds X_j c_lo to P_j and X_j c_hi to P_(j+1) (adjacent TMEM
+// columns): 3 such MMAs + one N = 64 MMA (X_3 c_lo) per 32 features give the exact Torus32 result.
+// Phases of a CTA:
 //   1. copy the tile's coefficient image (already in the K-major no-swizzle operand layout) to smem
 //   2. stage A: every thread loads 16 consecutive (rotated, sign-corrected) words of one input
 //      ciphertext, splits them into 4 byte planes (8 PRMT per 4 words) and stores one 16-byte chunk per
@@ -25,7 +27,7 @@
                                      // conflict-free 128-bit stores, verified by tools/umma_probe.cu)
 #define TC_A_LBO (8u * TC_A_SBO)     // bytes between 8-feature groups
 #define TC_B_SBO 128u                // 8 rows x 16 bytes
-#define TC_B_LBO (TC_TN * 16u)       // bytes between 16-feature chunks
+#define TC_B_LBO (2u * TC_TN * 16u)  // bytes between 16-feature halves of the [c_lo | c_hi] operand
 #define TC_B_CHUNK (2u * 32u * TC_TN)  // coefficient image of one 32-feature K step: c_lo (2048 B) then c_hi
 #define TC_THREADS 256
 
@@ -54,16 +56,26 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t addr, uint32_t lbo, uint32_
            ((uint64_t) 1 << 46);
 }
 
-// instruction descriptor: D = s32, A = u8 MN-major, B = u8 / s8 K-major, M = 128, N = 64
-__host__ __device__ constexpr uint32_t tc_idesc(uint32_t b_signed) {
-    return (2u << 4) | (0u << 7) | (b_signed << 10) | (1u << 15) | (0u << 16) | ((TC_TN >> 3) << 17) | ((128u >> 4) << 24);
-}
-
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+
+// instruction descriptor: D = s32, A = u8 MN-major, B = s8 K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t tc_idesc(uint32_t n) {
+    return (2u << 4) | (0u << 7) | (1u << 10) | (1u << 15) | (0u << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// The MMAs of one 32-feature K step: da = descriptor of limb plane 0 (planes are plane_units 16-byte units
+// apart), db = descriptor of the coefficient chunk, d0 = TMEM column of P_0, first = overwrite the accumulators.
+__device__ __forceinline__ void tc_mma_kstep(uint32_t d0, uint64_t da, uint32_t plane_units, uint64_t db, bool first) {
+    const uint32_t acc = first ? 0u : 1u;
+    tc_mma(d0 + 0 * TC_TN, da + 0 * (uint64_t) plane_units, db, tc_idesc(2 * TC_TN), acc);   // P0, P1  = X0 [c_lo | c_hi]
+    tc_mma(d0 + 2 * TC_TN, da + 2 * (uint64_t) plane_units, db, tc_idesc(2 * TC_TN), acc);   // P2, P3  = X2 [c_lo | c_hi]
+    tc_mma(d0 + 1 * TC_TN, da + 1 * (uint64_t) plane_units, db, tc_idesc(2 * TC_TN), 1u);    // P1, P2 += X1 [c_lo | c_hi]
+    tc_mma(d0 + 3 * TC_TN, da + 3 * (uint64_t) plane_units, db, tc_idesc(TC_TN), 1u);        // P3     += X3 c_lo
 }
 
 __device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
@@ -169,19 +181,9 @@ __global__ void __launch_bounds__(TC_THREADS, 3) cloud_tc_kernel(const TcParams 
         tmem = tmem_base_s;
         if (tid == 0) {
             const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-            for (uint32_t ks = 0; ks < (K >> 5); ++ks) {
-#pragma unroll
-                for (uint32_t j = 0; j < 4; ++j) {
-#pragma unroll
-                    for (uint32_t i = 0; i < 2; ++i) {
-                        if (i + j > 3) continue;
-                        const uint64_t da = tc_desc(a0 + j * plane_bytes + ks * 4u * TC_A_LBO, TC_A_LBO, TC_A_SBO);
-                        const uint64_t db = tc_desc(b0 + ks * TC_B_CHUNK + i * (TC_B_CHUNK / 2u), TC_B_LBO, TC_B_SBO);
-                        const uint32_t first = (ks == 0) && (i == 1 || j == 0);
-                        tc_mma(tmem + (i + j) * TC_TN, da, db, tc_idesc(i), first ? 0u : 1u);
-                    }
-                }
-            }
+            const uint64_t da = tc_desc(a0, TC_A_LBO, TC_A_SBO), db = tc_desc(b0, TC_B_LBO, TC_B_SBO);
+            for (uint32_t ks = 0; ks < (K >> 5); ++ks)
+                tc_mma_kstep(tmem, da + (uint64_t) ((ks * 4u * TC_A_LBO) >> 4), plane_bytes >> 4, db + (uint64_t) ((ks * TC_B_CHUNK) >> 4), ks == 0);
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_bar)) : "memory");
         }
         uint32_t done = 0;

@@ -582,14 +582,16 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
         p.n_chunks = (uint32_t) c->sm_count / 16u;
         const uint32_t max_nb = L->tile_kmax / 32u;
         p.n_slots = std::min<uint32_t>(RG_MAX_SLOTS, max_nb + 2u);
-        p.n_bslots = std::min<uint32_t>(RG_MAX_BSLOTS, (RG_SMEM_MAX - p.n_slots * RG_BLOCK_BYTES) / TC_B_CHUNK);
+        p.b_stage_bytes = max_nb * TC_B_CHUNK;
+        p.n_bstages = std::min<uint32_t>(RG_MAX_BSTAGES, (RG_SMEM_MAX - p.n_slots * RG_BLOCK_BYTES) / p.b_stage_bytes);
+        if (p.n_bstages < 2) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: internal: ring kernel shared-memory budget");
         p.in = in; p.out = out;
         p.slot_of_ct = d_slot_of_ct; p.n_ct_slots = n_ct_slots; p.slot_of_row = d_slot_of_row;
         p.S = L->S;
         p.status = c->d_status;
         if (const char *ko = getenv("IDASH_B200_KNOCKOUT")) p.knockout = (uint32_t) atoi(ko);
         if (const char *tr = getenv("IDASH_B200_TRACE")) p.trace_cta = (uint32_t) atoi(tr) + 1u;
-        cloud_ring_kernel<<<16u * p.n_chunks, RG_THREADS, ring_smem_bytes(p.n_slots, p.n_bslots), st>>>(p);
+        cloud_ring_kernel<<<16u * p.n_chunks, RG_THREADS, ring_smem_bytes(p.n_slots, p.n_bstages, p.b_stage_bytes), st>>>(p);
         if (p.trace_cta) {   // debugging only: dump the timeline of the traced CTA to the file named by IDASH_B200_TRACE_FILE
             static unsigned long long h[RG_TRACE_TILES * RG_TRACE_EVENTS];
             CUDA_TRY(cudaStreamSynchronize(st));

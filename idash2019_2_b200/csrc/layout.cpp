@@ -197,7 +197,7 @@ extern "C" int idash_b200_layout_compile(const idash_b200_model_desc *d, idash_b
                 for (uint64_t i = r0; i < r1 && ok; ++i)
                     for (const Feat &f : feats[order[i]]) {
                         if (f.coef == 0) continue;
-                        if (f.coef < -32768 || f.coef > 32767) { ok = false; break; }
+                        if (f.coef < IDASH_B200_TILE_COEF_MIN || f.coef > IDASH_B200_TILE_COEF_MAX) { ok = false; break; }
                         fmin = std::min(fmin, f.bidx);
                         fmax = std::max(fmax, f.bidx);
                     }
@@ -233,10 +233,12 @@ extern "C" int idash_b200_layout_compile(const idash_b200_model_desc *d, idash_b
                     for (const Feat &f : feats[r]) {
                         if (f.coef == 0) continue;
                         const uint32_t k = f.bidx - fmin;
-                        // chunk of 32 features = 4096 bytes: c_lo image (2048) then c_hi image (2048)
-                        const size_t o = (size_t) (k / 32) * (2 * 32 * TN) + (size_t) ((k % 32) / 16) * (TN * 16) + (size_t) n * 16 + (k % 16);
-                        img[o] = (uint8_t) ((uint32_t) f.coef & 0xFFu);
-                        img[o + 32 * TN] = (uint8_t) (((uint32_t) f.coef >> 8) & 0xFFu);   // two's complement: signed high byte
+                        // chunk of 32 features = 4096 bytes = two 16-feature halves of [c_lo rows (1024 B) | c_hi rows (1024 B)]
+                        const size_t o = (size_t) (k / 32) * (2 * 32 * TN) + (size_t) ((k % 32) / 16) * (2 * TN * 16) + (size_t) n * 16 + (k % 16);
+                        const int32_t c_lo = ((f.coef + 128) & 0xFF) - 128;       // balanced signed limbs: coef = c_lo + 256 c_hi
+                        const int32_t c_hi = (f.coef - c_lo) >> 8;
+                        img[o] = (uint8_t) (int8_t) c_lo;
+                        img[o + TN * 16] = (uint8_t) (int8_t) c_hi;
                         used[k / 32] |= 1u << (k % 32);
                     }
                 }

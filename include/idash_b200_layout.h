@@ -52,15 +52,21 @@ typedef struct idash_b200_group {
  * rows only use input features (bigIndex) inside one contiguous band [f_base, f_base + K), K a multiple
  * of 32, so the tile is a dense (rows x K) coefficient block times the (K x 2048 words) block of
  * (rotated) input ciphertexts:  out[row][word] = sum_k coef[row][k] * X[f_base + k][word]  mod 2^32.
- * The kernel evaluates it with u8 limbs on the tensor cores: X = sum_j 2^(8j) X_j (4 unsigned limbs,
- * split on the fly), coef = c_lo + 256 * c_hi (c_lo unsigned, c_hi signed; needs -32768 <= coef <= 32767),
+ * The kernel evaluates it with 8-bit limbs on the tensor cores: X = sum_j 2^(8j) X_j (4 unsigned limbs, split
+ * on the fly), coef = c_lo + 256 * c_hi with BALANCED signed limbs c_lo, c_hi in [-128, 127] (so
+ * IDASH_B200_TILE_COEF_MIN <= coef <= IDASH_B200_TILE_COEF_MAX),
  *     out = sum_{w=0..3} 2^(8w) * P_w,    P_w = X_w * c_lo + X_(w-1) * c_hi     (int32 accumulators).
  * The coefficient image of a tile is stored ready to be copied into shared memory as the K-major,
- * no-swizzle tcgen05 operand, one 4096-byte CHUNK per 32 features (= one MMA K step): chunk k / 32 at
- * b_off + 4096 * (k / 32) holds the c_lo image (2048 bytes) then the c_hi image, and inside an image byte
- * ((k % 32) / 16) * (TILE_ROWS * 16) + n * 16 + (k % 16) is the limb of coef[row n][feature f_base + k].
+ * no-swizzle tcgen05 operand, one 4096-byte CHUNK per 32 features (= one MMA K step) at
+ * b_off + 4096 * (k / 32). A chunk is two 16-feature halves of 2048 bytes; a half is the 128-row operand
+ * [c_lo of rows 0..63 | c_hi of rows 0..63], 16 bytes per row: byte
+ *     ((k % 32) / 16) * 2048 + limb * 1024 + n * 16 + (k % 16)
+ * is limb (0 = c_lo, 1 = c_hi) of coef[row n][feature f_base + k]. One N = 128 MMA of limb plane X_j against a
+ * chunk therefore adds X_j c_lo to P_j and X_j c_hi to P_(j+1), which sit in adjacent TMEM columns.
  * The "Constant" (bias) is NOT part of the band: the kernel adds bias * 2^18 to b[0..S) in its epilogue. */
 #define IDASH_B200_TILE_ROWS 64u
+#define IDASH_B200_TILE_COEF_MIN (-32896)
+#define IDASH_B200_TILE_COEF_MAX 32639
 #define IDASH_B200_TILE_KMAX 256u   /* widest band (features) a tile may have; wider models use the IMAD kernel */
 /* With NUM_REGIONS == 1 every band starts on a multiple of 32 features (a "block"). When, in addition, bands
  * only move forward from tile to tile and are at most RING_KMAX wide, the persistent kernel keeps the staged

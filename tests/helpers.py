@@ -84,9 +84,9 @@ def interpret_tiles(layout, S, NR, RS, in_ct, slot_of_ct=None):
     n_slots = len(in_ct)
     for t, T in enumerate(layout.tiles):
         K, f_base, b_off = int(T["K"]), int(T["f_base"]), int(T["b_off"])
-        img = layout.tile_coef[b_off:b_off + 2 * K * TN].reshape(K // 32, 2, 2, TN, 16)     # [chunk][limb][k16][row][k%16]
-        c_lo = img[:, 0].transpose(2, 0, 1, 3).reshape(TN, K).astype(np.int64)              # [row][k] unsigned
-        c_hi = np.ascontiguousarray(img[:, 1].transpose(2, 0, 1, 3)).reshape(TN, K).view(np.int8).astype(np.int64)   # signed
+        img = layout.tile_coef[b_off:b_off + 2 * K * TN].view(np.int8).reshape(K // 32, 2, 2, TN, 16)   # [chunk][k16][limb][row][k%16]
+        c_lo = img[:, :, 0].transpose(2, 0, 1, 3).reshape(TN, K).astype(np.int64)           # [row][k], balanced signed limbs
+        c_hi = img[:, :, 1].transpose(2, 0, 1, 3).reshape(TN, K).astype(np.int64)
         used = layout.tile_used[int(T["used_off"]):int(T["used_off"]) + K // 32]
         X = np.zeros((K, 2048), np.uint32)
         for k in range(K):

@@ -125,11 +125,11 @@ def test_cloud_auto_picks_tensor_kernel_for_idash_models(gpu_ctx):
 
 
 def test_cloud_tensor_kernel_extreme_int16_coefficients_and_wide_band(kctx):
-    """+-32767/-32768 coefficients (signed high limb), all-ones words (max limb products), a 40-neighbour band."""
+    """Extreme eligible coefficients (both limbs at +-128/127), all-ones words (max limb products), a 40-neighbour band."""
     S = 1004
     geo, model, cts, var = make_case(S, T=120, G=150, n=40, seed=9, coef_range=200, bias_range=500)
     rng = np.random.default_rng(5)
-    coef = rng.choice(np.array([-32768, -32767, -1, 1, 255, 256, 32767, -256, -255], np.int32), size=model.nnz)
+    coef = rng.choice(np.array([-32896, -32768, -32767, -129, -128, -1, 1, 127, 128, 255, 256, 32639, 32512, -256, -255], np.int32), size=model.nnz)
     cts = cts.copy()
     cts[::3] = 0xFFFFFFFF
     m = _model(kctx, S, 1, 1024, model.out_bidx, model.row_ptr, model.col, coef)

@@ -51,7 +51,7 @@ def test_layout_interpreter_matches_oracle(built_lib, S, n):
         assert (lay.entries[e0 + int(G["n_a"] + G["n_ab"]):e0 + cnt]["coef"][:, :3] == 0).all()
 
 
-@pytest.mark.parametrize("S,n,cr", [(1004, 5, 200), (1024, 1, 32767), (512, 5, 8191), (400, 20, 200), (335, 5, 8191), (64, 3, 200),
+@pytest.mark.parametrize("S,n,cr", [(1004, 5, 200), (1024, 1, 32639), (512, 5, 8191), (400, 20, 200), (335, 5, 8191), (64, 3, 200),
                                     (16, 5, 8191)])
 def test_tile_interpreter_matches_oracle(built_lib, S, n, cr):
     """The tensor-core operand layout (band tiles, limb-split coefficients) reproduces the oracle."""
