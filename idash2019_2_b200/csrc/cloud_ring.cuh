@@ -48,6 +48,8 @@ struct RingParams {
     uint32_t n_slots;              // input-block ring slots (>= widest tile in blocks, + prefetch)
     uint32_t n_bstages;            // coefficient ring stages (one tile each)
     uint32_t b_stage_bytes;        // bytes of one coefficient stage = widest tile's image
+    uint32_t hdr_off;              // byte offset (dynamic shared memory) of the CTA's tile-header table
+    uint32_t max_chunk_tiles;      // capacity of that table (tiles per chunk, rounded up)
     CtView in, out;
     const uint32_t *slot_of_ct;
     uint32_t n_ct_slots;
@@ -55,12 +57,14 @@ struct RingParams {
     uint32_t S;
     int *status;
     uint32_t trace_cta;            // 0 = off, else 1 + index of the CTA whose timeline is recorded
+    uint32_t tune;                 // experiment switches (IDASH_B200_TUNE): 1 epilogue waits with try_wait, 2 publisher waits with
+                                   // try_wait, 4 MMA warp polls without nanosleep, 8 warp-converged MMA issue (uniform operands)
     uint32_t knockout;             // profiling aid (IDASH_B200_KNOCKOUT, results are wrong when non-zero):
                                    // 1 no MMAs, 2 no output stores, 4 no epilogue TMEM loads, 8 no input loads
 };
 
-__host__ __device__ constexpr uint32_t ring_smem_bytes(uint32_t n_slots, uint32_t n_bstages, uint32_t b_stage_bytes) {
-    return n_slots * RG_BLOCK_BYTES + n_bstages * b_stage_bytes;
+__host__ __device__ constexpr uint32_t ring_smem_bytes(uint32_t n_slots, uint32_t n_bstages, uint32_t b_stage_bytes, uint32_t max_chunk_tiles) {
+    return n_slots * RG_BLOCK_BYTES + n_bstages * b_stage_bytes + 4u * max_chunk_tiles;
 }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -93,6 +97,25 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred;
+}
+// tcgen05.mma issued by the elected lane of a converged warp; the operands are warp-uniform
+__device__ __forceinline__ void tc_mma_p(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate, uint32_t leader) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_kstep_p(uint32_t d0, uint64_t da, uint32_t plane_units, uint64_t db, bool first, uint32_t leader) {
+    const uint32_t acc = first ? 0u : 1u;
+    tc_mma_p(d0 + 0 * TC_TN, da + 0 * (uint64_t) plane_units, db, tc_idesc(2 * TC_TN), acc, leader);
+    tc_mma_p(d0 + 2 * TC_TN, da + 2 * (uint64_t) plane_units, db, tc_idesc(2 * TC_TN), acc, leader);
+    tc_mma_p(d0 + 1 * TC_TN, da + 1 * (uint64_t) plane_units, db, tc_idesc(2 * TC_TN), 1u, leader);
+    tc_mma_p(d0 + 3 * TC_TN, da + 3 * (uint64_t) plane_units, db, tc_idesc(TC_TN), 1u, leader);
+}
 // monotonic progress counters in shared memory
 __device__ __forceinline__ void progress_publish(uint32_t *ctr, uint32_t v) {
     asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(ctr)), "r"(v) : "memory");
@@ -108,7 +131,7 @@ __device__ __forceinline__ void progress_wait(const uint32_t *ctr, uint32_t at_l
 
 // tracing aid (IDASH_B200_TRACE=<cta>): per-tile SM-clock timestamps of one CTA, see tools/trace_ring.py
 #define RG_TRACE_TILES 96
-#define RG_TRACE_EVENTS 8
+#define RG_TRACE_EVENTS 12
 __device__ unsigned long long g_ring_trace[RG_TRACE_TILES * RG_TRACE_EVENTS];
 #define RG_TRACE(ev, it_)                                                                                     \
     do {                                                                                                      \
@@ -116,34 +139,30 @@ __device__ unsigned long long g_ring_trace[RG_TRACE_TILES * RG_TRACE_EVENTS];
             g_ring_trace[((it_) - 64u) * RG_TRACE_EVENTS + (ev)] = clock64();                                    \
     } while (0)
 
-struct RingTile { uint32_t a, nb; uint64_t b_off; };   // first block, blocks, coefficient image
+struct RingTile { uint32_t a, nb, fast; };   // first input block, blocks, rows are consecutive caller rows
 
-__device__ __forceinline__ RingTile ring_tile(const RingParams &p, uint32_t t) {
-    const uint4 t0 = __ldg(reinterpret_cast<const uint4 *>(p.tiles + t));
+// Tile headers: every role walks the tiles of the chunk, and a header read from global memory inside those loops
+// exposes an L2 / HBM round trip per tile per role (measured: 40% of the epilogue warps' time). The CTA therefore
+// packs the headers of its chunk into shared memory once, before the roles start:
+//     bits 0..19 first block (f_base / 32), bits 20..30 blocks (K / 32), bit 31 flags & 1
+#define RG_HDR_A_BITS 20
+__device__ __forceinline__ uint32_t ring_pack_hdr(const idash_b200_tile *tp) {
+    const uint4 t0 = __ldg(reinterpret_cast<const uint4 *>(tp));
+    const uint32_t flags = __ldg(&tp->flags);
+    return (t0.x >> 5) | ((t0.y >> 5) << RG_HDR_A_BITS) | ((flags & 1u) << 31);
+}
+__device__ __forceinline__ RingTile ring_hdr(const uint32_t *hdr_s, uint32_t i) {
+    const uint32_t h = hdr_s[i];
     RingTile r;
-    r.a = t0.x >> 5; r.nb = t0.y >> 5;
-    r.b_off = (uint64_t) t0.z | ((uint64_t) t0.w << 32);
+    r.a = h & ((1u << RG_HDR_A_BITS) - 1u); r.nb = (h >> RG_HDR_A_BITS) & 0x7FFu; r.fast = h >> 31;
     return r;
 }
 
-// Tile headers come from global memory (~1 us away): every role reads them RG_AHEAD tiles ahead of use through a
-// small register queue, otherwise each tile iteration would expose one dependent L2 / HBM round trip.
-#define RG_AHEAD 4
-struct RingTileQueue {
-    RingTile q[RG_AHEAD];
-    uint32_t t_end;
-    __device__ __forceinline__ void init(const RingParams &p, uint32_t t_begin, uint32_t t_end_) {
-        t_end = t_end_;
-#pragma unroll
-        for (uint32_t i = 0; i < RG_AHEAD; ++i) q[i] = ring_tile(p, min(t_begin + i, t_end_ - 1));
-    }
-    // header of tile t (front) is consumed; fetch tile t + RG_AHEAD
-    __device__ __forceinline__ void pop(const RingParams &p, uint32_t t) {
-#pragma unroll
-        for (uint32_t i = 0; i + 1 < RG_AHEAD; ++i) q[i] = q[i + 1];
-        q[RG_AHEAD - 1] = ring_tile(p, min(t + RG_AHEAD, t_end - 1));
-    }
-};
+#define RG_TRACE_V(ev, it_, val)                                                                             \
+    do {                                                                                                      \
+        if (p.trace_cta == blockIdx.x + 1u && (it_) >= 64u && (it_) < 64u + RG_TRACE_TILES)                     \
+            g_ring_trace[((it_) - 64u) * RG_TRACE_EVENTS + (ev)] = (unsigned long long) (val);                    \
+    } while (0)
 
 // The walk over the tiles of a chunk that every role repeats identically: which input blocks a tile adds to the
 // ring (staged in order, one slot each) and which it lets go of once its MMAs are complete.
@@ -214,6 +233,9 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
     if (t_begin >= t_end) return;
     uint8_t *sA = smem;
     uint8_t *sB = smem + p.n_slots * RG_BLOCK_BYTES;
+    uint32_t *hdr_s = reinterpret_cast<uint32_t *>(smem + p.hdr_off);
+    const uint32_t n_my = t_end - t_begin;             // <= p.max_chunk_tiles
+    for (uint32_t i = tid; i < n_my; i += RG_THREADS) hdr_s[i] = ring_pack_hdr(p.tiles + t_begin + i);
     const uint32_t w_slice = slice * 128u;
     const bool is_b = (w_slice & POLY_N) != 0;
     const uint32_t i_slice = w_slice & (POLY_N - 1);
@@ -242,57 +264,59 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
         const uint32_t lane_off = 4u * word_in_slice;
         const uint32_t bias_flag = (is_b && i_slice + word_in_slice < p.S) ? 1u : 0u;
         const bool records = p.out.records != 0;
-        uint32_t it = 0;
-        // row information is fetched RG_AHEAD tiles ahead: lane l owns row col_base + l
-        uint32_t row_q[RG_AHEAD], flags_q[RG_AHEAD];
-        int32_t bias_q[RG_AHEAD];
+        // Row information (caller row + Constant of row col_base + lane) comes from global memory. It is prefetched TWO
+        // tiles ahead into registers that are statically bound to the tile's parity (= its TMEM stage): the loop is
+        // unrolled by two, so no register is shifted between tiles and nothing waits for a load that was just issued.
+        uint32_t row_q[2];
+        int32_t bias_q[2];
 #pragma unroll
-        for (uint32_t i = 0; i < RG_AHEAD; ++i) {
-            const uint32_t tt = min(t_begin + i, t_end - 1);
-            row_q[i] = __ldg(p.tile_rows + (uint64_t) tt * TC_TN + col_base + lane);
-            bias_q[i] = __ldg(p.tile_bias + (uint64_t) tt * TC_TN + col_base + lane);
-            flags_q[i] = __ldg(&p.tiles[tt].flags);
+        for (uint32_t u = 0; u < 2; ++u) {
+            const uint32_t tt = min(t_begin + u, t_end - 1);
+            row_q[u] = __ldg(p.tile_rows + (uint64_t) tt * TC_TN + col_base + lane);
+            bias_q[u] = __ldg(p.tile_bias + (uint64_t) tt * TC_TN + col_base + lane);
         }
-        for (uint32_t t = t_begin; t < t_end; ++t, ++it) {
-            const uint32_t row = row_q[0], flags = flags_q[0];
-            const uint32_t bias_own = (uint32_t) bias_q[0] * (uint32_t) IDASH_B200_ONE_IN_T32;
-            {
+        for (uint32_t t2 = t_begin; t2 < t_end; t2 += 2) {
 #pragma unroll
-                for (uint32_t i = 0; i + 1 < RG_AHEAD; ++i) { row_q[i] = row_q[i + 1]; bias_q[i] = bias_q[i + 1]; flags_q[i] = flags_q[i + 1]; }
-                const uint32_t tt = min(t + RG_AHEAD, t_end - 1);
-                row_q[RG_AHEAD - 1] = __ldg(p.tile_rows + (uint64_t) tt * TC_TN + col_base + lane);
-                bias_q[RG_AHEAD - 1] = __ldg(p.tile_bias + (uint64_t) tt * TC_TN + col_base + lane);
-                flags_q[RG_AHEAD - 1] = __ldg(&p.tiles[tt].flags);
-            }
-            const bool fast = (flags & 1u) && p.slot_of_row == nullptr;
-            uint64_t ptr_own = 0;
-            uint8_t *base_lane = nullptr;
-            if (fast) {
-                const uint32_t row0 = __shfl_sync(0xFFFFFFFFu, row, 0);     // caller row of tile row col_base
-                base_lane = p.out.words + (uint64_t) row0 * p.out.stride + 4u * w_slice + lane_off;
-            } else if (row != IDASH_B200_NO_ROW) {
-                ptr_own = (uint64_t) (p.out.words + (uint64_t) (p.slot_of_row ? __ldg(p.slot_of_row + row) : row) * p.out.stride + 4u * w_slice);
-            }
-            const uint32_t st = it & 1u;
-            mbar_spin(&t_full[st], (it >> 1) & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (tid == 0) RG_TRACE(6, it);
-            const uint32_t taddr = tmem + ((quad * 32u) << 16) + st * 4u * TC_TN + col_base;
-            if (fast) {
-                if (records) {
-                    if (is_b) ring_epilogue<true, IDASH_B200_RECORD_BYTES, true>(taddr, base_lane, 0, bias_own, bias_flag, lane_off, p.knockout);
-                    else ring_epilogue<true, IDASH_B200_RECORD_BYTES, false>(taddr, base_lane, 0, 0, 0, lane_off, p.knockout);
-                } else {
-                    if (is_b) ring_epilogue<true, IDASH_B200_CT_BYTES, true>(taddr, base_lane, 0, bias_own, bias_flag, lane_off, p.knockout);
-                    else ring_epilogue<true, IDASH_B200_CT_BYTES, false>(taddr, base_lane, 0, 0, 0, lane_off, p.knockout);
+            for (uint32_t u = 0; u < 2; ++u) {
+                const uint32_t t = t2 + u;
+                if (t >= t_end) break;
+                const uint32_t it = t - t_begin, st = u;
+                const uint32_t row = row_q[u];
+                const uint32_t bias_own = (uint32_t) bias_q[u] * (uint32_t) IDASH_B200_ONE_IN_T32;
+                const bool fast = ring_hdr(hdr_s, it).fast && p.slot_of_row == nullptr;
+                uint64_t ptr_own = 0;
+                uint8_t *base_lane = nullptr;
+                if (fast) {
+                    const uint32_t row0 = __shfl_sync(0xFFFFFFFFu, row, 0);     // caller row of tile row col_base
+                    base_lane = p.out.words + (uint64_t) row0 * p.out.stride + 4u * w_slice + lane_off;
+                } else if (row != IDASH_B200_NO_ROW) {
+                    ptr_own = (uint64_t) (p.out.words + (uint64_t) (p.slot_of_row ? __ldg(p.slot_of_row + row) : row) * p.out.stride + 4u * w_slice);
                 }
-            } else {
-                ring_epilogue<false, 0, true>(taddr, nullptr, ptr_own, bias_own, bias_flag, lane_off, p.knockout);
+                {   // prefetch for tile t + 2 (same parity): consumed a whole tile pair later
+                    const uint32_t tt = min(t + 2u, t_end - 1);
+                    row_q[u] = __ldg(p.tile_rows + (uint64_t) tt * TC_TN + col_base + lane);
+                    bias_q[u] = __ldg(p.tile_bias + (uint64_t) tt * TC_TN + col_base + lane);
+                }
+                if (p.tune & 1u) mbar_wait(&t_full[st], (it >> 1) & 1u); else mbar_spin(&t_full[st], (it >> 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (tid == 0) RG_TRACE(6, it);
+                const uint32_t taddr = tmem + ((quad * 32u) << 16) + st * 4u * TC_TN + col_base;
+                if (fast) {
+                    if (records) {
+                        if (is_b) ring_epilogue<true, IDASH_B200_RECORD_BYTES, true>(taddr, base_lane, 0, bias_own, bias_flag, lane_off, p.knockout);
+                        else ring_epilogue<true, IDASH_B200_RECORD_BYTES, false>(taddr, base_lane, 0, 0, 0, lane_off, p.knockout);
+                    } else {
+                        if (is_b) ring_epilogue<true, IDASH_B200_CT_BYTES, true>(taddr, base_lane, 0, bias_own, bias_flag, lane_off, p.knockout);
+                        else ring_epilogue<true, IDASH_B200_CT_BYTES, false>(taddr, base_lane, 0, 0, 0, lane_off, p.knockout);
+                    }
+                } else {
+                    ring_epilogue<false, 0, true>(taddr, nullptr, ptr_own, bias_own, bias_flag, lane_off, p.knockout);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (tid == 0) RG_TRACE(8, it);
+                if (lane == 0) mbar_arrive(&t_empty[st]);      // one arrival per epilogue warp
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (tid == 0) RG_TRACE(7, it);
-            if (lane == 0) mbar_arrive(&t_empty[st]);      // one arrival per epilogue warp
         }
     } else if (warp == RG_WARP_MMA) {
         // ================= MMA issuer =================
@@ -303,14 +327,14 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
         uint32_t next_slot = 0, next_par = 0;       // slot / phase parity of the next input block to be staged
         uint32_t first_slot = 0;                    // slot of block T.a
         uint32_t bstage = 0, bpar = 0;              // coefficient ring position
-        RingTileQueue tq;
-        tq.init(p, t_begin, t_end);
         RingWalk walk;
-        walk.init(tq.q[0].a);
+        walk.init(ring_hdr(hdr_s, 0).a);
+        const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem, 0);
+        const uint32_t bsb_u = p.b_stage_bytes;
+        const uint32_t leader = elect_one();
         for (uint32_t t = t_begin; t < t_end; ++t, ++it) {
-            const RingTile T = tq.q[0], Tn = tq.q[1];
             const bool has_next = t + 1 < t_end;
-            tq.pop(p, t);
+            const RingTile T = ring_hdr(hdr_s, it), Tn = ring_hdr(hdr_s, has_next ? it + 1u : it);
             const uint32_t st = it & 1u;
             const uint32_t n_new = T.a + T.nb - walk.first_new(T);
             if (lane == 0) RG_TRACE(0, it);
@@ -330,18 +354,38 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                 // warp-uniform polling loop: lanes without a barrier count as done
                 const uint32_t bar_addr = bar ? smem_u32(bar) : 0u;
                 uint32_t done = bar ? 0u : 1u;
+                long long t_done = 0;
                 for (;;) {
-                    if (!done) done = mbar_test(bar_addr, par);
+                    if (!done) { done = mbar_test(bar_addr, par); if (done && p.trace_cta) t_done = clock64(); }
                     if (__all_sync(0xFFFFFFFFu, done)) break;
-                    __nanosleep(40);      // polling hot next to running MMAs slows them down (measured)
+                    if (!(p.tune & 4u)) __nanosleep(40);      // polling hot next to running MMAs slows them down (measured)
                 }
-                if (lane == 0) RG_TRACE(1, it);
+                if (p.trace_cta) {
+                    if (lane == 0) { RG_TRACE_V(1, it, t_done); RG_TRACE(4, it); }
+                    if (lane == 1) RG_TRACE_V(2, it, t_done);
+                    if (lane == 2) RG_TRACE_V(3, it, t_done);
+                }
             }
             next_slot += n_new;
             if (next_slot >= n_slots) { next_slot -= n_slots; next_par ^= 1u; }
-            if (lane == 0) RG_TRACE(2, it);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) RG_TRACE(3, it);
+            if (p.tune & 8u) {
+                // warp-converged issue: every operand is made provably warp-uniform (shuffle from lane 0), so that the
+                // compiler feeds the MMA's uniform-register operands without a per-instruction broadcast loop
+                const uint32_t nb_u = __shfl_sync(0xFFFFFFFFu, T.nb, 0);
+                uint32_t aslot = __shfl_sync(0xFFFFFFFFu, first_slot, 0);
+                const uint32_t d0 = tmem_u + st * 4u * TC_TN;
+                const uint64_t db = db_base + (uint64_t) ((bstage * bsb_u) >> 4);
+                if (!(p.knockout & 1u)) {
+                    for (uint32_t ks = 0; ks < nb_u; ++ks) {
+                        tc_mma_kstep_p(d0, da_base + (uint64_t) ((aslot * RG_BLOCK_BYTES) >> 4), RG_PLANE_BYTES >> 4,
+                                       db + (uint64_t) ((ks * TC_B_CHUNK) >> 4), ks == 0, leader);
+                        if (++aslot == n_slots) aslot = 0;
+                    }
+                }
+                if (leader) tc_commit(&t_full[st]);
+                if (lane == 0) RG_TRACE(5, it);
+            } else
             if (lane == 0) {
                 const uint32_t d0 = tmem + st * 4u * TC_TN;
                 const uint64_t db = db_base + (uint64_t) ((bstage * p.b_stage_bytes) >> 4);
@@ -354,7 +398,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                     }
                 }
                 tc_commit(&t_full[st]);     // the only commit of the tile: epilogue and publisher wait on it
-                RG_TRACE(4, it);
+                RG_TRACE(5, it);
             }
             __syncwarp();
             if (++bstage == n_bstages) { bstage = 0; bpar ^= 1u; }
@@ -370,19 +414,20 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
         // ================= coefficient loader: one bulk copy per tile =================
         if (lane == 0) {
             uint32_t bstage = 0, it = 0;
-            RingTileQueue tq;
-            tq.init(p, t_begin, t_end);
+            // the coefficient images of consecutive tiles are contiguous (layout.cpp): b_off advances by the tile's size
+            const uint4 h0 = __ldg(reinterpret_cast<const uint4 *>(p.tiles + t_begin));
+            uint64_t b_off = (uint64_t) h0.z | ((uint64_t) h0.w << 32);
             for (uint32_t t = t_begin; t < t_end; ++t, ++it) {
-                const RingTile T = tq.q[0];
-                tq.pop(p, t);
+                const RingTile T = ring_hdr(hdr_s, it);
                 // the stage was last used by tile it - n_bstages: its MMAs must be complete
                 if (it >= p.n_bstages) progress_wait(&tiles_done_s, it - p.n_bstages + 1u);
                 const uint32_t bytes = T.nb * TC_B_CHUNK;
-                RG_TRACE(5, it);
+                RG_TRACE(10, it);
                 mbar_arrive_expect_tx(&b_full[bstage], bytes);
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(smem_u32(sB + bstage * p.b_stage_bytes)), "l"(p.tile_coef + T.b_off), "r"(bytes), "r"(smem_u32(&b_full[bstage]))
+                             ::"r"(smem_u32(sB + bstage * p.b_stage_bytes)), "l"(p.tile_coef + b_off), "r"(bytes), "r"(smem_u32(&b_full[bstage]))
                              : "memory");
+                b_off += bytes;
                 if (++bstage == p.n_bstages) bstage = 0;
             }
         }
@@ -391,18 +436,16 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
         // Sees each tile's t_full complete (= its MMAs are done) and advances the two counters the loader and
         // the producers poll, so that the MMA thread needs no per-slot / per-stage tcgen05.commit.
         if (lane == 0) {
-            RingTileQueue tq;
-            tq.init(p, t_begin, t_end);
             RingWalk walk;
-            walk.init(tq.q[0].a);
+            walk.init(ring_hdr(hdr_s, 0).a);
             uint32_t freed = 0, it = 0;
             for (uint32_t t = t_begin; t < t_end; ++t, ++it) {
-                const RingTile T = tq.q[0], Tn = tq.q[1];
-                tq.pop(p, t);
+                const RingTile T = ring_hdr(hdr_s, it), Tn = ring_hdr(hdr_s, t + 1 < t_end ? it + 1u : it);
                 uint32_t rb, re;
                 walk.advance(T, Tn, t + 1 < t_end, rb, re);
                 freed += re - rb;
-                mbar_spin(&t_full[it & 1u], (it >> 1) & 1u);
+                if (p.tune & 2u) mbar_wait(&t_full[it & 1u], (it >> 1) & 1u); else mbar_spin(&t_full[it & 1u], (it >> 1) & 1u);
+                RG_TRACE(9, it);
                 progress_publish(&blocks_freed_s, freed);
                 progress_publish(&tiles_done_s, it + 1u);
                 mbar_arrive(&t_empty[it & 1u]);     // the stage's next phase cannot complete before this one was seen here
@@ -413,13 +456,11 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
         const uint32_t ptid = tid - RG_WARP_PROD * 32u;
         const uint32_t mg = ptid & 7u, k0 = ptid >> 3;          // this thread stages features k0 and k0 + 16 of a block
         uint32_t slot = 0, seq = 0;
-        RingTileQueue tq;
-        tq.init(p, t_begin, t_end);
         RingWalk walk;
-        walk.init(tq.q[0].a);
+        walk.init(ring_hdr(hdr_s, 0).a);
         for (uint32_t t = t_begin; t < t_end; ++t) {
-            const RingTile T = tq.q[0], Tn = tq.q[1];
-            tq.pop(p, t);
+            const uint32_t it = t - t_begin;
+            const RingTile T = ring_hdr(hdr_s, it), Tn = ring_hdr(hdr_s, t + 1 < t_end ? it + 1u : it);
             const uint32_t bt = T.a + T.nb;
             for (uint32_t kb = walk.first_new(T); kb < bt; ++kb, ++seq) {
                 // issue the global loads before waiting for the slot: they do not depend on it

@@ -569,7 +569,13 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
         return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: the persistent ring kernel was requested but the model is not eligible "
                                                  "(needs NUM_REGIONS == 1, forward-moving bands of at most %u features)", IDASH_B200_RING_KMAX);
     const bool use_tc = tc_ok && c->kernel_choice != IDASH_B200_KERNEL_IMAD;
-    const bool use_ring = use_tc && L->ring_ok && c->kernel_choice != IDASH_B200_KERNEL_TENSOR_TILE && c->sm_count >= 16;
+    // the ring kernel keeps a 4-byte header per tile of a chunk in shared memory (first block in 20 bits)
+    const uint64_t ring_chunk_tiles = c->sm_count >= 16 ? (L->tiles.size() + c->sm_count / 16 - 1) / (c->sm_count / 16) + 1 : 0;
+    const bool ring_fits = c->sm_count >= 16 && ring_chunk_tiles * 4u <= 32768u &&
+                           (L->tiles.empty() || (L->tiles.back().f_base >> 5) + IDASH_B200_TILE_KMAX / 32u < (1u << RG_HDR_A_BITS));
+    if (c->kernel_choice == IDASH_B200_KERNEL_TENSOR_RING && L->ring_ok && !ring_fits)
+        return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: the persistent ring kernel was requested but the model has too many tiles per chunk");
+    const bool use_ring = use_tc && L->ring_ok && ring_fits && c->kernel_choice != IDASH_B200_KERNEL_TENSOR_TILE;
     const bool timed = c->t_used < (int) c->t_begin.size();
     if (timed) CUDA_TRY(cudaEventRecord(c->t_begin[c->t_used], st));
     if (use_ring) {
@@ -583,15 +589,19 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
         const uint32_t max_nb = L->tile_kmax / 32u;
         p.n_slots = std::min<uint32_t>(RG_MAX_SLOTS, max_nb + 2u);
         p.b_stage_bytes = max_nb * TC_B_CHUNK;
-        p.n_bstages = std::min<uint32_t>(RG_MAX_BSTAGES, (RG_SMEM_MAX - p.n_slots * RG_BLOCK_BYTES) / p.b_stage_bytes);
+        p.max_chunk_tiles = (p.n_tiles + p.n_chunks - 1u) / p.n_chunks + 1u;
+        p.n_bstages = std::min<uint32_t>(RG_MAX_BSTAGES, (RG_SMEM_MAX - p.n_slots * RG_BLOCK_BYTES - 4u * p.max_chunk_tiles) / p.b_stage_bytes);
+        p.hdr_off = p.n_slots * RG_BLOCK_BYTES + p.n_bstages * p.b_stage_bytes;
         if (p.n_bstages < 2) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: internal: ring kernel shared-memory budget");
         p.in = in; p.out = out;
         p.slot_of_ct = d_slot_of_ct; p.n_ct_slots = n_ct_slots; p.slot_of_row = d_slot_of_row;
         p.S = L->S;
         p.status = c->d_status;
         if (const char *ko = getenv("IDASH_B200_KNOCKOUT")) p.knockout = (uint32_t) atoi(ko);
+        p.tune = 8u;      // warp-converged MMA issue (see cloud_ring.cuh)
+        if (const char *tu = getenv("IDASH_B200_TUNE")) p.tune = (uint32_t) atoi(tu);
         if (const char *tr = getenv("IDASH_B200_TRACE")) p.trace_cta = (uint32_t) atoi(tr) + 1u;
-        cloud_ring_kernel<<<16u * p.n_chunks, RG_THREADS, ring_smem_bytes(p.n_slots, p.n_bstages, p.b_stage_bytes), st>>>(p);
+        cloud_ring_kernel<<<16u * p.n_chunks, RG_THREADS, ring_smem_bytes(p.n_slots, p.n_bstages, p.b_stage_bytes, p.max_chunk_tiles), st>>>(p);
         if (p.trace_cta) {   // debugging only: dump the timeline of the traced CTA to the file named by IDASH_B200_TRACE_FILE
             static unsigned long long h[RG_TRACE_TILES * RG_TRACE_EVENTS];
             CUDA_TRY(cudaStreamSynchronize(st));

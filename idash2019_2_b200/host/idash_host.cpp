@@ -1,0 +1,506 @@
+// idash_host.cpp -- see idash_host.h. Host logic only: file formats, container plumbing and the calls into
+// libidash_b200.so. All torus arithmetic of the cloud and decrypt stages runs on the GPU behind the C ABI; there
+// is no CPU evaluation path in this file.
+#include "idash_host.h"
+#include "parse_vw.h"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <thread>
+
+#include <sys/resource.h>
+#include <sys/time.h>
+#include <time.h>
+
+#include "idash_b200.h"
+
+using std::string;
+
+// ---- constants (eval/idash.cpp:20-45) --------------------------------------------------------------------------
+const double IdashParams::alpha = 1.0 / 33554432.0;            // pow(2., -25)
+const Torus32 IdashParams::ONE_IN_T32 = IDASH_B200_ONE_IN_T32;   // dtot32(1 / 16384)
+static const TLweParams g_tlwe_params = {(int32_t) IdashParams::N, (int32_t) IdashParams::k, IdashParams::alpha, 0.25};
+const TLweParams *IdashParams::tlweParams = &g_tlwe_params;
+
+static const uint32_t REC = IDASH_B200_RECORD_BYTES;
+static const uint32_t REC_WORDS_OFF = 8;                          // u32 index, i32 type uid
+static const uint32_t REC_VAR_OFF = 8 + IDASH_B200_CT_BYTES;
+
+namespace {
+
+double g_last_gpu_seconds = 0.0;
+
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+unsigned host_threads() {
+    if (const char *e = getenv("IDASH_HOST_THREADS")) { const int v = atoi(e); if (v > 0) return (unsigned) v; }
+    const unsigned hc = std::thread::hardware_concurrency();
+    return hc ? hc : 4u;
+}
+
+// runs fn(begin, end) over [0, n) split into contiguous ranges, one per worker thread
+template <class F>
+void parallel_ranges(size_t n, F fn) {
+    const size_t nt = std::max<size_t>(1, std::min<size_t>(host_threads(), n / 64 + 1));
+    if (nt == 1) { fn((size_t) 0, n); return; }
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nt; ++t) th.emplace_back([=]() { fn(n * t / nt, n * (t + 1) / nt); });
+    for (auto &x : th) x.join();
+}
+
+// Host staging memory: pinned through the library when a CUDA device is there; plain aligned memory otherwise, so
+// that the file-format half of this layer also works on a box without a GPU (the compute calls then fail loudly).
+struct HostBuf { void *p; bool pinned; };
+HostBuf host_buf_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (idash_b200_host_alloc(&p, bytes) == IDASH_B200_OK) return {p, true};
+    p = aligned_alloc(256, (bytes + 255) & ~(size_t) 255);
+    REQUIRE_DRAMATICALLY(p != nullptr, "out of host memory (" << bytes << " bytes)");
+    return {p, false};
+}
+void host_buf_free(void *p, bool pinned) {
+    if (!p) return;
+    if (pinned) idash_b200_host_free(p); else free(p);
+}
+
+// one context per process (one process per GPU)
+idash_b200_ctx *gpu_ctx() {
+    static idash_b200_ctx *ctx = nullptr;
+    if (!ctx) {
+        const int rc = idash_b200_init(&ctx, idash_host_device());
+        if (rc != IDASH_B200_OK) DIE_DRAMATICALLY("idash_b200_init: " << idash_b200_last_error());
+    }
+    return ctx;
+}
+
+void read_exact(std::istream &in, void *dst, size_t n, const char *what) {
+    in.read(static_cast<char *>(dst), (std::streamsize) n);
+    REQUIRE_DRAMATICALLY((size_t) in.gcount() == n, "truncated file while reading " << what);
+}
+
+// params stream: eval/idash.cpp:128-186 (writer), 200-261 (reader)
+void read_params_stream(IdashParams &p, std::istream &in) {
+    uint32_t head[7];
+    read_exact(in, head, sizeof(head), "params header");
+    p.NUM_SAMPLES = head[0]; p.NUM_INPUT_POSITIONS = head[1]; p.NUM_OUTPUT_POSITIONS = head[2];
+    p.NUM_INPUT_FEATURES = head[3]; p.NUM_OUTPUT_FEATURES = head[4]; p.NUM_REGIONS = head[5]; p.REGION_SIZE = head[6];
+    REQUIRE_DRAMATICALLY(p.NUM_REGIONS >= 1 && p.REGION_SIZE >= 1 && (uint64_t) p.NUM_REGIONS * p.REGION_SIZE <= IdashParams::N,
+                         "params: NUM_REGIONS x REGION_SIZE does not fit the polynomial");
+    std::vector<uint8_t> tags((size_t) p.NUM_INPUT_POSITIONS * 20u);     // packed {u64 pos, u32 bidx[3]}
+    if (!tags.empty()) read_exact(in, tags.data(), tags.size(), "tag positions");
+    for (uint32_t i = 0; i < p.NUM_INPUT_POSITIONS; ++i) {
+        uint64_t pos;
+        std::array<FeatBigIndex, 3> b;
+        memcpy(&pos, &tags[(size_t) i * 20u], 8);
+        memcpy(b.data(), &tags[(size_t) i * 20u + 8], 12);
+        p.in_features_index.emplace(pos, b);           // first occurrence wins, as with the reference's emplace
+    }
+    REQUIRE_DRAMATICALLY(p.NUM_INPUT_POSITIONS == p.in_features_index.size(), "NUM_INPUT_POSITIONS != in_features_index.size()");
+    for (uint32_t i = 0; i < p.NUM_OUTPUT_POSITIONS; ++i) {
+        uint64_t pos;
+        read_exact(in, &pos, 8, "target position");
+        string name;
+        std::getline(in, name, '\0');
+        REQUIRE_DRAMATICALLY(!in.fail(), "truncated file while reading target name");
+        std::array<FeatBigIndex, 3> b;
+        read_exact(in, b.data(), 12, "target indices");
+        p.out_position_names.push_back({pos, name});
+        p.out_features_index.emplace(pos, b);
+    }
+    REQUIRE_DRAMATICALLY(p.NUM_OUTPUT_POSITIONS == p.out_features_index.size(), "NUM_OUTPUT_POSITIONS != out_features_index.size()");
+    REQUIRE_DRAMATICALLY(p.NUM_OUTPUT_POSITIONS == p.out_position_names.size(), "NUM_OUTPUT_POSITIONS != out_position_names.size()");
+}
+
+// whole ciphertext file -> slab; checks the size and every record's TLWE type uid (tfhe_io.cpp:308 aborts on a bad one)
+std::shared_ptr<CtSlab> read_ct_file(const string &filename, const char *what) {
+    FILE *f = fopen(filename.c_str(), "rb");
+    REQUIRE_DRAMATICALLY(f != nullptr, "Cannot open encrypted " << what << " file for read");
+    uint64_t count = 0;
+    REQUIRE_DRAMATICALLY(fread(&count, 8, 1, f) == 1, "truncated encrypted " << what << " file");
+    REQUIRE_DRAMATICALLY(count < ((uint64_t) 1 << 32), "encrypted " << what << " file: implausible record count");
+    auto slab = std::make_shared<CtSlab>(count);
+    const size_t bytes = (size_t) count * REC;
+    REQUIRE_DRAMATICALLY(bytes == 0 || fread(slab->records(), 1, bytes, f) == bytes, "truncated encrypted " << what << " file");
+    fclose(f);
+    for (uint64_t i = 0; i < count; ++i) {
+        int32_t uid;
+        memcpy(&uid, slab->record(i) + 4, 4);
+        REQUIRE_DRAMATICALLY(uid == IDASH_B200_TLWE_SAMPLE_UID, "encrypted " << what << " file: bad TLWE sample type in record " << i);
+    }
+    slab->pull_variances();
+    return slab;
+}
+
+// map iteration order == slab slot order? then the slab image IS the file
+template <class Map>
+bool map_matches_slab(const Map &m, const std::shared_ptr<CtSlab> &slab) {
+    if (!slab || slab->count != m.size()) return false;
+    uint64_t k = 0;
+    for (const auto &it : m) {
+        if (it.second != &slab->samples[k] || slab->index_of(k) != it.first) return false;
+        ++k;
+    }
+    return true;
+}
+
+template <class Map>
+void write_ct_file(const Map &m, const std::shared_ptr<CtSlab> &slab, const string &filename, const char *what) {
+    FILE *f = fopen(filename.c_str(), "wb");
+    REQUIRE_DRAMATICALLY(f != nullptr, "Cannot open encrypted " << what << " file for write");
+    if (map_matches_slab(m, slab)) {
+        slab->push_variances();
+        const size_t n = slab->image_bytes();
+        REQUIRE_DRAMATICALLY(fwrite(slab->image(), 1, n, f) == n, "short write to encrypted " << what << " file");
+    } else {   // containers not built by this library: record by record, in the map's iteration order
+        const uint64_t count = m.size();
+        fwrite(&count, 8, 1, f);
+        std::vector<uint8_t> rec(REC);
+        const int32_t uid = IDASH_B200_TLWE_SAMPLE_UID;
+        for (const auto &it : m) {
+            const uint32_t idx = it.first;
+            memcpy(&rec[0], &idx, 4);
+            memcpy(&rec[4], &uid, 4);
+            memcpy(&rec[REC_WORDS_OFF], it.second->a[0].coefsT, 4096);
+            memcpy(&rec[REC_WORDS_OFF + 4096], it.second->a[1].coefsT, 4096);
+            memcpy(&rec[REC_VAR_OFF], &it.second->current_variance, 8);
+            REQUIRE_DRAMATICALLY(fwrite(rec.data(), 1, REC, f) == REC, "short write to encrypted " << what << " file");
+        }
+    }
+    REQUIRE_DRAMATICALLY(fclose(f) == 0, "error closing encrypted " << what << " file");
+}
+
+// pinned staging buffer for containers whose samples are not views into a slab
+struct PackedCts {
+    void *mem = nullptr;
+    bool pinned = false;
+    uint64_t count = 0;
+    uint32_t *words() const { return static_cast<uint32_t *>(mem); }
+    uint32_t *index() const { return words() + count * IDASH_B200_CT_WORDS; }
+    double *variance() const { return reinterpret_cast<double *>(static_cast<uint8_t *>(mem) + ((count * (IDASH_B200_CT_BYTES + 4u) + 7u) & ~(uint64_t) 7u)); }
+    explicit PackedCts(uint64_t n) : count(n) {
+        const size_t bytes = ((n * (IDASH_B200_CT_BYTES + 4u) + 7u) & ~(uint64_t) 7u) + n * 8u + 16u;
+        const HostBuf b = host_buf_alloc(bytes);
+        mem = b.p; pinned = b.pinned;
+    }
+    ~PackedCts() { host_buf_free(mem, pinned); }
+};
+
+template <class Map>
+std::unique_ptr<PackedCts> pack_map(const Map &m) {
+    std::unique_ptr<PackedCts> pk(new PackedCts(m.size()));
+    std::vector<std::pair<uint32_t, const TLweSample *>> v;
+    v.reserve(m.size());
+    for (const auto &it : m) v.push_back({it.first, it.second});
+    parallel_ranges(v.size(), [&](size_t b, size_t e) {
+        for (size_t i = b; i < e; ++i) {
+            memcpy(pk->words() + i * IDASH_B200_CT_WORDS, v[i].second->a[0].coefsT, 4096);
+            memcpy(pk->words() + i * IDASH_B200_CT_WORDS + 1024, v[i].second->a[1].coefsT, 4096);
+            pk->index()[i] = v[i].first;
+            pk->variance()[i] = v[i].second->current_variance;
+        }
+    });
+    return pk;
+}
+
+template <class Map>
+bool all_views_of(const Map &m, const std::shared_ptr<CtSlab> &slab) {
+    if (!slab || slab->count != m.size()) return false;
+    for (const auto &it : m) {
+        const int64_t s = slab->slot_of(it.second);
+        if (s < 0 || slab->index_of((uint64_t) s) != it.first) return false;
+    }
+    return true;
+}
+
+}  // namespace
+
+// ---- CtSlab ----------------------------------------------------------------------------------------------------
+CtSlab::CtSlab(uint64_t n) : count(n), samples(n), polys(2 * n) {
+    const HostBuf hb = host_buf_alloc(image_bytes() + 16);
+    mem = static_cast<uint8_t *>(hb.p);   // at least 256-byte aligned either way
+    pinned = hb.pinned;
+    memcpy(mem, &count, 8);
+    for (uint64_t i = 0; i < n; ++i) {
+        polys[2 * i].N = polys[2 * i + 1].N = (int32_t) IdashParams::N;
+        polys[2 * i].coefsT = reinterpret_cast<Torus32 *>(record(i) + REC_WORDS_OFF);
+        polys[2 * i + 1].coefsT = polys[2 * i].coefsT + IdashParams::N;
+        samples[i].a = &polys[2 * i];
+        samples[i].b = &polys[2 * i + 1];
+        samples[i].current_variance = 0.0;
+        samples[i].k = (int32_t) IdashParams::k;
+    }
+}
+CtSlab::~CtSlab() { host_buf_free(mem, pinned); }
+uint32_t CtSlab::index_of(uint64_t i) const { uint32_t v; memcpy(&v, record(i), 4); return v; }
+void CtSlab::pull_variances() { for (uint64_t i = 0; i < count; ++i) memcpy(&samples[i].current_variance, record(i) + REC_VAR_OFF, 8); }
+void CtSlab::push_variances() { for (uint64_t i = 0; i < count; ++i) memcpy(record(i) + REC_VAR_OFF, &samples[i].current_variance, 8); }
+
+// ---- files -----------------------------------------------------------------------------------------------------
+// NOTE: none of the reference-visible hash maps is reserve()d anywhere in this file: their bucket counts, hence their
+// iteration order, must evolve exactly as in the reference, because that order is the record order of the files it
+// writes (eval/idash.cpp:550, 607) and the row order of the model walk (eval/idash.cpp:772).
+void read_params(IdashParams &params, const string &filename) {
+    std::ifstream in(filename.c_str(), std::ios::binary);
+    REQUIRE_DRAMATICALLY(in.is_open(), "Cannot open parameters file for read");
+    read_params_stream(params, in);
+}
+
+// keys.bin = params stream, TLWEPARAMS text block, i32 85, N key bits (eval/idash.cpp:476-502, tfhe_io.cpp:243-252, 395-436)
+void read_key(IdashKey &key, const string &filename) {
+    std::ifstream in(filename.c_str(), std::ios::binary);
+    REQUIRE_DRAMATICALLY(in.is_open(), "Cannot open key file for read");
+    IdashParams *params = new IdashParams();
+    read_params_stream(*params, in);
+    key.idashParams = params;
+    int64_t N = -1, k = -1;
+    double a_min = 0, a_max = 0;
+    string line;
+    REQUIRE_DRAMATICALLY(std::getline(in, line) && line == "-----BEGIN TLWEPARAMS-----", "key file: TLWEPARAMS block not found");
+    for (;;) {
+        REQUIRE_DRAMATICALLY((bool) std::getline(in, line), "key file: unterminated TLWEPARAMS block");
+        if (line == "-----END TLWEPARAMS-----") break;
+        const size_t c = line.find(": ");
+        if (c == string::npos) continue;
+        const string name = line.substr(0, c), val = line.substr(c + 2);
+        if (name == "N") N = atoll(val.c_str());
+        else if (name == "k") k = atoll(val.c_str());
+        else if (name == "alpha_min") a_min = atof(val.c_str());
+        else if (name == "alpha_max") a_max = atof(val.c_str());
+    }
+    REQUIRE_DRAMATICALLY(N == (int64_t) IdashParams::N && k == 1, "key file: unsupported TLWE parameters N=" << N << " k=" << k);
+    int32_t uid = 0;
+    read_exact(in, &uid, 4, "key type");
+    REQUIRE_DRAMATICALLY(uid == 85, "key file: bad TLWE key type");         // TLWE_KEY_TYPE_UID, tfhe_generic_streams.h:27
+    TLweParams *tp = new TLweParams{(int32_t) N, (int32_t) k, a_min, a_max};
+    IntPolynomial *poly = new IntPolynomial{(int32_t) N, new int32_t[N]};
+    read_exact(in, poly->coefs, sizeof(int32_t) * (size_t) N, "key bits");
+    key.tlweKey = new TLweKey{tp, poly};
+}
+
+void read_encrypted_data(EncryptedData &d, const IdashParams &, const string &filename) {
+    d.slab = read_ct_file(filename, "data");
+    for (uint64_t i = 0; i < d.slab->count; ++i) d.enc_data.emplace(d.slab->index_of(i), &d.slab->samples[i]);
+}
+
+void read_encrypted_predictions(EncryptedPredictions &p, const IdashParams &, const string &filename) {
+    p.slab = read_ct_file(filename, "predictions");
+    for (uint64_t i = 0; i < p.slab->count; ++i) p.score.emplace(p.slab->index_of(i), &p.slab->samples[i]);
+}
+
+void write_encrypted_data(const EncryptedData &d, const IdashParams &, const string &filename) {
+    write_ct_file(d.enc_data, d.slab, filename, "data");
+}
+
+void write_encrypted_predictions(const EncryptedPredictions &p, const IdashParams &, const string &filename) {
+    write_ct_file(p.score, p.slab, filename, "predictions");
+}
+
+// eval/idash.cpp:66-90. The .hr files are parsed by a pool of threads (3 x NUM_OUTPUT_POSITIONS small files);
+// the model map is then filled in the reference's order (iteration order of out_features_index, variant 0..2),
+// which fixes the record order of encrypted_prediction.bin downstream.
+void read_model(Model &model, const IdashParams &params, const string &path) {
+    struct Job { uint64_t pos; std::array<FeatBigIndex, 3> out; };
+    std::vector<Job> jobs;
+    jobs.reserve(params.out_features_index.size());
+    for (const auto &e : params.out_features_index) jobs.push_back({e.first, e.second});
+    std::vector<std::array<std::vector<std::pair<FeatBigIndex, int32_t>>, 3>> parsed(jobs.size());
+    std::atomic<bool> unknown(false);
+    parallel_ranges(jobs.size(), [&](size_t b, size_t e) {
+        for (size_t i = b; i < e; ++i) {
+            for (int snp = 0; snp < 3; ++snp) {
+                const string fn = path + "/" + std::to_string(jobs[i].pos) + "_" + std::to_string(snp) + ".hr";
+                auto &dst = parsed[i][snp];
+                for (const auto &c : read_lines(fn)) {
+                    if (c.first == "Constant") { dst.push_back({params.constant_bigIndex(), c.second}); continue; }
+                    const size_t u = c.first.find('_');
+                    char *end = nullptr;
+                    const uint64_t pos = strtoull(c.first.c_str(), &end, 10);
+                    const auto it = params.in_features_index.find(pos);
+                    const long v = u == string::npos ? -1 : strtol(c.first.c_str() + u + 1, nullptr, 10);
+                    if (it == params.in_features_index.end() || v < 0 || v > 2) { unknown = true; continue; }
+                    dst.push_back({it->second[(size_t) v], c.second});
+                }
+            }
+        }
+    });
+    // the reference throws std::out_of_range (uncaught -> abort) on a tag position that params.bin does not know
+    REQUIRE_DRAMATICALLY(!unknown, "model refers to a tag SNP feature that is not in the parameters file");
+    for (size_t i = 0; i < jobs.size(); ++i) {
+        for (int snp = 0; snp < 3; ++snp) {
+            auto &row = model.model[jobs[i].out[snp]] = std::unordered_map<FeatBigIndex, int32_t>();
+            for (const auto &c : parsed[i][snp]) row[c.first] = c.second;     // a repeated name overwrites, as in parse_vw
+        }
+    }
+}
+
+// eval/idash.cpp:436-469: header, then for every sample, for every target in file order, "<sample>,<target>,<p0>,<p1>,<p2>".
+// Floats print like `ostream << float` (%g with 6 significant digits). Formatted by a pool of threads into per-range
+// buffers and written with large writes instead of one flush per row.
+void write_decrypted_predictions(const DecryptedPredictions &predictions, const IdashParams &params, const string &filename,
+                                 const bool PRINT_POS_NAME) {
+    FILE *f = fopen(filename.c_str(), "wb");
+    REQUIRE_DRAMATICALLY(f != nullptr, "Cannot open result file for write");
+    fputs("Subject ID,target SNP,0,1,2\n", f);
+    const size_t G = params.out_position_names.size();
+    std::vector<const std::array<std::vector<float>, 3> *> rows(G);
+    std::vector<string> labels(G);
+    for (size_t g = 0; g < G; ++g) {
+        rows[g] = &predictions.score.at(params.out_position_names[g].first);
+        labels[g] = PRINT_POS_NAME ? params.out_position_names[g].second : std::to_string(params.out_position_names[g].first);
+    }
+    const size_t S = params.NUM_SAMPLES;
+    const size_t batch = std::max<size_t>(1, std::min<size_t>(S, (size_t) host_threads() * 4));
+    std::vector<string> bufs(batch);
+    for (size_t s0 = 0; s0 < S; s0 += batch) {
+        const size_t nb = std::min(batch, S - s0);
+        parallel_ranges(nb, [&](size_t b, size_t e) {
+            char tmp[96];
+            for (size_t i = b; i < e; ++i) {
+                string &out = bufs[i];
+                out.clear();
+                const string sid = std::to_string(s0 + i);
+                for (size_t g = 0; g < G; ++g) {
+                    const auto &r = *rows[g];
+                    out += sid; out += ','; out += labels[g]; out += ',';
+                    const int n = snprintf(tmp, sizeof(tmp), "%g,%g,%g\n", (double) r[0][s0 + i], (double) r[1][s0 + i], (double) r[2][s0 + i]);
+                    out.append(tmp, (size_t) n);
+                }
+            }
+        });
+        for (size_t i = 0; i < nb; ++i)
+            REQUIRE_DRAMATICALLY(fwrite(bufs[i].data(), 1, bufs[i].size(), f) == bufs[i].size(), "short write to result file");
+    }
+    REQUIRE_DRAMATICALLY(fclose(f) == 0, "error closing result file");
+}
+
+// ---- the two GPU stages ----------------------------------------------------------------------------------------
+int idash_host_device() {
+    if (const char *e = getenv("IDASH_B200_DEVICE")) return atoi(e);
+    if (const char *e = getenv("LOCAL_RANK")) return atoi(e);
+    return 0;
+}
+double idash_host_last_gpu_seconds() { return g_last_gpu_seconds; }
+
+void cloud_compute_score(EncryptedPredictions &enc_preds, const EncryptedData &enc_data, const Model &model, const IdashParams &params) {
+    REQUIRE_DRAMATICALLY(params.k == 1, "blah");                                        // eval/idash.cpp:768
+    REQUIRE_DRAMATICALLY(enc_preds.score.empty(), "shit happens again");                // createAndGet, eval/idash.h:181
+    const uint64_t n_rows = model.model.size();
+
+    // Model -> CSR, rows in the map's iteration order (the order the reference walks them, eval/idash.cpp:772-777)
+    std::vector<uint32_t> out_bidx(n_rows), col;
+    std::vector<uint64_t> row_ptr(n_rows + 1, 0);
+    std::vector<int32_t> coef;
+    {
+        uint64_t r = 0, nnz = 0;
+        for (const auto &row : model.model) nnz += row.second.size();
+        col.reserve(nnz); coef.reserve(nnz);
+        for (const auto &row : model.model) {
+            out_bidx[r] = row.first;
+            for (const auto &c : row.second) {
+                if (c.first != params.constant_bigIndex())
+                    (void) enc_data.getTLWE(c.first, params);                           // dies like the reference on a missing input
+                col.push_back(c.first); coef.push_back(c.second);
+            }
+            row_ptr[++r] = col.size();
+        }
+    }
+
+    // outputs: one slab; the map is filled in the reference's insertion order, then record slot k goes to the k-th
+    // element in ITERATION order, so that the slab is the image of encrypted_prediction.bin (eval/idash.cpp:607)
+    auto slab = std::make_shared<CtSlab>(n_rows);
+    for (uint64_t r = 0; r < n_rows; ++r) enc_preds.score.emplace(out_bidx[r], nullptr);
+    {
+        uint64_t k = 0;
+        for (auto &it : enc_preds.score) it.second = &slab->samples[k++];
+    }
+    std::vector<uint32_t> slot_of_row(n_rows);
+    for (uint64_t r = 0; r < n_rows; ++r) slot_of_row[r] = (uint32_t) slab->slot_of(enc_preds.score.at(out_bidx[r]));
+    enc_preds.slab = slab;
+
+    idash_b200_ctx *ctx = gpu_ctx();
+    const double t0 = now_s();
+    idash_b200_model_desc desc;
+    desc.num_samples = params.NUM_SAMPLES; desc.num_regions = params.NUM_REGIONS; desc.region_size = params.REGION_SIZE;
+    desc.n_rows = n_rows; desc.out_bidx = out_bidx.data(); desc.row_ptr = row_ptr.data(); desc.col = col.data(); desc.coef = coef.data();
+    idash_b200_model *dm = nullptr;
+    if (idash_b200_model_upload(ctx, &desc, &dm) != IDASH_B200_OK) DIE_DRAMATICALLY("idash_b200_model_upload: " << idash_b200_last_error());
+
+    idash_b200_cts in, out;
+    std::unique_ptr<PackedCts> staged;
+    if (all_views_of(enc_data.enc_data, enc_data.slab)) {
+        enc_data.slab->push_variances();
+        in = {IDASH_B200_LAYOUT_RECORDS, enc_data.slab->records(), enc_data.slab->count, nullptr, nullptr};
+    } else {
+        staged = pack_map(enc_data.enc_data);
+        in = {IDASH_B200_LAYOUT_PACKED, staged->words(), staged->count, staged->index(), staged->variance()};
+    }
+    out = {IDASH_B200_LAYOUT_RECORDS, slab->records(), n_rows, nullptr, nullptr};
+    const int rc = idash_b200_cloud_eval_host(ctx, dm, &in, &out, slot_of_row.data());
+    if (rc != IDASH_B200_OK) DIE_DRAMATICALLY("idash_b200_cloud_eval_host: " << idash_b200_last_error());
+    idash_b200_model_free(dm);
+    g_last_gpu_seconds = now_s() - t0;
+    slab->pull_variances();
+}
+
+void decrypt_predictions(DecryptedPredictions &predictions, const EncryptedPredictions &enc_preds, const IdashKey &key) {
+    const IdashParams &params = *key.idashParams;
+    const uint32_t S = params.NUM_SAMPLES;
+    REQUIRE_DRAMATICALLY(key.tlweKey && key.tlweKey->params->N == (int32_t) IdashParams::N && key.tlweKey->params->k == 1,
+                         "unsupported TLWE key");
+    idash_b200_cts in;
+    std::unique_ptr<PackedCts> staged;
+    std::unordered_map<FeatBigIndex, uint64_t> slot;      // output bigIndex -> ciphertext slot in `in`
+    slot.reserve(enc_preds.score.size());
+    if (all_views_of(enc_preds.score, enc_preds.slab)) {
+        in = {IDASH_B200_LAYOUT_RECORDS, enc_preds.slab->records(), enc_preds.slab->count, nullptr, nullptr};
+        for (const auto &it : enc_preds.score) slot.emplace(it.first, (uint64_t) enc_preds.slab->slot_of(it.second));
+    } else {
+        staged = pack_map(enc_preds.score);
+        in = {IDASH_B200_LAYOUT_PACKED, staged->words(), staged->count, staged->index(), staged->variance()};
+        for (uint64_t i = 0; i < staged->count; ++i) slot.emplace(staged->index()[i], i);
+    }
+    const HostBuf sb = host_buf_alloc(std::max<size_t>(16, (size_t) in.count * S * sizeof(float)));
+    float *scores = static_cast<float *>(sb.p);
+    const double t0 = now_s();
+    const int rc = idash_b200_decrypt_host(gpu_ctx(), key.tlweKey->key[0].coefs, S, &in, scores, nullptr);
+    if (rc != IDASH_B200_OK) DIE_DRAMATICALLY("idash_b200_decrypt_host: " << idash_b200_last_error());
+    g_last_gpu_seconds = now_s() - t0;
+
+    // fan out into score[pos][snp] (eval/idash.cpp:689-696, 714-719); a missing output dies like .at()
+    struct Dst { std::array<std::vector<float>, 3> *v; std::array<uint64_t, 3> s; };
+    std::vector<Dst> dst;
+    dst.reserve(params.out_features_index.size());
+    for (const auto &it : params.out_features_index) {
+        auto &v = predictions.score[it.first];
+        Dst d{&v, {0, 0, 0}};
+        for (int snp = 0; snp < 3; ++snp) {
+            const auto s = slot.find(it.second[snp]);
+            REQUIRE_DRAMATICALLY(s != slot.end(), "encrypted predictions lack output feature " << it.second[snp]);
+            d.s[snp] = s->second;
+        }
+        dst.push_back(d);
+    }
+    parallel_ranges(dst.size(), [&](size_t b, size_t e) {
+        for (size_t i = b; i < e; ++i)
+            for (int snp = 0; snp < 3; ++snp) (*dst[i].v)[snp].assign(scores + dst[i].s[snp] * S, scores + (dst[i].s[snp] + 1) * S);
+    });
+    host_buf_free(sb.p, sb.pinned);
+}
+
+// ---- Profiler (eval/idash.cpp:935-965) -------------------------------------------------------------------------
+Profiler::Profiler() : tw0(universalWallTime()), tc0(universalClockTime()) {}
+double Profiler::universalWallTime() {
+    struct timeval tv;
+    return gettimeofday(&tv, nullptr) ? 0.0 : (double) tv.tv_sec + 1e-6 * (double) tv.tv_usec;
+}
+double Profiler::universalClockTime() { return (double) clock() / CLOCKS_PER_SEC; }
+double Profiler::walltime() const { return universalWallTime() - tw0; }
+double Profiler::clocktime() const { return universalClockTime() - tc0; }
+long int Profiler::maxrss() const {
+    struct rusage u;
+    return getrusage(RUSAGE_SELF, &u) ? -1 : u.ru_maxrss * 1000;
+}

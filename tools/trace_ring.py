@@ -1,18 +1,20 @@
 #!/usr/bin/env python
-"""Prints the per-tile timeline recorded by IDASH_B200_TRACE (cycles relative to the first event).
-events: 0 mma iteration start, 1 t_empty seen (lane 0), 2 b_full seen (lane 1), 3 after all waits + fence,
-        4 after MMA/commit issue, 5 first new a_full seen (lane 2; blank if none), 6 epilogue after t_full, 7 epilogue done"""
+"""Prints the per-tile timeline recorded by IDASH_B200_TRACE (SM cycles relative to the first event).
+MMA warp: it0 loop top, te/bf/af = time lane 0 / 1 / 2 saw t_empty / b_full / first new a_full complete (-1: nothing to wait
+for), waits = all waits done, issued = after the tile's MMAs and commit were issued. Epilogue warp 0: e_go = t_full seen,
+e_done = tile stored. pub = publisher saw t_full. b_copy = coefficient loader issued the tile's bulk copy."""
 import sys
 import numpy as np
 a = np.loadtxt(sys.argv[1], dtype=np.uint64).astype(np.int64)
 t0 = a[a > 0].min()
 r = a - t0
-names = ["it0", "lane0ok", "synced", "fenced", "issued", "b_copy", "e_go", "e_done"]
 r[a == 0] = -1
-print("tile " + " ".join(f"{n:>8}" for n in names) + "   | mma_iter  epi_busy  epi_wait")
+names = ["it0", "te", "bf", "af", "waits", "issued", "e_go", "-", "e_done", "pub", "b_copy", "-"]
+cols = [0, 1, 2, 3, 4, 5, 6, 8, 9, 10]
+print("tile " + " ".join(f"{names[c]:>8}" for c in cols) + "   | mma_iter  epi_busy  epi_wait commit->e_go")
 for i in range(1, len(r) - 1):
     row = r[i]
-    print(f"{i:4d} " + " ".join(f"{v:8d}" for v in row) + f"   | {r[i+1][0]-row[0]:8d} {row[7]-row[6]:8d} {r[i+1][6]-row[7]:8d}")
+    print(f"{i:4d} " + " ".join(f"{row[c]:8d}" for c in cols) + f"   | {r[i+1][0]-row[0]:8d} {row[8]-row[6]:8d} {r[i+1][6]-row[8]:8d} {row[6]-row[5]:8d}")
 d = np.diff(r[:, 0])
-print("mean cycles per tile (mma loop):", d[5:-5].mean(), " epilogue busy mean:", (r[:, 7] - r[:, 6])[5:-5].mean(),
-      " issue phase mean:", (r[:, 4] - r[:, 3])[5:-5].mean())
+print("mean cycles per tile (mma loop):", d[5:-5].mean(), " epilogue busy mean:", (r[:, 8] - r[:, 6])[5:-5].mean(),
+      " issue phase mean:", (r[:, 5] - r[:, 4])[5:-5].mean(), " commit->e_go mean:", (r[:, 6] - r[:, 5])[5:-5].mean())
