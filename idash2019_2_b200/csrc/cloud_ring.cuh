@@ -24,12 +24,13 @@
 //     epilogue of tile t.
 #pragma once
 
-#define RG_THREADS 480
+#define RG_THREADS 512
 #define RG_EPI_WARPS 8
 #define RG_WARP_MMA 8
 #define RG_WARP_BLOAD 9
 #define RG_WARP_PROD 10
 #define RG_WARP_PUB 14
+#define RG_WARP_MMA2 15
 #define RG_BLOCK_BYTES (16u * TC_A_LBO)          // 4 planes x 4 feature groups x 1152 B = 18432
 #define RG_PLANE_BYTES (4u * TC_A_LBO)
 #define RG_MAX_SLOTS 9
@@ -318,8 +319,13 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                 if (lane == 0) mbar_arrive(&t_empty[st]);      // one arrival per epilogue warp
             }
         }
-    } else if (warp == RG_WARP_MMA) {
-        // ================= MMA issuer =================
+    } else if (warp == RG_WARP_MMA || warp == RG_WARP_MMA2) {
+        // ================= MMA issuers =================
+        // Two warps: warp RG_WARP_MMA issues the even tiles of the chunk (TMEM stage 0), RG_WARP_MMA2 the odd ones (stage 1).
+        // One issuing thread is a serial instruction stream of a few hundred instructions per tile (waits, operand set-up,
+        // MMAs, commit, ring bookkeeping) and was what bounded the tile rate; the two stages are independent chains, so
+        // they get one stream each. Both warps walk every tile to keep the ring state, but wait and issue only for their own.
+        const uint32_t q = warp == RG_WARP_MMA2 ? 1u : 0u;
         const uint32_t n_slots = p.n_slots, n_bstages = p.n_bstages;
         const uint64_t da_base = tc_desc(smem_u32(sA), TC_A_LBO, TC_A_SBO);
         const uint64_t db_base = tc_desc(smem_u32(sB), TC_B_LBO, TC_B_SBO);
@@ -327,6 +333,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
         uint32_t next_slot = 0, next_par = 0;       // slot / phase parity of the next input block to be staged
         uint32_t first_slot = 0;                    // slot of block T.a
         uint32_t bstage = 0, bpar = 0;              // coefficient ring position
+        uint32_t prev_fn = 0, prev_bt = 0, prev_slot = 0, prev_par = 0;   // new blocks of the previous tile: [prev_fn, prev_bt) from prev_slot
         RingWalk walk;
         walk.init(ring_hdr(hdr_s, 0).a);
         const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem, 0);
@@ -336,11 +343,17 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
             const bool has_next = t + 1 < t_end;
             const RingTile T = ring_hdr(hdr_s, it), Tn = ring_hdr(hdr_s, has_next ? it + 1u : it);
             const uint32_t st = it & 1u;
-            const uint32_t n_new = T.a + T.nb - walk.first_new(T);
-            if (lane == 0) RG_TRACE(0, it);
-            // all waits of this tile at once, one barrier per lane: lane 0 the TMEM stage, lane 1 the coefficient
-            // stage, lanes 2.. the input blocks this tile adds to the ring
-            {
+            const bool mine = st == q;
+            const uint32_t bt = T.a + T.nb;
+            const uint32_t fn = walk.first_new(T);
+            const uint32_t n_new = bt - fn;
+            if (mine) {
+                if (lane == 0) RG_TRACE(0, it);
+                // all waits of this tile at once, one barrier per lane: lane 0 the TMEM stage, lane 1 the coefficient stage,
+                // then the input blocks this tile adds to the ring, then those the previous tile (issued by the other warp)
+                // added and this tile uses
+                const uint32_t p_lo = max(T.a, prev_fn), p_hi = min(prev_bt, bt);
+                const uint32_t n_prev = p_hi > p_lo ? p_hi - p_lo : 0u;
                 uint64_t *bar = nullptr;
                 uint32_t par = 0;
                 if (lane == 0) { bar = &t_empty[st]; par = ((it >> 1) & 1u) ^ 1u; }
@@ -348,6 +361,11 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                 else if (lane - 2u < n_new) {
                     uint32_t s = next_slot + (lane - 2u);
                     par = next_par;
+                    if (s >= n_slots) { s -= n_slots; par ^= 1u; }
+                    bar = &a_full[s];
+                } else if (lane - 2u - n_new < n_prev) {
+                    uint32_t s = prev_slot + (p_lo - prev_fn) + (lane - 2u - n_new);
+                    par = prev_par;
                     if (s >= n_slots) { s -= n_slots; par ^= 1u; }
                     bar = &a_full[s];
                 }
@@ -366,8 +384,10 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                     if (lane == 2) RG_TRACE_V(3, it, t_done);
                 }
             }
+            prev_fn = fn; prev_bt = bt; prev_slot = next_slot; prev_par = next_par;
             next_slot += n_new;
             if (next_slot >= n_slots) { next_slot -= n_slots; next_par ^= 1u; }
+            if (mine) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (p.tune & 8u) {
                 // warp-converged issue: every operand is made provably warp-uniform (shuffle from lane 0), so that the
@@ -401,6 +421,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                 RG_TRACE(5, it);
             }
             __syncwarp();
+            }
             if (++bstage == n_bstages) { bstage = 0; bpar ^= 1u; }
             uint32_t rb, re;
             walk.advance(T, Tn, has_next, rb, re);
@@ -456,61 +477,80 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
         const uint32_t ptid = tid - RG_WARP_PROD * 32u;
         const uint32_t mg = ptid & 7u, k0 = ptid >> 3;          // this thread stages features k0 and k0 + 16 of a block
         uint32_t slot = 0, seq = 0;
-        RingWalk walk;
-        walk.init(ring_hdr(hdr_s, 0).a);
-        for (uint32_t t = t_begin; t < t_end; ++t) {
-            const uint32_t it = t - t_begin;
-            const RingTile T = ring_hdr(hdr_s, it), Tn = ring_hdr(hdr_s, t + 1 < t_end ? it + 1u : it);
-            const uint32_t bt = T.a + T.nb;
-            for (uint32_t kb = walk.first_new(T); kb < bt; ++kb, ++seq) {
-                // issue the global loads before waiting for the slot: they do not depend on it
-                uint4 w[2][4];
-                const uint32_t used_word = kb < p.n_feat_words ? __ldg(p.feat_used + kb) : 0u;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t k = k0 + 16u * h;
-                    const uint32_t ct = kb * 32u + k;
-                    uint32_t sl = NO_SLOT;
-                    if (ct < p.n_ct_slots) sl = p.slot_of_ct ? __ldg(p.slot_of_ct + ct) : ct;
-                    if (p.knockout & 8u) sl = NO_SLOT;
-                    if (sl == NO_SLOT) {
-                        if (((used_word >> k) & 1u) && !(p.knockout & 8u)) atomicOr(p.status, 1);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) w[h][q] = make_uint4(0, 0, 0, 0);
-                    } else {
-                        const uint8_t *src = p.in.words + (uint64_t) sl * p.in.stride + 4u * (w_slice + mg * 16u);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) w[h][q] = ldg128(src + 16 * q);
-                    }
-                }
-                // the slot's previous block (staged n_slots blocks ago) must have been released
-                if (seq >= p.n_slots) progress_wait(&blocks_freed_s, seq - p.n_slots + 1u);
-                uint8_t *blk = sA + slot * RG_BLOCK_BYTES;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t k = k0 + 16u * h;
-                    uint32_t limb[4][4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const uint32_t x0 = __byte_perm(w[h][q].x, w[h][q].y, 0x5140), x1 = __byte_perm(w[h][q].x, w[h][q].y, 0x7362);
-                        const uint32_t x2 = __byte_perm(w[h][q].z, w[h][q].w, 0x5140), x3 = __byte_perm(w[h][q].z, w[h][q].w, 0x7362);
-                        limb[0][q] = __byte_perm(x0, x2, 0x5410);
-                        limb[1][q] = __byte_perm(x0, x2, 0x7632);
-                        limb[2][q] = __byte_perm(x1, x3, 0x5410);
-                        limb[3][q] = __byte_perm(x1, x3, 0x7632);
-                    }
-                    uint8_t *dst = blk + (k >> 3) * TC_A_LBO + mg * TC_A_SBO + (k & 7u) * 16u;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        *reinterpret_cast<uint4 *>(dst + j * RG_PLANE_BYTES) = make_uint4(limb[j][0], limb[j][1], limb[j][2], limb[j][3]);
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&a_full[slot]);      // one arrival per producer warp
-                if (++slot == p.n_slots) slot = 0;
+        // cursor over the input blocks of the chunk in staging order: tile by tile, the blocks [max(T.a, staged), T.a + T.nb)
+        uint32_t cur_it = 0, cur_kb = 0, cur_bt = 0, staged_upto = ring_hdr(hdr_s, 0).a;
+        auto next_block = [&]() -> uint32_t {
+            while (cur_kb >= cur_bt) {
+                if (cur_it >= n_my) return 0xFFFFFFFFu;
+                const RingTile T = ring_hdr(hdr_s, cur_it++);
+                cur_kb = max(T.a, staged_upto);
+                cur_bt = T.a + T.nb;
+                staged_upto = max(staged_upto, cur_bt);
             }
-            uint32_t rb, re;
-            walk.advance(T, Tn, t + 1 < t_end, rb, re);
+            return cur_kb++;
+        };
+        // global loads of one block: features k0 and k0 + 16, 16 words each
+        auto load_block = [&](uint32_t kb, uint4 (&w)[2][4]) {
+            const uint32_t used_word = kb < p.n_feat_words ? __ldg(p.feat_used + kb) : 0u;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t k = k0 + 16u * h;
+                const uint32_t ct = kb * 32u + k;
+                uint32_t sl = NO_SLOT;
+                if (ct < p.n_ct_slots) sl = p.slot_of_ct ? __ldg(p.slot_of_ct + ct) : ct;
+                if (p.knockout & 8u) sl = NO_SLOT;
+                if (sl == NO_SLOT) {
+                    if (((used_word >> k) & 1u) && !(p.knockout & 8u)) atomicOr(p.status, 1);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) w[h][q] = make_uint4(0, 0, 0, 0);
+                } else {
+                    const uint8_t *src = p.in.words + (uint64_t) sl * p.in.stride + 4u * (w_slice + mg * 16u);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) w[h][q] = ldg128(src + 16 * q);
+                }
+            }
+        };
+        // split into byte planes and store into the ring slot, once the slot's previous block has been released
+        auto store_block = [&](const uint4 (&w)[2][4]) {
+            if (seq >= p.n_slots) progress_wait(&blocks_freed_s, seq - p.n_slots + 1u);
+            uint8_t *blk = sA + slot * RG_BLOCK_BYTES;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t k = k0 + 16u * h;
+                uint32_t limb[4][4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t x0 = __byte_perm(w[h][q].x, w[h][q].y, 0x5140), x1 = __byte_perm(w[h][q].x, w[h][q].y, 0x7362);
+                    const uint32_t x2 = __byte_perm(w[h][q].z, w[h][q].w, 0x5140), x3 = __byte_perm(w[h][q].z, w[h][q].w, 0x7362);
+                    limb[0][q] = __byte_perm(x0, x2, 0x5410);
+                    limb[1][q] = __byte_perm(x0, x2, 0x7632);
+                    limb[2][q] = __byte_perm(x1, x3, 0x5410);
+                    limb[3][q] = __byte_perm(x1, x3, 0x7632);
+                }
+                uint8_t *dst = blk + (k >> 3) * TC_A_LBO + mg * TC_A_SBO + (k & 7u) * 16u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4 *>(dst + j * RG_PLANE_BYTES) = make_uint4(limb[j][0], limb[j][1], limb[j][2], limb[j][3]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[slot]);      // one arrival per producer warp
+            if (++slot == p.n_slots) slot = 0;
+            ++seq;
+        };
+        // Two blocks in flight per thread (register sets A and B, statically alternated): the loads of the next block are
+        // issued before the current one is split and stored, so the ~1 us HBM latency of a block overlaps the previous one.
+        uint4 wA[2][4], wB[2][4];
+        uint32_t kbA = next_block();
+        if (kbA != 0xFFFFFFFFu) load_block(kbA, wA);
+        while (kbA != 0xFFFFFFFFu) {
+            const uint32_t kbB = next_block();
+            if (kbB != 0xFFFFFFFFu) load_block(kbB, wB);
+            store_block(wA);
+            if (kbB == 0xFFFFFFFFu) break;
+            kbA = next_block();
+            if (kbA != 0xFFFFFFFFu) load_block(kbA, wA);
+            store_block(wB);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

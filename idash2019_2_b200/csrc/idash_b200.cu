@@ -587,10 +587,17 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
         p.n_tiles = (uint32_t) L->tiles.size();
         p.n_chunks = (uint32_t) c->sm_count / 16u;
         const uint32_t max_nb = L->tile_kmax / 32u;
-        p.n_slots = std::min<uint32_t>(RG_MAX_SLOTS, max_nb + 2u);
         p.b_stage_bytes = max_nb * TC_B_CHUNK;
         p.max_chunk_tiles = (p.n_tiles + p.n_chunks - 1u) / p.n_chunks + 1u;
-        p.n_bstages = std::min<uint32_t>(RG_MAX_BSTAGES, (RG_SMEM_MAX - p.n_slots * RG_BLOCK_BYTES - 4u * p.max_chunk_tiles) / p.b_stage_bytes);
+        // as many input-block slots as fit next to at least 4 (else 2) coefficient stages: slots beyond the widest tile
+        // (+ 2) are what lets the block producers run ahead of the MMAs
+        p.n_slots = RG_MAX_SLOTS;
+        const auto stages_for = [&](uint32_t slots) {
+            const uint32_t used = slots * RG_BLOCK_BYTES + 4u * p.max_chunk_tiles;
+            return used >= RG_SMEM_MAX ? 0u : (RG_SMEM_MAX - used) / p.b_stage_bytes;
+        };
+        while (p.n_slots > max_nb + 2u && stages_for(p.n_slots) < 4u) --p.n_slots;
+        p.n_bstages = std::min<uint32_t>(RG_MAX_BSTAGES, stages_for(p.n_slots));
         p.hdr_off = p.n_slots * RG_BLOCK_BYTES + p.n_bstages * p.b_stage_bytes;
         if (p.n_bstages < 2) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: internal: ring kernel shared-memory budget");
         p.in = in; p.out = out;
