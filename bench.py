@@ -124,19 +124,6 @@ def build_workload(args):
     return model
 
 
-def shard_rows(model, rank, world, n_targets):
-    """Contiguous target-SNP range of this rank; the model is re-based so that its first input ciphertext is 0."""
-    lo, hi = n_targets * rank // world, n_targets * (rank + 1) // world
-    sub = model.rows(3 * lo, 3 * hi)
-    real = sub.col != 0xFFFFFFFF
-    ct_min = int(sub.col[real].min()) if real.any() else 0      # NUM_REGIONS = 1: ct index == input bigIndex
-    ct_max = int(sub.col[real].max()) if real.any() else 0
-    col = sub.col.copy()
-    col[real] -= np.uint32(ct_min)
-    sub.col = col
-    return sub, ct_min, ct_max - ct_min + 1, (lo, hi)
-
-
 # ---------------------------------------------------------------------------------------------------
 def reference_sample_runner(args, model):
     """Returns (fn(sample_targets) -> seconds of the reference cloud_compute_score, kind, cores)."""
@@ -236,9 +223,9 @@ def run_b200(args):
     model = build_workload(args)
     NR = 1024 // args.samples
     RS = 1024 // NR
-    sub, ct_min, slab, (t_lo, t_hi) = shard_rows(model, rank, world, args.targets) if NR == 1 else (model, 0, 0, (0, args.targets))
-    if NR != 1:
-        slab = (3 * args.tags - 1) // NR + 1
+    from idash2019_2_b200 import shard as shard_mod
+    sh = shard_mod.make_shard(model, NR, args.targets, rank, world)     # contiguous target range + the input slab it reads
+    sub, slab, t_lo, t_hi = sh.model, sh.n_ct, sh.target_lo, sh.target_hi
     n_rows = sub.n_out
     n_batches = world
     ctx = api.Context(local_rank)
