@@ -44,7 +44,8 @@ struct RingParams {
     const uint8_t *tile_coef;
     const uint32_t *feat_used;     // bit f: feature f is used by some row
     uint32_t n_feat_words;
-    uint32_t n_tiles;
+    uint32_t n_tiles;              // tiles of this launch: [tile_base, tile_base + n_tiles)
+    uint32_t tile_base;
     uint32_t n_chunks;             // gridDim.x = 16 * n_chunks
     uint32_t n_slots;              // input-block ring slots (>= widest tile in blocks, + prefetch)
     uint32_t n_bstages;            // coefficient ring stages (one tile each)
@@ -229,8 +230,8 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t slice = blockIdx.x & 15u, chunk = blockIdx.x >> 4;
-    const uint32_t t_begin = (uint32_t) ((uint64_t) p.n_tiles * chunk / p.n_chunks);
-    const uint32_t t_end = (uint32_t) ((uint64_t) p.n_tiles * (chunk + 1) / p.n_chunks);
+    const uint32_t t_begin = p.tile_base + (uint32_t) ((uint64_t) p.n_tiles * chunk / p.n_chunks);
+    const uint32_t t_end = p.tile_base + (uint32_t) ((uint64_t) p.n_tiles * (chunk + 1) / p.n_chunks);
     if (t_begin >= t_end) return;
     uint8_t *sA = smem;
     uint8_t *sB = smem + p.n_slots * RG_BLOCK_BYTES;

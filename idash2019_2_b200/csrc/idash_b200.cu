@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(128) cloud_eval_kernel(const CloudParams p) {
 
 // Per caller row: output variance, record header / index array.
 struct FinalizeParams {
+    uint64_t row_lo;     // rows [row_lo, n_rows) of the model
     uint64_t n_rows;
     const uint64_t *var_ptr;
     const uint32_t *var_ct;
@@ -205,7 +206,7 @@ struct FinalizeParams {
 };
 
 __global__ void cloud_finalize_kernel(const FinalizeParams p) {
-    const uint64_t r = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t r = p.row_lo + (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= p.n_rows) return;
     double var = 0.;
     for (uint64_t e = p.var_ptr[r]; e < p.var_ptr[r + 1]; ++e) {
@@ -333,7 +334,14 @@ struct idash_b200_ctx {
     std::vector<cudaEvent_t> t_begin, t_end;   // per-launch timing of the dominant kernels (timing_enable)
     int t_used = 0;
     DevBuf in_buf, out_buf, slot_buf, row_slot_buf, aux_in_idx, aux_in_var, aux_out_idx, aux_out_var, scores_buf, phase_buf;
+    // pipelined host path (cloud_eval_host): copy-in / copy-out streams and per-piece events
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_k;
 };
+
+// A launch over part of the model: tiles [tile_lo, tile_hi) of the ring kernel = rows [row_lo, row_hi) (caller rows are
+// the sorted rows). `first`: also build the ciphertext-index -> slot table (once per evaluation).
+struct Piece { uint32_t tile_lo, tile_hi; uint64_t row_lo, row_hi; bool first; };
 
 struct idash_b200_model {
     idash_b200_layout *layout = nullptr;
@@ -350,6 +358,7 @@ struct idash_b200_model {
     uint8_t *d_tile_coef = nullptr;
     uint32_t *d_tile_used = nullptr;
     uint32_t *d_feat_used = nullptr;         // ring variant only
+    mutable int rows_identity = -1;          // cached: tile t holds exactly the caller rows 64 t .. (pipelined host path)
 };
 
 extern "C" int idash_b200_init(idash_b200_ctx **out, int device) {
@@ -384,6 +393,10 @@ extern "C" int idash_b200_destroy(idash_b200_ctx *c) {
     if (!c) return IDASH_B200_OK;
     cudaSetDevice(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
+    for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_k) cudaEventDestroy(e);
     DevBuf *bufs[] = {&c->in_buf, &c->out_buf, &c->slot_buf, &c->row_slot_buf, &c->aux_in_idx, &c->aux_in_var,
                       &c->aux_out_idx, &c->aux_out_var, &c->scores_buf, &c->phase_buf};
     for (DevBuf *b : bufs) b->release();
@@ -535,8 +548,10 @@ static int make_view(const idash_b200_cts *a, bool is_output, CtView *v, const c
     return IDASH_B200_OK;
 }
 
+static bool ring_selected(const idash_b200_ctx *c, const idash_b200_layout *L);
+
 static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtView &in, const CtView &out,
-                        const uint32_t *d_slot_of_row, cudaStream_t st) {
+                        const uint32_t *d_slot_of_row, cudaStream_t st, const Piece *piece = nullptr) {
     const idash_b200_layout *L = m->layout;
     if (out.count != L->n_rows) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: out->count (%llu) != model rows (%llu)",
                                                  (unsigned long long) out.count, (unsigned long long) L->n_rows);
@@ -552,10 +567,12 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
         n_ct_slots = has_entries ? L->ct_max + 1 : 1;
         int rc = c->slot_buf.ensure((size_t) n_ct_slots * 4);
         if (rc) return rc;
-        CUDA_TRY(cudaMemsetAsync(c->slot_buf.p, 0xFF, (size_t) n_ct_slots * 4, st));
-        if (in.count) {
-            slot_map_kernel<<<(unsigned) ((in.count + 255) / 256), 256, 0, st>>>(in, (uint32_t *) c->slot_buf.p, n_ct_slots);
-            c->launches++;
+        if (!piece || piece->first) {
+            CUDA_TRY(cudaMemsetAsync(c->slot_buf.p, 0xFF, (size_t) n_ct_slots * 4, st));
+            if (in.count) {
+                slot_map_kernel<<<(unsigned) ((in.count + 255) / 256), 256, 0, st>>>(in, (uint32_t *) c->slot_buf.p, n_ct_slots);
+                c->launches++;
+            }
         }
         d_slot_of_ct = (const uint32_t *) c->slot_buf.p;
     }
@@ -569,13 +586,10 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
         return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: the persistent ring kernel was requested but the model is not eligible "
                                                  "(needs NUM_REGIONS == 1, forward-moving bands of at most %u features)", IDASH_B200_RING_KMAX);
     const bool use_tc = tc_ok && c->kernel_choice != IDASH_B200_KERNEL_IMAD;
-    // the ring kernel keeps a 4-byte header per tile of a chunk in shared memory (first block in 20 bits)
-    const uint64_t ring_chunk_tiles = c->sm_count >= 16 ? (L->tiles.size() + c->sm_count / 16 - 1) / (c->sm_count / 16) + 1 : 0;
-    const bool ring_fits = c->sm_count >= 16 && ring_chunk_tiles * 4u <= 32768u &&
-                           (L->tiles.empty() || (L->tiles.back().f_base >> 5) + IDASH_B200_TILE_KMAX / 32u < (1u << RG_HDR_A_BITS));
-    if (c->kernel_choice == IDASH_B200_KERNEL_TENSOR_RING && L->ring_ok && !ring_fits)
+    if (c->kernel_choice == IDASH_B200_KERNEL_TENSOR_RING && L->ring_ok && !ring_selected(c, L))
         return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: the persistent ring kernel was requested but the model has too many tiles per chunk");
-    const bool use_ring = use_tc && L->ring_ok && ring_fits && c->kernel_choice != IDASH_B200_KERNEL_TENSOR_TILE;
+    const bool use_ring = ring_selected(c, L);
+    if (piece && !use_ring) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: internal: partial launches need the ring kernel");
     const bool timed = c->t_used < (int) c->t_begin.size();
     if (timed) CUDA_TRY(cudaEventRecord(c->t_begin[c->t_used], st));
     if (use_ring) {
@@ -584,7 +598,8 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
         p.tiles = m->d_tiles; p.tile_rows = m->d_tile_rows; p.tile_bias = m->d_tile_bias; p.tile_coef = m->d_tile_coef;
         p.feat_used = m->d_feat_used;
         p.n_feat_words = (uint32_t) L->feat_used.size();
-        p.n_tiles = (uint32_t) L->tiles.size();
+        p.n_tiles = piece ? piece->tile_hi - piece->tile_lo : (uint32_t) L->tiles.size();
+        p.tile_base = piece ? piece->tile_lo : 0u;
         p.n_chunks = (uint32_t) c->sm_count / 16u;
         const uint32_t max_nb = L->tile_kmax / 32u;
         p.b_stage_bytes = max_nb * TC_B_CHUNK;
@@ -670,7 +685,8 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
 
     FinalizeParams f;
     memset(&f, 0, sizeof(f));
-    f.n_rows = L->n_rows;
+    f.row_lo = piece ? piece->row_lo : 0;
+    f.n_rows = piece ? piece->row_hi : L->n_rows;
     f.var_ptr = m->d_var_ptr;
     f.var_ct = m->d_var_ct;
     f.var_w = m->d_var_w;
@@ -681,10 +697,19 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
     f.n_ct_slots = n_ct_slots;
     f.slot_of_row = d_slot_of_row;
     f.default_var = 8.8817841970012523e-16;   // alpha^2 = 2^-50 (eval/idash.cpp:20, tlwe-functions.cpp:38)
-    cloud_finalize_kernel<<<(unsigned) ((L->n_rows + 255) / 256), 256, 0, st>>>(f);
+    cloud_finalize_kernel<<<(unsigned) ((f.n_rows - f.row_lo + 255) / 256), 256, 0, st>>>(f);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return IDASH_B200_OK;
+}
+
+// Would launch_cloud pick the persistent ring kernel for this model under the ctx's kernel choice?
+static bool ring_selected(const idash_b200_ctx *c, const idash_b200_layout *L) {
+    if (L->tiles.empty() || !L->ring_ok || c->sm_count < 16) return false;
+    if (c->kernel_choice == IDASH_B200_KERNEL_IMAD || c->kernel_choice == IDASH_B200_KERNEL_TENSOR_TILE) return false;
+    // the ring kernel keeps a 4-byte header per tile of a chunk in shared memory (first block in 20 bits)
+    const uint64_t chunk_tiles = (L->tiles.size() + c->sm_count / 16 - 1) / (c->sm_count / 16) + 1;
+    return chunk_tiles * 4u <= 32768u && (L->tiles.back().f_base >> 5) + IDASH_B200_TILE_KMAX / 32u < (1u << RG_HDR_A_BITS);
 }
 
 extern "C" int idash_b200_cloud_eval_device(idash_b200_ctx *c, const idash_b200_model *m, const idash_b200_cts *in,
@@ -752,6 +777,116 @@ static int stage_in(idash_b200_ctx *c, const idash_b200_cts *a, DevBuf &buf, Dev
     return IDASH_B200_OK;
 }
 
+// Caller rows are already in tile order: tile t = rows [64 t, 64 t + n_valid), so a tile range writes a contiguous slot range.
+static bool rows_identity(const idash_b200_model *m) {
+    if (m->rows_identity < 0) {
+        const idash_b200_layout *L = m->layout;
+        bool ok = !L->tiles.empty();
+        for (size_t t = 0; ok && t < L->tiles.size(); ++t)
+            for (uint32_t i = 0; ok && i < IDASH_B200_TILE_ROWS; ++i) {
+                const uint32_t want = i < L->tiles[t].n_valid ? (uint32_t) (t * IDASH_B200_TILE_ROWS + i) : IDASH_B200_NO_ROW;
+                ok = L->tile_rows[t * IDASH_B200_TILE_ROWS + i] == want;
+            }
+        m->rows_identity = ok ? 1 : 0;
+    }
+    return m->rows_identity == 1;
+}
+
+// cloud_eval_host for the common big case (ring kernel, caller rows in sorted order, outputs in row order): the target
+// range is cut into pieces and the three engines run concurrently -- host->device copy of the input ciphertexts piece k+1
+// needs (copy-in stream), kernels of piece k (compute stream), device->host copy of the outputs of piece k-1 (copy-out
+// stream). PCIe is full duplex, so the input upload disappears behind the (5x larger) output download.
+static int cloud_eval_host_pipelined(idash_b200_ctx *c, const idash_b200_model *m, const idash_b200_cts *in, const idash_b200_cts *out) {
+    const idash_b200_layout *L = m->layout;
+    const uint32_t n_tiles = (uint32_t) L->tiles.size();
+    const uint32_t P = std::max<uint32_t>(1u, std::min<uint32_t>(8u, n_tiles / 64u));
+    if (!c->s_in) { CUDA_TRY(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking)); CUDA_TRY(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking)); }
+    while (c->ev_in.size() < P) {
+        cudaEvent_t a, b;
+        CUDA_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        c->ev_in.push_back(a); c->ev_k.push_back(b);
+    }
+    int rc;
+    CtView vin, vout;
+    const bool chunked_in = in->layout == IDASH_B200_LAYOUT_PACKED && !in->index;     // slot i holds ciphertext i
+    if (!chunked_in) {
+        if ((rc = stage_in(c, in, c->in_buf, c->aux_in_idx, c->aux_in_var, &vin, "cloud_eval_host(in)"))) return rc;
+    } else {
+        if (in->count && !in->data) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_host(in): null data pointer");
+        memset(&vin, 0, sizeof(vin));
+        vin.count = in->count;
+        if ((rc = c->in_buf.ensure((size_t) in->count * IDASH_B200_CT_BYTES + 16))) return rc;
+        vin.words = (uint8_t *) c->in_buf.p;
+        vin.stride = IDASH_B200_CT_BYTES;
+        if (in->variance) {
+            if ((rc = c->aux_in_var.ensure((size_t) in->count * 8 + 8))) return rc;
+            if (in->count) CUDA_TRY(cudaMemcpyAsync(c->aux_in_var.p, in->variance, (size_t) in->count * 8, cudaMemcpyHostToDevice, c->stream));
+            vin.variance = (double *) c->aux_in_var.p;
+        }
+    }
+    memset(&vout, 0, sizeof(vout));
+    vout.count = out->count;
+    const bool rec = out->layout == IDASH_B200_LAYOUT_RECORDS;
+    const size_t ostride = rec ? IDASH_B200_RECORD_BYTES : IDASH_B200_CT_BYTES;
+    if ((rc = c->out_buf.ensure((size_t) out->count * ostride + 32))) return rc;
+    if (rec) {
+        if (out->index || out->variance) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_host(out): index/variance must be NULL for the RECORDS layout");
+        vout.words = (uint8_t *) c->out_buf.p + 16; vout.stride = IDASH_B200_RECORD_BYTES; vout.records = 1;
+    } else {
+        vout.words = (uint8_t *) c->out_buf.p; vout.stride = IDASH_B200_CT_BYTES;
+        if (out->index) { if ((rc = c->aux_out_idx.ensure((size_t) out->count * 4 + 4))) return rc; vout.index = (uint32_t *) c->aux_out_idx.p; }
+        if (out->variance) { if ((rc = c->aux_out_var.ensure((size_t) out->count * 8 + 8))) return rc; vout.variance = (double *) c->aux_out_var.p; }
+    }
+    uint64_t uploaded = 0, need = 0;
+    uint32_t t_scan = 0;
+    for (uint32_t k = 0; k < P; ++k) {
+        Piece pc;
+        pc.tile_lo = (uint32_t) ((uint64_t) n_tiles * k / P);
+        pc.tile_hi = (uint32_t) ((uint64_t) n_tiles * (k + 1) / P);
+        pc.row_lo = (uint64_t) pc.tile_lo * IDASH_B200_TILE_ROWS;
+        pc.row_hi = std::min<uint64_t>(L->n_rows, (uint64_t) pc.tile_hi * IDASH_B200_TILE_ROWS);
+        pc.first = k == 0;
+        if (chunked_in) {
+            for (; t_scan < pc.tile_hi; ++t_scan) need = std::max<uint64_t>(need, (uint64_t) L->tiles[t_scan].f_base + L->tiles[t_scan].K);   // NUM_REGIONS == 1
+            const uint64_t upto = std::min<uint64_t>(need, in->count);
+            if (upto > uploaded) {
+                CUDA_TRY(cudaMemcpyAsync((uint8_t *) c->in_buf.p + uploaded * IDASH_B200_CT_BYTES, (const uint8_t *) in->data + uploaded * IDASH_B200_CT_BYTES,
+                                         (upto - uploaded) * IDASH_B200_CT_BYTES, cudaMemcpyHostToDevice, c->s_in));
+                uploaded = upto;
+            }
+            CUDA_TRY(cudaEventRecord(c->ev_in[k], c->s_in));
+            CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_in[k], 0));
+        }
+        if ((rc = launch_cloud(c, m, vin, vout, nullptr, c->stream, &pc))) { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_out); return rc; }
+        CUDA_TRY(cudaEventRecord(c->ev_k[k], c->stream));
+        CUDA_TRY(cudaStreamWaitEvent(c->s_out, c->ev_k[k], 0));
+        const uint64_t nr = pc.row_hi - pc.row_lo;
+        if (nr) {
+            if (rec) {
+                CUDA_TRY(cudaMemcpyAsync((uint8_t *) out->data + pc.row_lo * ostride, (uint8_t *) c->out_buf.p + 8 + pc.row_lo * ostride, nr * ostride, cudaMemcpyDeviceToHost, c->s_out));
+            } else {
+                CUDA_TRY(cudaMemcpyAsync((uint8_t *) out->data + pc.row_lo * ostride, (uint8_t *) c->out_buf.p + pc.row_lo * ostride, nr * ostride, cudaMemcpyDeviceToHost, c->s_out));
+            }
+        }
+    }
+    // the small per-row arrays go last, in one piece: callers often pass pageable memory for them, and a copy to pageable
+    // memory blocks the host thread, which would stop the pieces above from being enqueued ahead of the GPU
+    if (!rec && out->count) {
+        if (out->index) CUDA_TRY(cudaMemcpyAsync(out->index, vout.index, (size_t) out->count * 4, cudaMemcpyDeviceToHost, c->s_out));
+        if (out->variance) CUDA_TRY(cudaMemcpyAsync(out->variance, vout.variance, (size_t) out->count * 8, cudaMemcpyDeviceToHost, c->s_out));
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->s_out));
+    CUDA_TRY(cudaStreamSynchronize(c->s_in));
+    if (*c->h_status) {
+        CUDA_TRY(cudaMemset(c->d_status, 0, sizeof(int)));
+        return set_error(IDASH_B200_ERR_MISSING_INPUT, "cloud_eval: the model references an input ciphertext that was not supplied");
+    }
+    return IDASH_B200_OK;
+}
+
 extern "C" int idash_b200_cloud_eval_host(idash_b200_ctx *c, const idash_b200_model *m, const idash_b200_cts *in,
                                           const idash_b200_cts *out, const uint32_t *slot_of_row) {
     clear_error();
@@ -762,6 +897,10 @@ extern "C" int idash_b200_cloud_eval_host(idash_b200_ctx *c, const idash_b200_mo
     if (out->count != L->n_rows) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_host: out->count (%llu) != model rows (%llu)",
                                                   (unsigned long long) out->count, (unsigned long long) L->n_rows);
     if (out->count && !out->data) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_host: null output data pointer");
+    if (out->layout != IDASH_B200_LAYOUT_PACKED && out->layout != IDASH_B200_LAYOUT_RECORDS)
+        return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_host(out): unknown layout %d", out->layout);
+    if (!slot_of_row && L->tiles.size() >= 128 && in->count < NO_SLOT && ring_selected(c, L) && rows_identity(m) && !getenv("IDASH_B200_NO_PIPELINE"))
+        return cloud_eval_host_pipelined(c, m, in, out);
     int rc;
     CtView vin, vout;
     if ((rc = stage_in(c, in, c->in_buf, c->aux_in_idx, c->aux_in_var, &vin, "cloud_eval_host(in)"))) return rc;

@@ -235,3 +235,37 @@ def test_cloud_device_path_linearity_at_scale(kctx):
     assert np.array_equal(outs[0].cpu().numpy().view(np.uint32)[rows], ref_out)
     _used(kctx)
     m.free()
+
+
+@pytest.mark.parametrize("n", [5, 20])
+def test_cloud_host_path_pipelined_pieces(gpu_ctx, n, monkeypatch):
+    """Large-enough models take the pipelined host path (pieces of the target range; copy-in, kernels and copy-out on
+    three streams): PACKED with variances and RECORDS outputs must equal the oracle and the unpipelined path, and a
+    missing input ciphertext must still be reported."""
+    S, T, G = 1004, 800, 3200                      # 9600 rows = 150 tiles -> pipelined (>= 128 tiles)
+    geo, model, cts, var = make_case(S, T=T, G=G, n=n, seed=77 + n)
+    var = var * (1.0 + np.arange(len(var)) % 3)    # not all equal
+    m = api.Model(gpu_ctx, S, geo.NR, geo.RS, model.out_bidx, model.row_ptr, model.col, model.coef)
+    assert m.info["ring_ok"] and m.info["n_tiles"] >= 128
+    ref_out, ref_var = _oracle(S, geo, model, cts, var)
+    out, idx, ovar = api.cloud_compute_score(gpu_ctx, m, cts, in_var=var)
+    assert gpu_ctx.last_kernel() == _lib.KERNEL_TENSOR_RING
+    assert np.array_equal(out, ref_out) and np.array_equal(ovar, ref_var) and np.array_equal(idx, model.out_bidx)
+    # RECORDS in (hash-like permuted order: whole upload, pipelined download) and RECORDS out
+    perm = np.random.default_rng(3).permutation(len(cts))
+    img = formats.build_ct_image(perm.astype(np.uint32), cts[perm], var[perm])
+    pred = api.cloud_compute_score_records(gpu_ctx, m, img)
+    pi, pw, pv = formats.image_views(pred)
+    assert np.array_equal(pi, model.out_bidx) and np.array_equal(pw, ref_out) and np.array_equal(pv, ref_var)
+    # same call with the pipeline switched off
+    monkeypatch.setenv("IDASH_B200_NO_PIPELINE", "1")
+    out2, _, ovar2 = api.cloud_compute_score(gpu_ctx, m, cts, in_var=var)
+    monkeypatch.delenv("IDASH_B200_NO_PIPELINE")
+    assert np.array_equal(out2, out) and np.array_equal(ovar2, ovar)
+    # too few input ciphertexts: the model's last tiles reference slots that were not supplied
+    with pytest.raises(api.IdashB200Error) as e:
+        api.cloud_compute_score(gpu_ctx, m, cts[: len(cts) - 40], in_var=var[: len(cts) - 40])
+    assert e.value.code == _lib.ERR_MISSING_INPUT
+    out3, _, _ = api.cloud_compute_score(gpu_ctx, m, cts, in_var=var)     # the context stays usable
+    assert np.array_equal(out3, ref_out)
+    m.free()
