@@ -117,6 +117,18 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
 
 
+def ncu_traffic(kernel: str, args, world: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture
+    of this same workload (profiles/traffic.json, written from the .ncu-rep by tools/ncu_summary.py), or None."""
+    if world != 1 or (args.samples, args.tags, args.targets) != (S, T, G):
+        return None
+    try:
+        t = json.loads((ROOT / "profiles" / "traffic.json").read_text())
+        return t[kernel][str(args.neighbors)]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def build_workload(args):
     from idash2019_2_b200 import synth
     tag, tgt = synth.make_positions(args.tags, args.targets, SEED)
@@ -237,9 +249,25 @@ def run_b200(args):
            for _ in range(n_batches)]
     outs = [torch.empty((n_rows, 2048), dtype=torch.int32, device="cuda") for _ in range(n_batches)]
 
+    # The batches of a step are independent evaluations. With more than one they are issued round-robin on two side
+    # streams (fork/join around the main stream), so that the ramp-up and tail of consecutive persistent launches overlap.
+    side = [torch.cuda.Stream() for _ in range(2)] if n_batches > 1 else []
+
     def step():
+        if not side:
+            api.cloud_compute_score_device(ctx, m, ins[0], outs[0])
+            return
+        main = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for s_ in side:
+            s_.wait_event(fork)
         for b in range(n_batches):
-            api.cloud_compute_score_device(ctx, m, ins[b], outs[b])
+            api.cloud_compute_score_device(ctx, m, ins[b], outs[b], stream=side[b % 2].cuda_stream)
+        for s_ in side:
+            join = torch.cuda.Event()
+            join.record(s_)
+            main.wait_event(join)
 
     def barrier():
         if world > 1:
@@ -306,6 +334,8 @@ def run_b200(args):
         achieved = alg_bytes / (k_ms * 1e-3) * 1e-9
         h2d = n_batches * (slab * CT_BYTES)
         d2h = n_batches * (n_rows * (CT_BYTES + 4 + 8))
+        kernel_name = {api.KERNEL_IMAD: "cloud_eval_kernel", api.KERNEL_TENSOR_TILE: "cloud_tc_kernel",
+                       api.KERNEL_TENSOR_RING: "cloud_ring_kernel"}.get(kernel_used, "?")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -316,11 +346,11 @@ def run_b200(args):
                                    (f"; {n_batches} batches sharded by target range over {world} GPUs" if world > 1 else ""),
                        "neighbors": args.neighbors, "batches": n_batches, "targets_per_gpu": t_hi - t_lo,
                        "in_ct_per_gpu_batch": slab, "out_ct_per_gpu_batch": n_rows,
-                       "l2": "inputs+outputs per step (2.4 GB) exceed the 126 MB L2; no explicit flush"},
+                       "l2": "inputs+outputs per step (2.4 GB) exceed the 126 MB L2; no explicit flush",
+                       "streams": "batches of a step round-robin on 2 side streams" if side else "single stream"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None,
-                         "kernel": {api.KERNEL_IMAD: "cloud_eval_kernel", api.KERNEL_TENSOR_TILE: "cloud_tc_kernel",
-                                    api.KERNEL_TENSOR_RING: "cloud_ring_kernel"}.get(kernel_used, "?"), "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes,
+                         "traffic": ncu_traffic(kernel_name, args, world),
+                         "kernel": kernel_name, "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes,
                          "peak_source": peak_src, "kernel_share_of_step": k_ms * n_batches / (ms_total / args.steps)},
             "e2e": {"value": slots_per_step * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
