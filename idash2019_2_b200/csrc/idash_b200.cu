@@ -337,6 +337,9 @@ struct idash_b200_ctx {
     // pipelined host path (cloud_eval_host): copy-in / copy-out streams and per-piece events
     cudaStream_t s_in = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_k;
+    // the small per-row finalize kernel runs beside the main kernel on its own stream (fork / join events)
+    cudaStream_t s_aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 // A launch over part of the model: tiles [tile_lo, tile_hi) of the ring kernel = rows [row_lo, row_hi) (caller rows are
@@ -393,6 +396,9 @@ extern "C" int idash_b200_destroy(idash_b200_ctx *c) {
     if (!c) return IDASH_B200_OK;
     cudaSetDevice(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (c->s_aux) cudaStreamDestroy(c->s_aux);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
     for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
@@ -590,6 +596,34 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
         return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: the persistent ring kernel was requested but the model has too many tiles per chunk");
     const bool use_ring = ring_selected(c, L);
     if (piece && !use_ring) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: internal: partial launches need the ring kernel");
+    // Per-row variance / record headers: independent of the main kernel's words, so it is forked onto its own stream
+    // (after the slot table is ready on `st`) and joined at the end -- it hides behind the main kernel.
+    if (!c->s_aux) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventRecord(c->ev_fork, st));
+    CUDA_TRY(cudaStreamWaitEvent(c->s_aux, c->ev_fork, 0));
+    FinalizeParams f;
+    memset(&f, 0, sizeof(f));
+    f.row_lo = piece ? piece->row_lo : 0;
+    f.n_rows = piece ? piece->row_hi : L->n_rows;
+    f.var_ptr = m->d_var_ptr;
+    f.var_ct = m->d_var_ct;
+    f.var_w = m->d_var_w;
+    f.out_bidx = m->d_out_bidx;
+    f.in = in;
+    f.out = out;
+    f.slot_of_ct = d_slot_of_ct;
+    f.n_ct_slots = n_ct_slots;
+    f.slot_of_row = d_slot_of_row;
+    f.default_var = 8.8817841970012523e-16;   // alpha^2 = 2^-50 (eval/idash.cpp:20, tlwe-functions.cpp:38)
+    cloud_finalize_kernel<<<(unsigned) ((f.n_rows - f.row_lo + 63) / 64), 64, 0, c->s_aux>>>(f);   // 64-thread CTAs fit beside a resident ring CTA
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(c->ev_join, c->s_aux));
+
     const bool timed = c->t_used < (int) c->t_begin.size();
     if (timed) CUDA_TRY(cudaEventRecord(c->t_begin[c->t_used], st));
     if (use_ring) {
@@ -683,21 +717,7 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
     if (timed) CUDA_TRY(cudaEventRecord(c->t_end[c->t_used++], st));
     CUDA_TRY(cudaGetLastError());
 
-    FinalizeParams f;
-    memset(&f, 0, sizeof(f));
-    f.row_lo = piece ? piece->row_lo : 0;
-    f.n_rows = piece ? piece->row_hi : L->n_rows;
-    f.var_ptr = m->d_var_ptr;
-    f.var_ct = m->d_var_ct;
-    f.var_w = m->d_var_w;
-    f.out_bidx = m->d_out_bidx;
-    f.in = in;
-    f.out = out;
-    f.slot_of_ct = d_slot_of_ct;
-    f.n_ct_slots = n_ct_slots;
-    f.slot_of_row = d_slot_of_row;
-    f.default_var = 8.8817841970012523e-16;   // alpha^2 = 2^-50 (eval/idash.cpp:20, tlwe-functions.cpp:38)
-    cloud_finalize_kernel<<<(unsigned) ((f.n_rows - f.row_lo + 255) / 256), 256, 0, st>>>(f);
+    CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join, 0));     // join: the launch is complete when both kernels are
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return IDASH_B200_OK;
