@@ -61,6 +61,7 @@ TILE_DTYPE = np.dtype([("f_base", "<u4"), ("K", "<u4"), ("b_off", "<u8"), ("used
 assert ENTRY_DTYPE.itemsize == 32 and GROUP_DTYPE.itemsize == 64 and TILE_DTYPE.itemsize == 32
 TILE_ROWS, TILE_KMAX = 64, 256
 KERNEL_AUTO, KERNEL_IMAD, KERNEL_TENSOR, KERNEL_TENSOR_TILE, KERNEL_TENSOR_RING = 0, 1, 2, 3, 4
+DECRYPT_AUTO, DECRYPT_IADD, DECRYPT_TENSOR = 0, 1, 2
 
 # every symbol include/idash_b200.h and include/idash_b200_layout.h declare
 EXPORTS = {
@@ -70,6 +71,8 @@ EXPORTS = {
     "idash_b200_kernel_launches": (C.c_uint64, [C.c_void_p]),
     "idash_b200_set_kernel": (C.c_int, [C.c_void_p, C.c_int]),
     "idash_b200_last_kernel": (C.c_int, [C.c_void_p]),
+    "idash_b200_set_decrypt_kernel": (C.c_int, [C.c_void_p, C.c_int]),
+    "idash_b200_last_decrypt_kernel": (C.c_int, [C.c_void_p]),
     "idash_b200_timing_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "idash_b200_timing_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "idash_b200_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),

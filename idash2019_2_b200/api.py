@@ -18,7 +18,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib as L
-from ._lib import (CONSTANT_BIDX, CT_BYTES, CT_WORDS, KERNEL_AUTO, KERNEL_IMAD, KERNEL_TENSOR,  # noqa: F401
+from ._lib import (CONSTANT_BIDX, CT_BYTES, CT_WORDS, DECRYPT_AUTO, DECRYPT_IADD, DECRYPT_TENSOR, KERNEL_AUTO, KERNEL_IMAD, KERNEL_TENSOR,  # noqa: F401
                    KERNEL_TENSOR_RING, KERNEL_TENSOR_TILE, LAYOUT_PACKED, LAYOUT_RECORDS, N, RECORD_BYTES, IdashB200Error)
 
 
@@ -43,6 +43,13 @@ class Context:
 
     def last_kernel(self) -> int:
         return int(L.lib().idash_b200_last_kernel(self.handle))
+
+    def set_decrypt_kernel(self, which: int) -> None:
+        """DECRYPT_AUTO / DECRYPT_IADD / DECRYPT_TENSOR (idash_b200_set_decrypt_kernel)."""
+        L.check(L.lib().idash_b200_set_decrypt_kernel(self.handle, int(which)))
+
+    def last_decrypt_kernel(self) -> int:
+        return int(L.lib().idash_b200_last_decrypt_kernel(self.handle))
 
     def timing_enable(self, max_launches: int) -> None:
         L.check(L.lib().idash_b200_timing_enable(self.handle, int(max_launches)))

@@ -305,6 +305,8 @@ __global__ void __launch_bounds__(128) decrypt_kernel(CtView in, uint64_t n_ct, 
     }
 }
 
+#include "decrypt_tc.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -331,6 +333,8 @@ struct idash_b200_ctx {
     uint64_t launches = 0;
     int kernel_choice = IDASH_B200_KERNEL_AUTO;
     int last_kernel = 0;               // which cloud kernel the last launch used
+    int decrypt_choice = IDASH_B200_DECRYPT_AUTO;
+    int last_decrypt_kernel = 0;
     std::vector<cudaEvent_t> t_begin, t_end;   // per-launch timing of the dominant kernels (timing_enable)
     int t_used = 0;
     DevBuf in_buf, out_buf, slot_buf, row_slot_buf, aux_in_idx, aux_in_var, aux_out_idx, aux_out_var, scores_buf, phase_buf;
@@ -386,6 +390,7 @@ extern "C" int idash_b200_init(idash_b200_ctx **out, int device) {
     CUDA_TRY(cudaFuncSetAttribute(cloud_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_max));
     CUDA_TRY(cudaFuncSetAttribute(cloud_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_max));
     CUDA_TRY(cudaFuncSetAttribute(cloud_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_max));
+    CUDA_TRY(cudaFuncSetAttribute(decrypt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dec_tc_smem_bytes(DT_MAX_SLOTS)));
     CUDA_TRY(cudaFuncSetAttribute(cloud_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int) RG_SMEM_MAX));
     *out = c;
@@ -453,6 +458,14 @@ extern "C" int idash_b200_set_kernel(idash_b200_ctx *c, int which) {
     return IDASH_B200_OK;
 }
 extern "C" int idash_b200_last_kernel(const idash_b200_ctx *c) { return c ? c->last_kernel : 0; }
+
+extern "C" int idash_b200_set_decrypt_kernel(idash_b200_ctx *c, int which) {
+    clear_error();
+    if (!c || which < IDASH_B200_DECRYPT_AUTO || which > IDASH_B200_DECRYPT_TENSOR) return set_error(IDASH_B200_ERR_INVALID, "set_decrypt_kernel: bad argument");
+    c->decrypt_choice = which;
+    return IDASH_B200_OK;
+}
+extern "C" int idash_b200_last_decrypt_kernel(const idash_b200_ctx *c) { return c ? c->last_decrypt_kernel : 0; }
 
 extern "C" int idash_b200_host_alloc(void **ptr, size_t bytes) {
     clear_error();
@@ -983,10 +996,29 @@ static int pack_key(const int32_t *key, KeyBits *kb) {
 
 static int launch_decrypt(idash_b200_ctx *c, const KeyBits &kb, uint32_t S, const CtView &in, float *d_scores, uint32_t *d_phase, cudaStream_t st) {
     if (in.count == 0) return IDASH_B200_OK;
-    const unsigned grid = (unsigned) std::min<uint64_t>(in.count, (uint64_t) c->sm_count * 16);
     const bool timed = c->t_used < (int) c->t_begin.size();
     if (timed) CUDA_TRY(cudaEventRecord(c->t_begin[c->t_used], st));
-    decrypt_kernel<<<grid, 128, 0, st>>>(in, in.count, kb, S, d_scores, d_phase);
+    if (c->decrypt_choice != IDASH_B200_DECRYPT_IADD) {
+        DecTcParams p;
+        memset(&p, 0, sizeof(p));
+        p.in = in;
+        p.n_ct = in.count;
+        p.n_groups = (in.count + DT_CTS - 1) / DT_CTS;
+        p.S = S;
+        p.n_slots = DT_MAX_SLOTS;
+        p.scores = d_scores;
+        p.phase = d_phase;
+        p.key = kb;
+        uint64_t grid = std::min<uint64_t>(p.n_groups, (uint64_t) c->sm_count);
+        if (const char *gs = getenv("IDASH_B200_DECRYPT_GRID")) grid = std::max<uint64_t>(1, std::min<uint64_t>(grid, (uint64_t) atoi(gs)));   // tests: many groups per CTA
+        if (const char *ns = getenv("IDASH_B200_DECRYPT_SLOTS")) p.n_slots = std::max<uint32_t>(DT_GROUP_SLOTS, std::min<uint32_t>(DT_MAX_SLOTS, (uint32_t) atoi(ns)));
+        decrypt_tc_kernel<<<(unsigned) grid, DT_THREADS, dec_tc_smem_bytes(p.n_slots), st>>>(p);
+        c->last_decrypt_kernel = IDASH_B200_DECRYPT_TENSOR;
+    } else {
+        const unsigned grid = (unsigned) std::min<uint64_t>(in.count, (uint64_t) c->sm_count * 16);
+        decrypt_kernel<<<grid, 128, 0, st>>>(in, in.count, kb, S, d_scores, d_phase);
+        c->last_decrypt_kernel = IDASH_B200_DECRYPT_IADD;
+    }
     c->launches++;
     if (timed) CUDA_TRY(cudaEventRecord(c->t_end[c->t_used++], st));
     CUDA_TRY(cudaGetLastError());

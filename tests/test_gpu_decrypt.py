@@ -10,8 +10,17 @@ from helpers import GOLDEN_CASES, load_golden
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["tensor", "iadd"], autouse=True)
+def decrypt_kernel(request, gpu_ctx):
+    """Every test runs on both decrypt kernels (tcgen05 Toeplitz GEMM and the CUDA-core kernel)."""
+    which = {"tensor": api.DECRYPT_TENSOR, "iadd": api.DECRYPT_IADD}[request.param]
+    gpu_ctx.set_decrypt_kernel(which)
+    yield which
+    gpu_ctx.set_decrypt_kernel(api.DECRYPT_AUTO)
+
+
 @pytest.mark.parametrize("S", [1004, 1024, 400, 335, 16, 1])
-def test_decrypt_matches_exact_oracle(gpu_ctx, S):
+def test_decrypt_matches_exact_oracle(gpu_ctx, decrypt_kernel, S):
     rng = np.random.default_rng(S)
     key = rng.integers(0, 2, 1024).astype(np.int32)
     ct = rng.integers(0, 2 ** 32, size=(37, 2048), dtype=np.uint32)
@@ -19,6 +28,29 @@ def test_decrypt_matches_exact_oracle(gpu_ctx, S):
     ref_phase = po.phase_exact_port(key, ct)
     assert np.array_equal(phase, ref_phase)                       # bit-exact, every coefficient
     assert np.array_equal(scores, po.decode_port(S, ref_phase))   # decoded floats bit-equal
+    assert gpu_ctx.last_decrypt_kernel() == decrypt_kernel
+
+
+@pytest.mark.parametrize("n_ct,grid,slots", [(32, 1, 12), (64, 1, 8), (333, 2, 12), (1000, 3, 9), (5000, 148, 12)])
+def test_decrypt_many_groups_per_cta(gpu_ctx, monkeypatch, n_ct, grid, slots):
+    """The persistent tensor-core kernel with several 32-ciphertext groups per CTA: ring slots and TMEM stages wrap
+    (IDASH_B200_DECRYPT_GRID / _SLOTS shrink the grid and the ring), records layout with its 8208-byte stride."""
+    monkeypatch.setenv("IDASH_B200_DECRYPT_GRID", str(grid))
+    monkeypatch.setenv("IDASH_B200_DECRYPT_SLOTS", str(slots))
+    rng = np.random.default_rng(n_ct)
+    key = rng.integers(0, 2, 1024).astype(np.int32)
+    ct = rng.integers(0, 2 ** 32, size=(n_ct, 2048), dtype=np.uint32)
+    ct[0] = 0xFFFFFFFF                                            # every byte plane at its maximum
+    ct[-1, :1024] = 0x80000000
+    ref_phase = po.phase_exact_port(key, ct)
+    scores, phase = api.decrypt_predictions(gpu_ctx, key, 1004, ct, want_phase=True)
+    assert np.array_equal(phase, ref_phase)
+    assert np.array_equal(scores, po.decode_port(1004, ref_phase))
+    image = formats.build_ct_image(np.arange(n_ct, dtype=np.uint32), ct, np.zeros(n_ct))
+    _, scores_r, phase_r = api.decrypt_predictions_records(gpu_ctx, key, 1004, image, want_phase=True)
+    assert np.array_equal(phase_r, ref_phase) and np.array_equal(scores_r, scores)
+    scores_only = api.decrypt_predictions(gpu_ctx, key, 1004, ct)
+    assert np.array_equal(scores_only, scores)
 
 
 @pytest.mark.parametrize("key_kind", ["zeros", "ones", "single"])

@@ -24,22 +24,30 @@ def main():
     ct = torch.randint(-2 ** 31, 2 ** 31, (n, 2048), dtype=torch.int32, device="cuda", generator=g)
     key = np.random.default_rng(1).integers(0, 2, 1024).astype(np.int32)
     scores = torch.empty((n, S), dtype=torch.float32, device="cuda")
-    for _ in range(3):
-        api.decrypt_predictions_device(ctx, key, S, ct, scores)
-    torch.cuda.synchronize()
-    ctx.timing_enable(10)
-    for _ in range(10):
-        api.decrypt_predictions_device(ctx, key, S, ct, scores)
-    torch.cuda.synchronize()
-    ms = ctx.timing_read(10)
-    k_ms = float(np.mean(ms))
-    # parity of a sample against the exact oracle
-    sample = 64
-    ref_phase = po.phase_exact_port(key, ct[:sample].cpu().numpy().view(np.uint32))
-    ok = bool(np.array_equal(scores[:sample].cpu().numpy(), po.decode_port(S, ref_phase)))
-    line = {"kernel": "decrypt_kernel", "ciphertexts": n, "S": S, "kernel_ms": k_ms, "ct_per_s": n / (k_ms * 1e-3),
-            "algorithmic_bytes": n * (8192 + 4 * S), "achieved_GBps": n * (8192 + 4 * S) / (k_ms * 1e-3) * 1e-9,
-            "sample_matches_exact_oracle": ok}
+    line = {"ciphertexts": n, "S": S, "algorithmic_bytes": n * (8192 + 4 * S), "kernels": {}}
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+    for name, which in (("decrypt_tc_kernel", api.DECRYPT_TENSOR), ("decrypt_kernel", api.DECRYPT_IADD)):
+        ctx.set_decrypt_kernel(which)
+        scores.zero_()
+        for _ in range(3):
+            api.decrypt_predictions_device(ctx, key, S, ct, scores)
+        torch.cuda.synchronize()
+        ctx.timing_enable(10)
+        for _ in range(10):
+            api.decrypt_predictions_device(ctx, key, S, ct, scores)
+        torch.cuda.synchronize()
+        ms = ctx.timing_read(10)
+        k_ms = float(np.mean(ms))
+        # parity of a sample (first, middle, last ciphertexts) against the exact oracle
+        idx = np.unique(np.concatenate([np.arange(min(n, 64)), np.arange(n // 2, min(n, n // 2 + 64)), np.arange(max(0, n - 64), n)]))
+        ref_phase = po.phase_exact_port(key, ct[idx].cpu().numpy().view(np.uint32))
+        ok = bool(np.array_equal(scores[idx].cpu().numpy(), po.decode_port(S, ref_phase)))
+        gbs = n * (8192 + 4 * S) / (k_ms * 1e-3) * 1e-9
+        line["kernels"][name] = {"kernel_ms": k_ms, "min_ms": float(np.min(ms)), "ct_per_s": n / (k_ms * 1e-3), "achieved_GBps": gbs,
+                                 "frac_of_measured_hbm_peak": gbs / peaks["hbm_gbs"] if "hbm_gbs" in peaks else None,
+                                 "int8_mac_per_s": n * 4 * 1024 * 1024 / (k_ms * 1e-3) if which == api.DECRYPT_TENSOR else None,
+                                 "sample_matches_exact_oracle": ok}
+    ctx.set_decrypt_kernel(api.DECRYPT_AUTO)
     if po.have_ref():
         m = min(n, 20001) // 3 * 3
         host = ct[:m].cpu().numpy().view(np.uint32)
