@@ -11,36 +11,39 @@
 //     prod = sum_l 2^(8l) P_l mod 2^32,  phase = b - prod,  score = float(double(int32 phase) / 2^32)
 //
 // GEMM shape per MMA: D[j][n] += A[j][k'] B[k'][n],  M = 128 phase coefficients j (TMEM lanes),
-// N = 128 = 4 byte planes x 32 ciphertexts (n = 32 l + ct), K = 32.
+// N = 128 = 32 ciphertexts x 4 byte planes (n = 4 ct + l), K = 32.
 //   * A = T, signed bytes, MN-major, no swizzle. The coefficient axis of a is walked BACKWARDS (k' = 1023 - k),
 //     so that A[j][k'] = t(j + k' - 1023) depends on j + k' only, with t(x) = s[x] (x >= 0), -s[x + 1024] (x < 0).
 //     A core matrix (8 k' rows x 16 j bytes) at (j0, k0') is then a function of d = j0 + k0' (a multiple of 8):
 //     254 distinct core matrices, 32.5 KB, built ONCE per CTA from the key bits. Every A tile of the 8 x 32
 //     (j block, K step) grid is a descriptor into that table: start = 128 (16 jb + 4 ks), LBO (next 8 k') = 128 B,
 //     SBO (next 16 j) = 256 B -- overlapping core matrices, read-only.
-//   * B = byte planes of a, unsigned, K-major: rows of 16 consecutive k' of one (plane, ciphertext). Producer
-//     threads load 64 contiguous bytes (16 coefficients) of one ciphertext, transpose bytes with PRMT (reversed
-//     order) and store one 16-byte row per plane; lanes = ciphertexts, so a quarter-warp store is 128 contiguous
-//     bytes (no bank conflicts). The operand lives in a shared-memory ring of 16 KB slots (128 k' x 128 n).
+//   * B = byte planes of a, unsigned, K-major: rows of 16 consecutive k' of one (ciphertext, plane). A producer warp
+//     loads 512 contiguous bytes of one ciphertext per instruction (fully coalesced: the first version had lanes =
+//     ciphertexts, 32 cache lines per load instruction, and the LSU/L1 path -- not HBM -- bound the kernel); the 4
+//     lanes that hold one 16-coefficient block split their words into byte planes (PRMT, reversed order), transpose
+//     4 x 4 with 4 shuffles, and each stores one 16-byte row. The operand lives in a shared-memory ring of slots
+//     (128 k' x 128 n, 16.5 KB with the bank-conflict pad).
 //   * TMEM: 2 stages x 2 j blocks x 128 columns = all 512 columns. A group of 32 ciphertexts takes 4 passes
 //     (2 j blocks each) over its 8 ring slots: 256 MMAs ~ 16 k cycles, the same order as the HBM time of the
 //     group's 384 KB (a, b in; scores out), so the kernel sits near both rooflines; measured numbers in DESIGN.md.
 //   * roles (544 threads, one persistent CTA per SM, groups strided over the grid): warps 0-7 epilogue (lane
 //     quadrant = warp % 4, j block of the pass = warp / 4; b is prefetched before the accumulator is ready),
-//     warp 8 MMA issuer + TMEM owner, warps 9-16 producers (two 64-byte loads in flight per thread).
+//     warp 8 MMA issuer + TMEM owner, warps 9-16 producers (four 64-byte loads in flight per thread).
 #pragma once
 
 #define DT_CTS 32u                        // ciphertexts per group
 #define DT_N 128u                         // MMA N = 4 planes x DT_CTS
-#define DT_SLOT_BYTES 16384u              // one ring slot: 128 k' x 128 n bytes = 4 K steps
 #define DT_GROUP_SLOTS 8u                 // 1024 k' per group
-#define DT_B_LBO (16u * DT_N)             // bytes between 16-k' column blocks of a slot
+#define DT_B_LBO (16u * DT_N + 64u)       // bytes between 16-k' column blocks of a slot; the 64-byte pad makes the producers'
+                                          // 128-bit stores (two k' blocks x four planes per quarter-warp) conflict-free
 #define DT_B_SBO 128u                     // 8 n rows x 16 bytes
+#define DT_SLOT_BYTES (8u * DT_B_LBO)     // one ring slot: 128 k' x 128 n bytes = 4 K steps (16896 with the pads)
 #define DT_A_LBO 128u
 #define DT_A_SBO 256u
 #define DT_TOEP_CORES 254u
 #define DT_TOEP_BYTES 32768u              // 254 x 128 = 32512, rounded up
-#define DT_MAX_SLOTS 12u
+#define DT_MAX_SLOTS 11u
 #define DT_WARP_MMA 8u
 #define DT_WARP_PROD 9u
 #define DT_PROD_WARPS 8u
@@ -55,6 +58,8 @@ struct DecTcParams {
     float *scores;          // [n_ct][S] or null
     uint32_t *phase;        // [n_ct][1024] or null
     KeyBits key;
+    uint32_t knockout;      // profiling aid (IDASH_B200_DECRYPT_KNOCKOUT, results are wrong when non-zero): 1 no MMAs, 2 no output
+                            // stores, 4 no b loads, 8 no a loads, 16 no operand stores, 32 no epilogue TMEM loads
 };
 
 __host__ __device__ constexpr uint32_t dec_tc_smem_bytes(uint32_t n_slots) { return DT_TOEP_BYTES + n_slots * DT_SLOT_BYTES; }
@@ -76,6 +81,47 @@ __device__ __forceinline__ void dec_split_rev(const uint4 w, uint32_t &l0, uint3
 
 __device__ __forceinline__ uint32_t ldg32_nc(const void *p) { return __ldg(reinterpret_cast<const uint32_t *>(p)); }
 
+// One pass of one epilogue warp: 32 phase coefficients (lanes) x 32 ciphertexts. STRIDE (bytes between ciphertexts),
+// PHASE and FULL (all 32 ciphertexts of the group exist) are compile-time, so that every load / phase store is base +
+// immediate and the score address is one pointer walk: ~9 instructions per output (the first version spent ~40 and the
+// epilogue warps, not the tensor pipe or HBM, set the pace -- profiles/r01_ncu_decrypt_tc.txt).
+// bw[] holds this pass's b words on entry; as soon as a chunk of 8 is consumed its registers are refilled with the b
+// words of the NEXT pass (bj_next, n_next ciphertexts; n_next = 0: none), so the b loads of pass p+1 are in flight
+// while pass p is processed and while the warp waits for the next accumulator -- their latency is never exposed.
+template <uint32_t STRIDE, bool PHASE, bool FULL>
+__device__ __forceinline__ void dec_epilogue_pass(uint32_t (&bw)[DT_CTS], const uint8_t *bj_next, uint32_t n_next, uint32_t n_here,
+                                                  uint32_t taddr, float *sc, uint32_t S, bool sc_on, uint32_t *ph, uint64_t *tempty) {
+    uint8_t *scp = reinterpret_cast<uint8_t *>(sc);   // walks down the 32 score rows of the group: + 4 S bytes per ciphertext
+    const uint32_t s4 = 4u * S;
+#pragma unroll
+    for (uint32_t chunk = 0; chunk < 4; ++chunk) {
+        uint32_t v[4][8];     // v[m][4 e + l]: plane l of ciphertext 8 chunk + 2 m + e
+#pragma unroll
+        for (uint32_t m = 0; m < 4; ++m) tc_ld8(taddr + chunk * 32u + m * 8u, v[m]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (chunk == 3) {
+            // the accumulator is in registers: hand the TMEM stage back before the last 8 outputs are computed and stored
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(tempty);
+        }
+#pragma unroll
+        for (uint32_t c = 0; c < 8; ++c) {
+            const uint32_t cc = chunk * 8u + c;
+            const uint32_t *q = &v[c >> 1][4u * (c & 1u)];
+            const uint32_t phs = bw[cc] - (q[0] + (q[1] << 8) + (q[2] << 16) + (q[3] << 24));
+            bw[cc] = cc < n_next ? ldg32_nc(bj_next + cc * STRIDE) : 0u;
+            const bool here = FULL || cc < n_here;
+            if (PHASE && here) stg32_stream(ph + cc * POLY_N, phs);
+            // (float) (double(int32) / 2^32): one rounding to 24 bits, then an exact power-of-two scale --
+            // identical to idash.cpp:718 + numeric-functions.cpp:36-38. Only the store is predicated (j < S).
+            const uint32_t fbits = __float_as_uint(__int2float_rn((int32_t) phs) * 2.3283064365386963e-10f);
+            asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.global.cs.u32 [%0], %1;\n\t}\n" ::"l"(scp), "r"(fbits), "r"((uint32_t) (sc_on && here)) : "memory");
+            scp += s4;
+        }
+    }
+}
+
+template <uint32_t STRIDE, bool PHASE>
 __global__ void __launch_bounds__(DT_THREADS, 1) decrypt_tc_kernel(const DecTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar[DT_MAX_SLOTS], empty_bar[DT_MAX_SLOTS], tfull_bar[2], tempty_bar[2];
@@ -121,52 +167,48 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decrypt_tc_kernel(const DecTcPa
     if (warp < 8u) {
         // ---------------- epilogue: phase = b - sum_l 2^(8l) P_l, decode, store
         const uint32_t qd = warp & 3u, jl = warp >> 2;
+        const uint32_t j_w = jl * 128u + qd * 32u + lane;        // + 256 pass
+        const bool st_on = !(p.knockout & 2u), ld_on = !(p.knockout & 4u);
         uint32_t pc = 0;
+        uint32_t bw[DT_CTS];
+        {   // b words of the first pass
+            const uint64_t g = blockIdx.x;
+            const uint32_t n0 = (g < p.n_groups && ld_on) ? (uint32_t) min((uint64_t) DT_CTS, p.n_ct - g * DT_CTS) : 0u;
+            const uint8_t *bj = p.in.words + g * DT_CTS * STRIDE + 4u * POLY_N + 4u * j_w;
+#pragma unroll
+            for (uint32_t c = 0; c < DT_CTS; ++c) bw[c] = c < n0 ? ldg32_nc(bj + c * STRIDE) : 0u;
+        }
         for (uint64_t g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
             const uint64_t ct0 = g * DT_CTS;
             const uint32_t n_here = (uint32_t) min((uint64_t) DT_CTS, p.n_ct - ct0);
-            const uint8_t *b0 = p.in.words + ct0 * p.in.stride + 4u * POLY_N;
+            const uint64_t g_next = g + gridDim.x;
+            const uint32_t n_after = (g_next < p.n_groups && ld_on) ? (uint32_t) min((uint64_t) DT_CTS, p.n_ct - g_next * DT_CTS) : 0u;
 #pragma unroll 1
             for (uint32_t pass = 0; pass < 4; ++pass, ++pc) {
                 const uint32_t stage = pc & 1u;
-                const uint32_t j = (pass * 2u + jl) * 128u + qd * 32u + lane;
-                uint32_t bw[DT_CTS];
-#pragma unroll
-                for (uint32_t c = 0; c < DT_CTS; ++c) bw[c] = c < n_here ? ldg32_nc(b0 + c * p.in.stride + 4u * j) : 0u;
-                mbar_wait(&tfull_bar[stage], (pc >> 1) & 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t j = pass * 256u + j_w;
                 const uint32_t taddr = tmem + ((qd * 32u) << 16) + stage * 256u + jl * DT_N;
                 float *sc = p.scores ? p.scores + ct0 * p.S + j : nullptr;
                 uint32_t *ph = p.phase ? p.phase + ct0 * POLY_N + j : nullptr;
-#pragma unroll
-                for (uint32_t chunk = 0; chunk < 4; ++chunk) {
-                    uint32_t v0[8], v1[8], v2[8], v3[8];
-                    tc_ld8(taddr + 0 * DT_CTS + chunk * 8u, v0);
-                    tc_ld8(taddr + 1 * DT_CTS + chunk * 8u, v1);
-                    tc_ld8(taddr + 2 * DT_CTS + chunk * 8u, v2);
-                    tc_ld8(taddr + 3 * DT_CTS + chunk * 8u, v3);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (uint32_t c = 0; c < 8; ++c) {
-                        const uint32_t cc = chunk * 8u + c;
-                        if (cc < n_here) {
-                            const uint32_t prod = v0[c] + (v1[c] << 8) + (v2[c] << 16) + (v3[c] << 24);
-                            const uint32_t phs = bw[cc] - prod;
-                            if (ph) stg32_stream(ph + (uint64_t) cc * POLY_N, phs);
-                            // (float) (double(int32) / 2^32): one rounding to 24 bits, then an exact power-of-two scale --
-                            // identical to idash.cpp:718 + numeric-functions.cpp:36-38
-                            if (sc && j < p.S) stg32_stream(sc + (uint64_t) cc * p.S, __float_as_uint(__int2float_rn((int32_t) phs) * 2.3283064365386963e-10f));
-                        }
-                    }
-                }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                mbar_arrive(&tempty_bar[stage]);
+                // the pass after this one: same group, next 256 coefficients -- or the first pass of the CTA's next group
+                const uint8_t *bj_next = pass < 3u ? p.in.words + ct0 * STRIDE + 4u * POLY_N + 4u * (j + 256u)
+                                                   : p.in.words + g_next * DT_CTS * STRIDE + 4u * POLY_N + 4u * j_w;
+                const uint32_t n_next = pass < 3u ? (ld_on ? n_here : 0u) : n_after;
+                mbar_wait(&tfull_bar[stage], (pc >> 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const bool sc_on = sc != nullptr && j < p.S && st_on;
+                if (n_here == DT_CTS) dec_epilogue_pass<STRIDE, PHASE, true>(bw, bj_next, n_next, n_here, taddr, sc, p.S, sc_on, ph, &tempty_bar[stage]);
+                else dec_epilogue_pass<STRIDE, PHASE, false>(bw, bj_next, n_next, n_here, taddr, sc, p.S, sc_on, ph, &tempty_bar[stage]);
             }
         }
     } else if (warp == DT_WARP_MMA) {
         // ---------------- MMA issuer
         const uint32_t leader = elect_one();
-        const uint32_t toep_a = smem_u32(toep), ring_a = smem_u32(ring);
+        // descriptors (SWIZZLE_NONE, version 1): low word = address >> 4 | (LBO >> 4) << 16, high word = SBO >> 4 | 1 << 14. Every
+        // operand address stays below 2^18, so stepping through the Toeplitz table / the ring is an add on the low word.
+        const uint32_t a_lo0 = ((smem_u32(toep) >> 4) & 0x3FFFu) | ((DT_A_LBO >> 4) << 16), a_hi = (DT_A_SBO >> 4) | (1u << 14);
+        const uint32_t b_lo0 = ((smem_u32(ring) >> 4) & 0x3FFFu) | ((DT_B_LBO >> 4) << 16), b_hi = (DT_B_SBO >> 4) | (1u << 14);
+        auto mk = [](uint32_t lo, uint32_t hi) { uint64_t d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi)); return d; };
         uint32_t slot0 = 0, ph0 = 0, pc = 0;
         for (uint64_t g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
 #pragma unroll 1
@@ -175,23 +217,22 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decrypt_tc_kernel(const DecTcPa
                 mbar_wait(&tempty_bar[stage], ((pc >> 1) & 1u) ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 uint32_t slot = slot0, ph = ph0;
+                uint32_t a_lo = a_lo0 + 256u * pass;          // A tile (jb = 2 pass + q, ks): + 128 q + 32 ks  [16-byte units]
+                const uint32_t d0 = tmem + stage * 256u;
 #pragma unroll 1
-                for (uint32_t s = 0; s < DT_GROUP_SLOTS; ++s) {
+                for (uint32_t s = 0; s < DT_GROUP_SLOTS; ++s, a_lo += 128u) {
                     if (pass == 0) {
                         mbar_wait(&full_bar[slot], ph);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     }
-                    const uint32_t b_a = ring_a + slot * DT_SLOT_BYTES;
+                    const uint32_t b_lo = b_lo0 + slot * (DT_SLOT_BYTES >> 4);
+                    if (!(p.knockout & 1u))
 #pragma unroll
                     for (uint32_t kk = 0; kk < 4; ++kk) {
-                        const uint32_t ks = s * 4u + kk;
-                        const uint64_t db = tc_desc(b_a + kk * 2u * DT_B_LBO, DT_B_LBO, DT_B_SBO);
-#pragma unroll
-                        for (uint32_t q = 0; q < 2; ++q) {
-                            const uint32_t jb = pass * 2u + q;
-                            const uint64_t da = tc_desc(toep_a + 128u * (16u * jb + 4u * ks), DT_A_LBO, DT_A_SBO);
-                            tc_mma_p(tmem + stage * 256u + q * DT_N, da, db, dec_idesc(DT_N), ks != 0u, leader);
-                        }
+                        const uint64_t db = mk(b_lo + kk * ((2u * DT_B_LBO) >> 4), b_hi);
+                        const uint32_t acc = (s | kk) != 0u;
+                        tc_mma_p(d0, mk(a_lo + 32u * kk, a_hi), db, dec_idesc(DT_N), acc, leader);
+                        tc_mma_p(d0 + DT_N, mk(a_lo + 32u * kk + 128u, a_hi), db, dec_idesc(DT_N), acc, leader);
                     }
                     if (pass == 3 && leader) tc_commit(&empty_bar[slot]);   // the group is done with this slot
                     if (++slot == NS) { slot = 0; ph ^= 1u; }
@@ -203,45 +244,65 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decrypt_tc_kernel(const DecTcPa
             if (slot0 >= NS) { slot0 -= NS; ph0 ^= 1u; }
         }
     } else {
-        // ---------------- producers: unit i = (group, slot s): thread (ct, ub) stages k' block 8 s + ub of its ciphertext
-        const uint32_t pt = tid - DT_WARP_PROD * 32u;
-        const uint32_t ct_l = pt & 31u, ub = pt >> 5;
+        // ---------------- producers: unit i = (group, slot s). Warp w stages ciphertexts 4 w .. 4 w + 3 of the group: load q
+        // of a unit reads the 512 contiguous bytes (8 k' blocks) of ciphertext 4 w + q; lane = (block ub = lane / 4, piece = lane % 4).
+        const uint32_t pw = warp - DT_WARP_PROD;
+        const uint32_t ub = lane >> 2, piece = lane & 3u;
         const uint64_t my_groups = p.n_groups > blockIdx.x ? (p.n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
         const uint64_t total = my_groups * DT_GROUP_SLOTS;
         auto load_unit = [&](uint64_t i, uint4 (&w)[4]) {
-            if (i >= total) return;
+            if (i >= total || (p.knockout & 8u)) return;
             const uint64_t g = blockIdx.x + (i >> 3) * gridDim.x;
-            const uint32_t kb = (uint32_t) (i & 7u) * 8u + ub;
-            uint64_t ct = g * DT_CTS + ct_l;
-            if (ct >= p.n_ct) ct = p.n_ct - 1;     // tail group: a valid address; the epilogue ignores these columns
-            const uint8_t *src = p.in.words + ct * p.in.stride + 64u * (63u - kb);
+            const uint32_t kb = (uint32_t) (i & 7u) * 8u + ub;     // k' block; its coefficients are 16 (63 - kb) .. + 15
 #pragma unroll
-            for (int q = 0; q < 4; ++q) w[q] = ldg128(src + 16 * q);
+            for (int q = 0; q < 4; ++q) {
+                uint64_t ct = g * DT_CTS + pw * 4u + q;
+                if (ct >= p.n_ct) ct = p.n_ct - 1;     // tail group: a valid address; the epilogue ignores these columns
+                w[q] = ldg128(p.in.words + ct * STRIDE + 64u * (63u - kb) + 16u * piece);
+            }
         };
         uint32_t slot = 0, ph = 0;
+        const bool odd = piece & 1u, hi = piece & 2u;
         auto store_unit = [&](const uint4 (&w)[4]) {
-            uint32_t l[4][4];   // [plane][16-byte row word]: row bytes 0..15 = coefficients k_start+15 .. k_start
+            uint4 row[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) dec_split_rev(w[3 - q], l[0][q], l[1][q], l[2][q], l[3][q]);
+            for (int q = 0; q < 4; ++q) {
+                // byte planes of this lane's 4 coefficients (reversed), then a 4 x 4 transpose over the 4 lanes of the block:
+                // lane `piece` ends with plane `piece` of all 16 coefficients
+                uint32_t v0, v1, v2, v3;
+                dec_split_rev(w[q], v0, v1, v2, v3);
+                const uint32_t r0 = __shfl_xor_sync(0xFFFFFFFFu, odd ? v0 : v1, 1), r1 = __shfl_xor_sync(0xFFFFFFFFu, odd ? v2 : v3, 1);
+                const uint32_t a0 = odd ? r0 : v0, a1 = odd ? v1 : r0, a2 = odd ? r1 : v2, a3 = odd ? v3 : r1;
+                const uint32_t s0 = __shfl_xor_sync(0xFFFFFFFFu, hi ? a0 : a2, 2), s1 = __shfl_xor_sync(0xFFFFFFFFu, hi ? a1 : a3, 2);
+                // t[i] = plane `piece` of the coefficients held by lane i of the block; row bytes run from the highest coefficient down
+                const uint32_t t0 = hi ? s0 : a0, t1 = hi ? s1 : a1, t2 = hi ? a2 : s0, t3 = hi ? a3 : s1;
+                row[q] = make_uint4(t3, t2, t1, t0);
+            }
             mbar_wait(&empty_bar[slot], ph ^ 1u);
-            uint8_t *dst = ring + slot * DT_SLOT_BYTES + ub * DT_B_LBO + ct_l * 16u;
+            uint8_t *dst = ring + slot * DT_SLOT_BYTES + ub * DT_B_LBO + (pw * 16u + piece) * 16u;   // n = 4 ct + plane
+            if (!(p.knockout & 16u)) {
 #pragma unroll
-            for (int pl = 0; pl < 4; ++pl)
-                *reinterpret_cast<uint4 *>(dst + pl * (DT_CTS * 16u)) = make_uint4(l[pl][0], l[pl][1], l[pl][2], l[pl][3]);
+                for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4 *>(dst + q * 64u) = row[q];
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(&full_bar[slot]);
             if (++slot == NS) { slot = 0; ph ^= 1u; }
         };
-        uint4 wa[4], wb[4];
-        load_unit(0, wa);
-        load_unit(1, wb);
-        for (uint64_t i = 0; i < total; i += 2) {
-            store_unit(wa);
-            load_unit(i + 2, wa);
-            if (i + 1 < total) {
-                store_unit(wb);
-                load_unit(i + 3, wb);
-            }
+        // four units (4 x 16-byte loads each) in flight per thread, register sets bound statically; total is a multiple of 8
+        uint4 w0[4], w1[4], w2[4], w3[4];
+        load_unit(0, w0);
+        load_unit(1, w1);
+        load_unit(2, w2);
+        load_unit(3, w3);
+        for (uint64_t i = 0; i < total; i += 4) {
+            store_unit(w0);
+            load_unit(i + 4, w0);
+            store_unit(w1);
+            load_unit(i + 5, w1);
+            store_unit(w2);
+            load_unit(i + 6, w2);
+            store_unit(w3);
+            load_unit(i + 7, w3);
         }
     }
 

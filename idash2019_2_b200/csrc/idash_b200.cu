@@ -390,7 +390,10 @@ extern "C" int idash_b200_init(idash_b200_ctx **out, int device) {
     CUDA_TRY(cudaFuncSetAttribute(cloud_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_max));
     CUDA_TRY(cudaFuncSetAttribute(cloud_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_max));
     CUDA_TRY(cudaFuncSetAttribute(cloud_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_max));
-    CUDA_TRY(cudaFuncSetAttribute(decrypt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dec_tc_smem_bytes(DT_MAX_SLOTS)));
+    CUDA_TRY(cudaFuncSetAttribute(decrypt_tc_kernel<IDASH_B200_CT_BYTES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dec_tc_smem_bytes(DT_MAX_SLOTS)));
+    CUDA_TRY(cudaFuncSetAttribute(decrypt_tc_kernel<IDASH_B200_CT_BYTES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dec_tc_smem_bytes(DT_MAX_SLOTS)));
+    CUDA_TRY(cudaFuncSetAttribute(decrypt_tc_kernel<IDASH_B200_RECORD_BYTES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dec_tc_smem_bytes(DT_MAX_SLOTS)));
+    CUDA_TRY(cudaFuncSetAttribute(decrypt_tc_kernel<IDASH_B200_RECORD_BYTES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dec_tc_smem_bytes(DT_MAX_SLOTS)));
     CUDA_TRY(cudaFuncSetAttribute(cloud_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int) RG_SMEM_MAX));
     *out = c;
@@ -1012,7 +1015,15 @@ static int launch_decrypt(idash_b200_ctx *c, const KeyBits &kb, uint32_t S, cons
         uint64_t grid = std::min<uint64_t>(p.n_groups, (uint64_t) c->sm_count);
         if (const char *gs = getenv("IDASH_B200_DECRYPT_GRID")) grid = std::max<uint64_t>(1, std::min<uint64_t>(grid, (uint64_t) atoi(gs)));   // tests: many groups per CTA
         if (const char *ns = getenv("IDASH_B200_DECRYPT_SLOTS")) p.n_slots = std::max<uint32_t>(DT_GROUP_SLOTS, std::min<uint32_t>(DT_MAX_SLOTS, (uint32_t) atoi(ns)));
-        decrypt_tc_kernel<<<(unsigned) grid, DT_THREADS, dec_tc_smem_bytes(p.n_slots), st>>>(p);
+        if (const char *ko = getenv("IDASH_B200_DECRYPT_KNOCKOUT")) p.knockout = (uint32_t) atoi(ko);
+        const size_t smem = dec_tc_smem_bytes(p.n_slots);
+        if (in.stride == IDASH_B200_RECORD_BYTES) {
+            if (d_phase) decrypt_tc_kernel<IDASH_B200_RECORD_BYTES, true><<<(unsigned) grid, DT_THREADS, smem, st>>>(p);
+            else decrypt_tc_kernel<IDASH_B200_RECORD_BYTES, false><<<(unsigned) grid, DT_THREADS, smem, st>>>(p);
+        } else {
+            if (d_phase) decrypt_tc_kernel<IDASH_B200_CT_BYTES, true><<<(unsigned) grid, DT_THREADS, smem, st>>>(p);
+            else decrypt_tc_kernel<IDASH_B200_CT_BYTES, false><<<(unsigned) grid, DT_THREADS, smem, st>>>(p);
+        }
         c->last_decrypt_kernel = IDASH_B200_DECRYPT_TENSOR;
     } else {
         const unsigned grid = (unsigned) std::min<uint64_t>(in.count, (uint64_t) c->sm_count * 16);

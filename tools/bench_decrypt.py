@@ -26,7 +26,9 @@ def main():
     scores = torch.empty((n, S), dtype=torch.float32, device="cuda")
     line = {"ciphertexts": n, "S": S, "algorithmic_bytes": n * (8192 + 4 * S), "kernels": {}}
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
-    for name, which in (("decrypt_tc_kernel", api.DECRYPT_TENSOR), ("decrypt_kernel", api.DECRYPT_IADD)):
+    quick = bool(os.environ.get("DEC_QUICK"))       # tensor kernel only, no CPU leg (knock-out / tuning runs)
+    kernels = (("decrypt_tc_kernel", api.DECRYPT_TENSOR), ("decrypt_kernel", api.DECRYPT_IADD))
+    for name, which in kernels[:1] if quick else kernels:
         ctx.set_decrypt_kernel(which)
         scores.zero_()
         for _ in range(3):
@@ -48,7 +50,7 @@ def main():
                                  "int8_mac_per_s": n * 4 * 1024 * 1024 / (k_ms * 1e-3) if which == api.DECRYPT_TENSOR else None,
                                  "sample_matches_exact_oracle": ok}
     ctx.set_decrypt_kernel(api.DECRYPT_AUTO)
-    if po.have_ref():
+    if po.have_ref() and not quick:
         m = min(n, 20001) // 3 * 3
         host = ct[:m].cpu().numpy().view(np.uint32)
         os.environ["OMP_NUM_THREADS"] = str(po.host_threads())
