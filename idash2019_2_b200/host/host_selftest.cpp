@@ -6,6 +6,8 @@
 #include "parse_vw.h"
 
 #include <algorithm>
+#include <charconv>
+#include <cstring>
 #include <cstdio>
 #include <fstream>
 #include <map>
@@ -58,6 +60,27 @@ int main(int argc, char **argv) {
         }
     write_decrypted_predictions(dec, params, out + "/" RESULT_FILE, true);
     write_decrypted_predictions(dec, params, out + "/" RESULT_BYPOS_FILE, false);
+    // the csv writer formats with std::to_chars(general, 6); the reference streams `ostream << float` = printf("%g"):
+    // cross-check the two on two million floats (scores in [-0.5, 0.5), random bit patterns, edge values)
+    {
+        uint64_t x = 88172645463325252ull;
+        char a[64], b[64];
+        for (int i = 0; i < 2000000; ++i) {
+            x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+            float f;
+            if (i % 3 == 0) f = (float) ((double) (int32_t) (uint32_t) x / 4294967296.0);
+            else if (i % 3 == 1) { uint32_t u = (uint32_t) (x >> 16); memcpy(&f, &u, 4); if (f != f || f - f != 0.0f) continue; }
+            else f = (float) ((double) (int32_t) (uint32_t) (x >> 40) / 4294967296.0);
+            if (i < 8) { const float edge[8] = {0.0f, -0.0f, 1.0f, -0.5f, 1e-5f, 9.99999e-5f, 123456.0f, 1234567.0f}; f = edge[i]; }
+            const int n = snprintf(a, sizeof(a), "%g", (double) f);
+            const auto r = std::to_chars(b, b + sizeof(b), (double) f, std::chars_format::general, 6);
+            if ((size_t) n != (size_t) (r.ptr - b) || memcmp(a, b, (size_t) n) != 0) {
+                *r.ptr = 0;
+                fprintf(stderr, "float formatting differs: printf '%s' to_chars '%s'\n", a, b);
+                return 1;
+            }
+        }
+    }
     printf("host_selftest ok: %zu model rows, %zu input cts, %zu prediction cts\n", model.model.size(), enc.enc_data.size(), pred.score.size());
     return 0;
 }

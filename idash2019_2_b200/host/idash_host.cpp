@@ -6,11 +6,18 @@
 
 #include <algorithm>
 #include <atomic>
+#include <charconv>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <future>
+#include <mutex>
 #include <thread>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
 
 #include <sys/resource.h>
 #include <sys/time.h>
@@ -44,8 +51,8 @@ unsigned host_threads() {
 
 // runs fn(begin, end) over [0, n) split into contiguous ranges, one per worker thread
 template <class F>
-void parallel_ranges(size_t n, F fn) {
-    const size_t nt = std::max<size_t>(1, std::min<size_t>(host_threads(), n / 64 + 1));
+void parallel_ranges(size_t n, F fn, size_t grain = 64) {
+    const size_t nt = std::max<size_t>(1, std::min<size_t>(host_threads(), n / grain + (grain > 1)));
     if (nt == 1) { fn((size_t) 0, n); return; }
     std::vector<std::thread> th;
     for (size_t t = 0; t < nt; ++t) th.emplace_back([=]() { fn(n * t / nt, n * (t + 1) / nt); });
@@ -68,13 +75,45 @@ void host_buf_free(void *p, bool pinned) {
 }
 
 // one context per process (one process per GPU)
-idash_b200_ctx *gpu_ctx() {
+// (thread-safe: the cloud binary creates it on a helper thread while the model files are parsed; `die` = false is that
+// helper's probe -- a box without a GPU must still run the file-format half of this layer)
+idash_b200_ctx *gpu_ctx(bool die = true) {
     static idash_b200_ctx *ctx = nullptr;
-    if (!ctx) {
-        const int rc = idash_b200_init(&ctx, idash_host_device());
-        if (rc != IDASH_B200_OK) DIE_DRAMATICALLY("idash_b200_init: " << idash_b200_last_error());
-    }
+    static string error;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        if (idash_b200_init(&ctx, idash_host_device()) != IDASH_B200_OK) { ctx = nullptr; error = idash_b200_last_error(); }
+    });
+    if (!ctx && die) DIE_DRAMATICALLY("idash_b200_init: " << error);
     return ctx;
+}
+
+// Whole-range pread / pwrite by a pool of threads: a 2 GB ciphertext file moves through the page cache at memory speed
+// instead of one core's memcpy speed (eval/idash.cpp:513-613 streams record by record).
+void parallel_file_io(int fd, uint8_t *buf, size_t bytes, off_t off0, bool write, const char *what) {
+    std::atomic<bool> bad(false);
+    const size_t piece = (size_t) 8 << 20;
+    const size_t n_pieces = (bytes + piece - 1) / piece;
+    std::atomic<size_t> next(0);
+    const size_t nt = std::max<size_t>(1, std::min<size_t>(host_threads(), n_pieces));
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nt; ++t)
+        th.emplace_back([&]() {
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= n_pieces || bad) return;
+                size_t lo = i * piece;
+                const size_t hi = std::min(bytes, lo + piece);
+                while (lo < hi) {
+                    const ssize_t r = write ? ::pwrite(fd, buf + lo, hi - lo, off0 + (off_t) lo) : ::pread(fd, buf + lo, hi - lo, off0 + (off_t) lo);
+                    if (r < 0 && errno == EINTR) continue;
+                    if (r <= 0) { bad = true; return; }
+                    lo += (size_t) r;
+                }
+            }
+        });
+    for (auto &x : th) x.join();
+    REQUIRE_DRAMATICALLY(!bad, (write ? "short write to encrypted " : "truncated encrypted ") << what << " file");
 }
 
 void read_exact(std::istream &in, void *dst, size_t n, const char *what) {
@@ -116,22 +155,40 @@ void read_params_stream(IdashParams &p, std::istream &in) {
 }
 
 // whole ciphertext file -> slab; checks the size and every record's TLWE type uid (tfhe_io.cpp:308 aborts on a bad one)
+// Buffered write()s to ONE file are serialised by the inode lock (measured: 8 threads of pwrite are no faster than one),
+// so a large image is copied through a shared mapping instead: page-cache pages are faulted in and filled by all
+// threads at once. Falls back to pwrite where the file cannot be mapped.
+void parallel_file_write(int fd, uint8_t *buf, size_t bytes, const char *what) {
+    if (bytes == 0) return;
+    void *map = getenv("IDASH_HOST_NO_MMAP") ? MAP_FAILED : ::mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    if (map == MAP_FAILED) { parallel_file_io(fd, buf, bytes, 0, true, what); return; }
+    const size_t piece = (size_t) 4 << 20;
+    parallel_ranges((bytes + piece - 1) / piece, [&](size_t b, size_t e) {
+        const size_t lo = b * piece, hi = std::min(bytes, e * piece);
+        if (lo < hi) memcpy(static_cast<uint8_t *>(map) + lo, buf + lo, hi - lo);
+    }, 1);
+    REQUIRE_DRAMATICALLY(::munmap(map, bytes) == 0, "error unmapping encrypted " << what << " file");
+}
+
 std::shared_ptr<CtSlab> read_ct_file(const string &filename, const char *what) {
-    FILE *f = fopen(filename.c_str(), "rb");
-    REQUIRE_DRAMATICALLY(f != nullptr, "Cannot open encrypted " << what << " file for read");
+    const int fd = ::open(filename.c_str(), O_RDONLY);
+    REQUIRE_DRAMATICALLY(fd >= 0, "Cannot open encrypted " << what << " file for read");
     uint64_t count = 0;
-    REQUIRE_DRAMATICALLY(fread(&count, 8, 1, f) == 1, "truncated encrypted " << what << " file");
+    REQUIRE_DRAMATICALLY(::pread(fd, &count, 8, 0) == 8, "truncated encrypted " << what << " file");
     REQUIRE_DRAMATICALLY(count < ((uint64_t) 1 << 32), "encrypted " << what << " file: implausible record count");
     auto slab = std::make_shared<CtSlab>(count);
-    const size_t bytes = (size_t) count * REC;
-    REQUIRE_DRAMATICALLY(bytes == 0 || fread(slab->records(), 1, bytes, f) == bytes, "truncated encrypted " << what << " file");
-    fclose(f);
-    for (uint64_t i = 0; i < count; ++i) {
-        int32_t uid;
-        memcpy(&uid, slab->record(i) + 4, 4);
-        REQUIRE_DRAMATICALLY(uid == IDASH_B200_TLWE_SAMPLE_UID, "encrypted " << what << " file: bad TLWE sample type in record " << i);
-    }
-    slab->pull_variances();
+    parallel_file_io(fd, slab->records(), (size_t) count * REC, 8, false, what);
+    ::close(fd);
+    std::atomic<uint64_t> bad_rec(UINT64_MAX);
+    parallel_ranges(count, [&](size_t b, size_t e) {
+        for (size_t i = b; i < e; ++i) {
+            int32_t uid;
+            memcpy(&uid, slab->record(i) + 4, 4);
+            if (uid != IDASH_B200_TLWE_SAMPLE_UID) { bad_rec = i; return; }
+            memcpy(&slab->samples[i].current_variance, slab->record(i) + REC_VAR_OFF, 8);
+        }
+    });
+    REQUIRE_DRAMATICALLY(bad_rec == UINT64_MAX, "encrypted " << what << " file: bad TLWE sample type in record " << bad_rec.load());
     return slab;
 }
 
@@ -149,13 +206,18 @@ bool map_matches_slab(const Map &m, const std::shared_ptr<CtSlab> &slab) {
 
 template <class Map>
 void write_ct_file(const Map &m, const std::shared_ptr<CtSlab> &slab, const string &filename, const char *what) {
+    if (map_matches_slab(m, slab)) {   // the slab image IS the file: one parallel write
+        slab->push_variances();
+        const int fd = ::open(filename.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0644);
+        REQUIRE_DRAMATICALLY(fd >= 0, "Cannot open encrypted " << what << " file for write");
+        REQUIRE_DRAMATICALLY(::ftruncate(fd, (off_t) slab->image_bytes()) == 0, "cannot size encrypted " << what << " file");
+        parallel_file_write(fd, slab->image(), slab->image_bytes(), what);
+        REQUIRE_DRAMATICALLY(::close(fd) == 0, "error closing encrypted " << what << " file");
+        return;
+    }
     FILE *f = fopen(filename.c_str(), "wb");
     REQUIRE_DRAMATICALLY(f != nullptr, "Cannot open encrypted " << what << " file for write");
-    if (map_matches_slab(m, slab)) {
-        slab->push_variances();
-        const size_t n = slab->image_bytes();
-        REQUIRE_DRAMATICALLY(fwrite(slab->image(), 1, n, f) == n, "short write to encrypted " << what << " file");
-    } else {   // containers not built by this library: record by record, in the map's iteration order
+    {   // containers not built by this library: record by record, in the map's iteration order
         const uint64_t count = m.size();
         fwrite(&count, 8, 1, f);
         std::vector<uint8_t> rec(REC);
@@ -206,6 +268,47 @@ std::unique_ptr<PackedCts> pack_map(const Map &m) {
     return pk;
 }
 
+// Helper-thread warm-up for the cloud stage (started by read_model, collected by cloud_compute_score): GPU context +
+// the pinned slab the output ciphertexts will be copied into.
+std::mutex g_warm_mutex;
+std::shared_future<void> g_warm_ctx;
+std::future<std::shared_ptr<CtSlab>> g_warm_slab;
+// read_params is the first call of both GPU stages: start creating the CUDA context (0.3-0.5 s) right away
+void warm_up_context() {
+    if (getenv("IDASH_HOST_NO_WARMUP")) return;
+    std::lock_guard<std::mutex> lock(g_warm_mutex);
+    if (g_warm_ctx.valid()) return;
+    g_warm_ctx = std::async(std::launch::async, []() {
+        const double t0 = now_s();
+        const bool ok = gpu_ctx(false) != nullptr;
+        if (getenv("IDASH_HOST_TIMING")) fprintf(stderr, "[idash_host] warm-up: context %s in %.3f s\n", ok ? "created" : "unavailable", now_s() - t0);
+    }).share();
+}
+void warm_up_cloud(uint64_t n_rows) {
+    if (getenv("IDASH_HOST_NO_WARMUP")) return;
+    warm_up_context();
+    std::lock_guard<std::mutex> lock(g_warm_mutex);
+    if (g_warm_slab.valid()) return;
+    std::shared_future<void> ctx_ready = g_warm_ctx;
+    g_warm_slab = std::async(std::launch::async, [n_rows, ctx_ready]() {
+        ctx_ready.wait();
+        if (!gpu_ctx(false)) return std::shared_ptr<CtSlab>();      // no GPU: nothing to warm up
+        const double t0 = now_s();
+        auto slab = std::make_shared<CtSlab>(n_rows);
+        if (getenv("IDASH_HOST_TIMING")) fprintf(stderr, "[idash_host] warm-up: pinned output slab (%.2f GB) in %.3f s\n", slab->image_bytes() * 1e-9, now_s() - t0);
+        return slab;
+    });
+}
+std::shared_ptr<CtSlab> take_output_slab(uint64_t n_rows) {
+    std::shared_ptr<CtSlab> slab;
+    {
+        std::lock_guard<std::mutex> lock(g_warm_mutex);
+        if (g_warm_slab.valid()) slab = g_warm_slab.get();
+    }
+    if (!slab || slab->count != n_rows) slab = std::make_shared<CtSlab>(n_rows);
+    return slab;
+}
+
 template <class Map>
 bool all_views_of(const Map &m, const std::shared_ptr<CtSlab> &slab) {
     if (!slab || slab->count != m.size()) return false;
@@ -244,6 +347,7 @@ void CtSlab::push_variances() { for (uint64_t i = 0; i < count; ++i) memcpy(reco
 // iteration order, must evolve exactly as in the reference, because that order is the record order of the files it
 // writes (eval/idash.cpp:550, 607) and the row order of the model walk (eval/idash.cpp:772).
 void read_params(IdashParams &params, const string &filename) {
+    warm_up_context();
     std::ifstream in(filename.c_str(), std::ios::binary);
     REQUIRE_DRAMATICALLY(in.is_open(), "Cannot open parameters file for read");
     read_params_stream(params, in);
@@ -303,38 +407,44 @@ void write_encrypted_predictions(const EncryptedPredictions &p, const IdashParam
 // the model map is then filled in the reference's order (iteration order of out_features_index, variant 0..2),
 // which fixes the record order of encrypted_prediction.bin downstream.
 void read_model(Model &model, const IdashParams &params, const string &path) {
+    // Only the cloud stage loads a model: bring the GPU context up and allocate the pinned output slab on a helper
+    // thread while the files are parsed (CUDA initialisation and page-locking 2 GB are the two largest fixed costs
+    // of cloud_compute_score at iDASH scale).
+    warm_up_cloud(3 * (uint64_t) params.out_features_index.size());
+
+    const double t_begin = now_s();
     struct Job { uint64_t pos; std::array<FeatBigIndex, 3> out; };
     std::vector<Job> jobs;
     jobs.reserve(params.out_features_index.size());
     for (const auto &e : params.out_features_index) jobs.push_back({e.first, e.second});
-    std::vector<std::array<std::vector<std::pair<FeatBigIndex, int32_t>>, 3>> parsed(jobs.size());
+    std::vector<std::array<std::unordered_map<FeatBigIndex, int32_t>, 3>> parsed(jobs.size());
     std::atomic<bool> unknown(false);
     parallel_ranges(jobs.size(), [&](size_t b, size_t e) {
+        string fn;
         for (size_t i = b; i < e; ++i) {
             for (int snp = 0; snp < 3; ++snp) {
-                const string fn = path + "/" + std::to_string(jobs[i].pos) + "_" + std::to_string(snp) + ".hr";
+                fn = path; fn += '/'; fn += std::to_string(jobs[i].pos); fn += '_'; fn += (char) ('0' + snp); fn += ".hr";
                 auto &dst = parsed[i][snp];
                 for (const auto &c : read_lines(fn)) {
-                    if (c.first == "Constant") { dst.push_back({params.constant_bigIndex(), c.second}); continue; }
+                    if (c.first == "Constant") { dst[params.constant_bigIndex()] = c.second; continue; }
                     const size_t u = c.first.find('_');
                     char *end = nullptr;
                     const uint64_t pos = strtoull(c.first.c_str(), &end, 10);
                     const auto it = params.in_features_index.find(pos);
                     const long v = u == string::npos ? -1 : strtol(c.first.c_str() + u + 1, nullptr, 10);
                     if (it == params.in_features_index.end() || v < 0 || v > 2) { unknown = true; continue; }
-                    dst.push_back({it->second[(size_t) v], c.second});
+                    dst[it->second[(size_t) v]] = c.second;                       // a repeated name overwrites, as in parse_vw
                 }
             }
         }
     });
     // the reference throws std::out_of_range (uncaught -> abort) on a tag position that params.bin does not know
     REQUIRE_DRAMATICALLY(!unknown, "model refers to a tag SNP feature that is not in the parameters file");
-    for (size_t i = 0; i < jobs.size(); ++i) {
-        for (int snp = 0; snp < 3; ++snp) {
-            auto &row = model.model[jobs[i].out[snp]] = std::unordered_map<FeatBigIndex, int32_t>();
-            for (const auto &c : parsed[i][snp]) row[c.first] = c.second;     // a repeated name overwrites, as in parse_vw
-        }
-    }
+    const double t_parsed = now_s();
+    // outer map: filled serially in the reference's order (its iteration order is the row order downstream)
+    for (size_t i = 0; i < jobs.size(); ++i)
+        for (int snp = 0; snp < 3; ++snp) model.model[jobs[i].out[snp]] = std::move(parsed[i][snp]);
+    if (getenv("IDASH_HOST_TIMING")) fprintf(stderr, "[idash_host] read_model: parse %.3f s, fill %.3f s\n", t_parsed - t_begin, now_s() - t_parsed);
 }
 
 // eval/idash.cpp:436-469: header, then for every sample, for every target in file order, "<sample>,<target>,<p0>,<p1>,<p2>".
@@ -342,39 +452,74 @@ void read_model(Model &model, const IdashParams &params, const string &path) {
 // buffers and written with large writes instead of one flush per row.
 void write_decrypted_predictions(const DecryptedPredictions &predictions, const IdashParams &params, const string &filename,
                                  const bool PRINT_POS_NAME) {
-    FILE *f = fopen(filename.c_str(), "wb");
-    REQUIRE_DRAMATICALLY(f != nullptr, "Cannot open result file for write");
-    fputs("Subject ID,target SNP,0,1,2\n", f);
+    const int fd = ::open(filename.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    REQUIRE_DRAMATICALLY(fd >= 0, "Cannot open result file for write");
+    static const char header[] = "Subject ID,target SNP,0,1,2\n";
+    off_t file_off = (off_t) (sizeof(header) - 1);
+    REQUIRE_DRAMATICALLY(::pwrite(fd, header, sizeof(header) - 1, 0) == (ssize_t) (sizeof(header) - 1), "short write to result file");
     const size_t G = params.out_position_names.size();
+    const size_t S = params.NUM_SAMPLES;
     std::vector<const std::array<std::vector<float>, 3> *> rows(G);
-    std::vector<string> labels(G);
+    std::vector<string> labels(G);          // ",<label>,"
+    size_t label_max = 0;
     for (size_t g = 0; g < G; ++g) {
         rows[g] = &predictions.score.at(params.out_position_names[g].first);
-        labels[g] = PRINT_POS_NAME ? params.out_position_names[g].second : std::to_string(params.out_position_names[g].first);
+        labels[g] = "," + (PRINT_POS_NAME ? params.out_position_names[g].second : std::to_string(params.out_position_names[g].first)) + ",";
+        label_max = std::max(label_max, labels[g].size());
     }
-    const size_t S = params.NUM_SAMPLES;
-    const size_t batch = std::max<size_t>(1, std::min<size_t>(S, (size_t) host_threads() * 4));
-    std::vector<string> bufs(batch);
+    // A batch of consecutive samples at a time: (1) gather the batch's scores into a sample-major tile -- the score
+    // vectors are target-major, so this is the one pass that walks 3 G separate heap vectors, done with contiguous
+    // reads; (2) every thread formats whole samples into its own buffer; (3) the buffers go out with parallel pwrites at
+    // offsets known from their sizes. The reference issues S x G hash lookups and one flush per row (eval/idash.cpp:436-469).
+    const size_t batch = std::max<size_t>(1, std::min<size_t>(S, (size_t) host_threads() * 2));
+    const size_t row_max = 12 + label_max + 3 * 16 + 1;      // "<sample>" + label + three "%g," + newline
+    std::vector<float> tile(batch * G * 3);
+    std::vector<std::vector<char>> bufs(batch);
+    std::vector<size_t> used(batch, 0);
+    for (auto &b : bufs) b.resize(G * row_max);
     for (size_t s0 = 0; s0 < S; s0 += batch) {
         const size_t nb = std::min(batch, S - s0);
+        parallel_ranges(G, [&](size_t b, size_t e) {
+            for (size_t g = b; g < e; ++g)
+                for (int v = 0; v < 3; ++v) {
+                    const float *src = (*rows[g])[v].data() + s0;
+                    for (size_t i = 0; i < nb; ++i) tile[(i * G + g) * 3 + v] = src[i];
+                }
+        });
         parallel_ranges(nb, [&](size_t b, size_t e) {
-            char tmp[96];
             for (size_t i = b; i < e; ++i) {
-                string &out = bufs[i];
-                out.clear();
-                const string sid = std::to_string(s0 + i);
+                char *out = bufs[i].data();
+                char sid[24];
+                const size_t sid_n = (size_t) (std::to_chars(sid, sid + sizeof(sid), s0 + i).ptr - sid);
+                const float *t = tile.data() + i * G * 3;
                 for (size_t g = 0; g < G; ++g) {
-                    const auto &r = *rows[g];
-                    out += sid; out += ','; out += labels[g]; out += ',';
-                    const int n = snprintf(tmp, sizeof(tmp), "%g,%g,%g\n", (double) r[0][s0 + i], (double) r[1][s0 + i], (double) r[2][s0 + i]);
-                    out.append(tmp, (size_t) n);
+                    memcpy(out, sid, sid_n); out += sid_n;
+                    memcpy(out, labels[g].data(), labels[g].size()); out += labels[g].size();
+                    // operator<<(float) = printf("%g", double): std::to_chars(general, precision 6) is specified as exactly that
+                    out = std::to_chars(out, out + 24, (double) t[3 * g + 0], std::chars_format::general, 6).ptr; *out++ = ',';
+                    out = std::to_chars(out, out + 24, (double) t[3 * g + 1], std::chars_format::general, 6).ptr; *out++ = ',';
+                    out = std::to_chars(out, out + 24, (double) t[3 * g + 2], std::chars_format::general, 6).ptr; *out++ = '\n';
+                }
+                used[i] = (size_t) (out - bufs[i].data());
+            }
+        }, 1);
+        std::vector<off_t> offs(nb);
+        for (size_t i = 0; i < nb; ++i) { offs[i] = file_off; file_off += (off_t) used[i]; }
+        std::atomic<bool> bad(false);
+        parallel_ranges(nb, [&](size_t b, size_t e) {
+            for (size_t i = b; i < e; ++i) {
+                size_t lo = 0;
+                while (lo < used[i]) {
+                    const ssize_t r = ::pwrite(fd, bufs[i].data() + lo, used[i] - lo, offs[i] + (off_t) lo);
+                    if (r < 0 && errno == EINTR) continue;
+                    if (r <= 0) { bad = true; return; }
+                    lo += (size_t) r;
                 }
             }
-        });
-        for (size_t i = 0; i < nb; ++i)
-            REQUIRE_DRAMATICALLY(fwrite(bufs[i].data(), 1, bufs[i].size(), f) == bufs[i].size(), "short write to result file");
+        }, 1);
+        REQUIRE_DRAMATICALLY(!bad, "short write to result file");
     }
-    REQUIRE_DRAMATICALLY(fclose(f) == 0, "error closing result file");
+    REQUIRE_DRAMATICALLY(::close(fd) == 0, "error closing result file");
 }
 
 // ---- the two GPU stages ----------------------------------------------------------------------------------------
@@ -389,38 +534,40 @@ void cloud_compute_score(EncryptedPredictions &enc_preds, const EncryptedData &e
     REQUIRE_DRAMATICALLY(params.k == 1, "blah");                                        // eval/idash.cpp:768
     REQUIRE_DRAMATICALLY(enc_preds.score.empty(), "shit happens again");                // createAndGet, eval/idash.h:181
     const uint64_t n_rows = model.model.size();
+    const bool timing = getenv("IDASH_HOST_TIMING") != nullptr;
+    const double t_begin = now_s();
 
-    // Model -> CSR, rows in the map's iteration order (the order the reference walks them, eval/idash.cpp:772-777)
-    std::vector<uint32_t> out_bidx(n_rows), col;
+    // Model -> CSR, rows in the map's iteration order (the order the reference walks them, eval/idash.cpp:772-777);
+    // row pointers serially, entries by a pool of threads
+    std::vector<uint32_t> out_bidx(n_rows);
     std::vector<uint64_t> row_ptr(n_rows + 1, 0);
-    std::vector<int32_t> coef;
+    std::vector<const std::unordered_map<FeatBigIndex, int32_t> *> rows(n_rows);
     {
-        uint64_t r = 0, nnz = 0;
-        for (const auto &row : model.model) nnz += row.second.size();
-        col.reserve(nnz); coef.reserve(nnz);
+        uint64_t r = 0;
         for (const auto &row : model.model) {
             out_bidx[r] = row.first;
-            for (const auto &c : row.second) {
-                if (c.first != params.constant_bigIndex())
-                    (void) enc_data.getTLWE(c.first, params);                           // dies like the reference on a missing input
-                col.push_back(c.first); coef.push_back(c.second);
-            }
-            row_ptr[++r] = col.size();
+            rows[r] = &row.second;
+            row_ptr[r + 1] = row_ptr[r] + row.second.size();
+            ++r;
         }
     }
+    std::vector<uint32_t> col(row_ptr[n_rows]);
+    std::vector<int32_t> coef(row_ptr[n_rows]);
+    std::atomic<bool> missing(false);
+    parallel_ranges(n_rows, [&](size_t b, size_t e) {
+        for (size_t r = b; r < e; ++r) {
+            uint64_t k = row_ptr[r];
+            for (const auto &c : *rows[r]) {
+                if (c.first != params.constant_bigIndex() && enc_data.enc_data.find(params.feature_indexOf(c.first)) == enc_data.enc_data.end())
+                    missing = true;
+                col[k] = c.first; coef[k] = c.second;
+                ++k;
+            }
+        }
+    });
+    REQUIRE_DRAMATICALLY(!missing, "shit happens before");                              // getTLWE, eval/idash.h:164
 
-    // outputs: one slab; the map is filled in the reference's insertion order, then record slot k goes to the k-th
-    // element in ITERATION order, so that the slab is the image of encrypted_prediction.bin (eval/idash.cpp:607)
-    auto slab = std::make_shared<CtSlab>(n_rows);
-    for (uint64_t r = 0; r < n_rows; ++r) enc_preds.score.emplace(out_bidx[r], nullptr);
-    {
-        uint64_t k = 0;
-        for (auto &it : enc_preds.score) it.second = &slab->samples[k++];
-    }
-    std::vector<uint32_t> slot_of_row(n_rows);
-    for (uint64_t r = 0; r < n_rows; ++r) slot_of_row[r] = (uint32_t) slab->slot_of(enc_preds.score.at(out_bidx[r]));
-    enc_preds.slab = slab;
-
+    const double t_csr0 = now_s();
     idash_b200_ctx *ctx = gpu_ctx();
     const double t0 = now_s();
     idash_b200_model_desc desc;
@@ -428,6 +575,26 @@ void cloud_compute_score(EncryptedPredictions &enc_preds, const EncryptedData &e
     desc.n_rows = n_rows; desc.out_bidx = out_bidx.data(); desc.row_ptr = row_ptr.data(); desc.col = col.data(); desc.coef = coef.data();
     idash_b200_model *dm = nullptr;
     if (idash_b200_model_upload(ctx, &desc, &dm) != IDASH_B200_OK) DIE_DRAMATICALLY("idash_b200_model_upload: " << idash_b200_last_error());
+    const double t_upload = now_s();
+    // outputs: one slab; the map is filled in the reference's insertion order, then record slot k goes to the k-th
+    // element in ITERATION order, so that the slab is the image of encrypted_prediction.bin (eval/idash.cpp:607)
+    auto slab = take_output_slab(n_rows);
+    const double t_slab = now_s();
+    for (uint64_t r = 0; r < n_rows; ++r) enc_preds.score.emplace(out_bidx[r], nullptr);
+    std::vector<uint32_t> slot_of_row(n_rows);
+    {
+        // the k-th element in iteration order gets slot k; its row is found through a bigIndex -> row table
+        std::unordered_map<FeatBigIndex, uint32_t> row_of;
+        row_of.reserve(n_rows);
+        for (uint64_t r = 0; r < n_rows; ++r) row_of.emplace(out_bidx[r], (uint32_t) r);
+        uint64_t k = 0;
+        for (auto &it : enc_preds.score) {
+            it.second = &slab->samples[k];
+            slot_of_row[row_of.at(it.first)] = (uint32_t) k;
+            ++k;
+        }
+    }
+    enc_preds.slab = slab;
 
     idash_b200_cts in, out;
     std::unique_ptr<PackedCts> staged;
@@ -439,11 +606,16 @@ void cloud_compute_score(EncryptedPredictions &enc_preds, const EncryptedData &e
         in = {IDASH_B200_LAYOUT_PACKED, staged->words(), staged->count, staged->index(), staged->variance()};
     }
     out = {IDASH_B200_LAYOUT_RECORDS, slab->records(), n_rows, nullptr, nullptr};
+    const double t_eval0 = now_s();
     const int rc = idash_b200_cloud_eval_host(ctx, dm, &in, &out, slot_of_row.data());
     if (rc != IDASH_B200_OK) DIE_DRAMATICALLY("idash_b200_cloud_eval_host: " << idash_b200_last_error());
+    const double t_eval1 = now_s();
     idash_b200_model_free(dm);
-    g_last_gpu_seconds = now_s() - t0;
+    g_last_gpu_seconds = (t_upload - t0) + (t_eval1 - t_eval0);
     slab->pull_variances();
+    if (timing)
+        fprintf(stderr, "[idash_host] cloud_compute_score: csr %.3f s, context wait %.3f s, model_upload %.3f s, output slab wait %.3f s, containers %.3f s, cloud_eval_host %.3f s, total %.3f s\n",
+                t_csr0 - t_begin, t0 - t_csr0, t_upload - t0, t_slab - t_upload, t_eval0 - t_slab, t_eval1 - t_eval0, now_s() - t_begin);
 }
 
 void decrypt_predictions(DecryptedPredictions &predictions, const EncryptedPredictions &enc_preds, const IdashKey &key) {

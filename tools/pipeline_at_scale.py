@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--neighbors", type=int, default=5)
     ap.add_argument("--workdir", default=None)
     ap.add_argument("--decrypt", action="store_true")
+    ap.add_argument("--ref-decrypt", action="store_true")
     ap.add_argument("--no-gpu", action="store_true")
     a = ap.parse_args()
     from idash2019_2_b200 import synth
@@ -78,19 +79,28 @@ def main():
     if not a.no_gpu:
         bins = ROOT / "idash2019_2_b200" / "lib" / "bin"
         t0 = time.perf_counter()
-        out = subprocess.run([str(bins / "cloud"), str(work / "model")], cwd=work / "b200", capture_output=True, text=True)
+        out = subprocess.run([str(bins / "cloud"), str(work / "model")], cwd=work / "b200", capture_output=True, text=True,
+                             env=dict(os.environ, IDASH_HOST_TIMING="1"))
         assert out.returncode == 0, out.stdout + out.stderr
         res["b200_cloud"] = bench_block(out.stdout)
+        res["b200_cloud"]["phases"] = [ln for ln in out.stderr.splitlines() if ln.startswith("[idash_host]")]
         res["b200_cloud"]["wall_s"] = time.perf_counter() - t0
         t0 = time.perf_counter()
         same = subprocess.run(["cmp", str(work / "ref" / "encrypted_prediction.bin"), str(work / "b200" / "encrypted_prediction.bin")]).returncode == 0
         res["encrypted_prediction_byte_identical"] = same
         res["cmp_s"] = time.perf_counter() - t0
         if a.decrypt:
+            if a.ref_decrypt:      # ~5 minutes of host time at iDASH scale (one flush per csv row)
+                t0 = time.perf_counter()
+                rout = po.run_ref_bin("decrypt", ["bypos"], work / "ref")
+                res["ref_decrypt"] = bench_block(rout)
+                res["ref_decrypt"]["wall_s"] = time.perf_counter() - t0
             t0 = time.perf_counter()
-            out = subprocess.run([str(bins / "decrypt"), "bypos"], cwd=work / "b200", capture_output=True, text=True)
+            out = subprocess.run([str(bins / "decrypt"), "bypos"], cwd=work / "b200", capture_output=True, text=True,
+                                 env=dict(os.environ, IDASH_HOST_TIMING="1"))
             assert out.returncode == 0, out.stdout + out.stderr
             res["b200_decrypt"] = bench_block(out.stdout)
+            res["b200_decrypt"]["phases"] = [ln for ln in out.stderr.splitlines() if ln.startswith("[idash_host]")]
             res["b200_decrypt"]["wall_s"] = time.perf_counter() - t0
             res["bytes"]["result_bypos_csv"] = (work / "b200" / "result_bypos.csv").stat().st_size
     print(json.dumps(res))
