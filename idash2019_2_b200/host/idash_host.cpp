@@ -59,19 +59,38 @@ void parallel_ranges(size_t n, F fn, size_t grain = 64) {
     for (auto &x : th) x.join();
 }
 
-// Host staging memory: pinned through the library when a CUDA device is there; plain aligned memory otherwise, so
-// that the file-format half of this layer also works on a box without a GPU (the compute calls then fail loudly).
-struct HostBuf { void *p; bool pinned; };
+// Host staging memory for ciphertext slabs and score matrices. Default: anonymous mapping with transparent huge pages,
+// pre-faulted by all threads -- pageable. Measured on the B200 box for the 2 GB output slab (tools/pin_bench.cu): cudaHostAlloc
+// 0.93 s (+ 0.035 s D2H), mmap + touch + cudaHostRegister 0.20 s (+ 0.036 s), mmap + touch and a pageable D2H 0.045 + 0.105 s.
+// For a buffer that is written or read by the device ONCE, page-locking costs more than it saves, and cudaHostAlloc holds a
+// driver lock that stalls the concurrent model upload. IDASH_HOST_PIN=alloc restores cudaHostAlloc.
+enum { HOST_MEM_MALLOC = 0, HOST_MEM_PINNED = 1, HOST_MEM_MAPPED = 2 };
+struct HostBuf { void *p; int kind; size_t bytes; };
 HostBuf host_buf_alloc(size_t bytes) {
     void *p = nullptr;
-    if (idash_b200_host_alloc(&p, bytes) == IDASH_B200_OK) return {p, true};
+    const char *pin = getenv("IDASH_HOST_PIN");
+    if (pin && !strcmp(pin, "alloc") && idash_b200_host_alloc(&p, bytes) == IDASH_B200_OK) return {p, HOST_MEM_PINNED, bytes};
+    if (bytes >= ((size_t) 4 << 20)) {
+        const size_t huge = (size_t) 2 << 20, len = (bytes + huge - 1) & ~(huge - 1);
+        p = ::mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (p != MAP_FAILED) {
+            ::madvise(p, len, MADV_HUGEPAGE);
+            uint8_t *b = static_cast<uint8_t *>(p);
+            parallel_ranges(len / huge, [&](size_t lo, size_t hi) {
+                for (size_t i = lo * huge; i < hi * huge; i += 4096) b[i] = 0;     // fault the pages in, all threads at once
+            }, 1);
+            return {p, HOST_MEM_MAPPED, len};
+        }
+    }
     p = aligned_alloc(256, (bytes + 255) & ~(size_t) 255);
     REQUIRE_DRAMATICALLY(p != nullptr, "out of host memory (" << bytes << " bytes)");
-    return {p, false};
+    return {p, HOST_MEM_MALLOC, bytes};
 }
-void host_buf_free(void *p, bool pinned) {
-    if (!p) return;
-    if (pinned) idash_b200_host_free(p); else free(p);
+void host_buf_free(const HostBuf &b) {
+    if (!b.p) return;
+    if (b.kind == HOST_MEM_PINNED) idash_b200_host_free(b.p);
+    else if (b.kind == HOST_MEM_MAPPED) ::munmap(b.p, b.bytes);
+    else free(b.p);
 }
 
 // one context per process (one process per GPU)
@@ -238,17 +257,17 @@ void write_ct_file(const Map &m, const std::shared_ptr<CtSlab> &slab, const stri
 // pinned staging buffer for containers whose samples are not views into a slab
 struct PackedCts {
     void *mem = nullptr;
-    bool pinned = false;
+    HostBuf buf{nullptr, 0, 0};
     uint64_t count = 0;
     uint32_t *words() const { return static_cast<uint32_t *>(mem); }
     uint32_t *index() const { return words() + count * IDASH_B200_CT_WORDS; }
     double *variance() const { return reinterpret_cast<double *>(static_cast<uint8_t *>(mem) + ((count * (IDASH_B200_CT_BYTES + 4u) + 7u) & ~(uint64_t) 7u)); }
     explicit PackedCts(uint64_t n) : count(n) {
         const size_t bytes = ((n * (IDASH_B200_CT_BYTES + 4u) + 7u) & ~(uint64_t) 7u) + n * 8u + 16u;
-        const HostBuf b = host_buf_alloc(bytes);
-        mem = b.p; pinned = b.pinned;
+        buf = host_buf_alloc(bytes);
+        mem = buf.p;
     }
-    ~PackedCts() { host_buf_free(mem, pinned); }
+    ~PackedCts() { host_buf_free(buf); }
 };
 
 template <class Map>
@@ -269,7 +288,7 @@ std::unique_ptr<PackedCts> pack_map(const Map &m) {
 }
 
 // Helper-thread warm-up for the cloud stage (started by read_model, collected by cloud_compute_score): GPU context +
-// the pinned slab the output ciphertexts will be copied into.
+// the slab the output ciphertexts will be copied into.
 std::mutex g_warm_mutex;
 std::shared_future<void> g_warm_ctx;
 std::future<std::shared_ptr<CtSlab>> g_warm_slab;
@@ -289,13 +308,10 @@ void warm_up_cloud(uint64_t n_rows) {
     warm_up_context();
     std::lock_guard<std::mutex> lock(g_warm_mutex);
     if (g_warm_slab.valid()) return;
-    std::shared_future<void> ctx_ready = g_warm_ctx;
-    g_warm_slab = std::async(std::launch::async, [n_rows, ctx_ready]() {
-        ctx_ready.wait();
-        if (!gpu_ctx(false)) return std::shared_ptr<CtSlab>();      // no GPU: nothing to warm up
+    g_warm_slab = std::async(std::launch::async, [n_rows]() {
         const double t0 = now_s();
         auto slab = std::make_shared<CtSlab>(n_rows);
-        if (getenv("IDASH_HOST_TIMING")) fprintf(stderr, "[idash_host] warm-up: pinned output slab (%.2f GB) in %.3f s\n", slab->image_bytes() * 1e-9, now_s() - t0);
+        if (getenv("IDASH_HOST_TIMING")) fprintf(stderr, "[idash_host] warm-up: output slab (%.2f GB) in %.3f s\n", slab->image_bytes() * 1e-9, now_s() - t0);
         return slab;
     });
 }
@@ -325,7 +341,8 @@ bool all_views_of(const Map &m, const std::shared_ptr<CtSlab> &slab) {
 CtSlab::CtSlab(uint64_t n) : count(n), samples(n), polys(2 * n) {
     const HostBuf hb = host_buf_alloc(image_bytes() + 16);
     mem = static_cast<uint8_t *>(hb.p);   // at least 256-byte aligned either way
-    pinned = hb.pinned;
+    mem_kind = hb.kind;
+    mem_bytes = hb.bytes;
     memcpy(mem, &count, 8);
     for (uint64_t i = 0; i < n; ++i) {
         polys[2 * i].N = polys[2 * i + 1].N = (int32_t) IdashParams::N;
@@ -337,7 +354,7 @@ CtSlab::CtSlab(uint64_t n) : count(n), samples(n), polys(2 * n) {
         samples[i].k = (int32_t) IdashParams::k;
     }
 }
-CtSlab::~CtSlab() { host_buf_free(mem, pinned); }
+CtSlab::~CtSlab() { host_buf_free(HostBuf{mem, mem_kind, mem_bytes}); }
 uint32_t CtSlab::index_of(uint64_t i) const { uint32_t v; memcpy(&v, record(i), 4); return v; }
 void CtSlab::pull_variances() { for (uint64_t i = 0; i < count; ++i) memcpy(&samples[i].current_variance, record(i) + REC_VAR_OFF, 8); }
 void CtSlab::push_variances() { for (uint64_t i = 0; i < count; ++i) memcpy(record(i) + REC_VAR_OFF, &samples[i].current_variance, 8); }
@@ -407,9 +424,9 @@ void write_encrypted_predictions(const EncryptedPredictions &p, const IdashParam
 // the model map is then filled in the reference's order (iteration order of out_features_index, variant 0..2),
 // which fixes the record order of encrypted_prediction.bin downstream.
 void read_model(Model &model, const IdashParams &params, const string &path) {
-    // Only the cloud stage loads a model: bring the GPU context up and allocate the pinned output slab on a helper
-    // thread while the files are parsed (CUDA initialisation and page-locking 2 GB are the two largest fixed costs
-    // of cloud_compute_score at iDASH scale).
+    // Only the cloud stage loads a model: bring the GPU context up and allocate + fault in the output slab on helper
+    // threads while the files are parsed (CUDA initialisation and 2 GB of fresh host memory are the two largest fixed
+    // costs of cloud_compute_score at iDASH scale).
     warm_up_cloud(3 * (uint64_t) params.out_features_index.size());
 
     const double t_begin = now_s();
@@ -660,7 +677,7 @@ void decrypt_predictions(DecryptedPredictions &predictions, const EncryptedPredi
         for (size_t i = b; i < e; ++i)
             for (int snp = 0; snp < 3; ++snp) (*dst[i].v)[snp].assign(scores + dst[i].s[snp] * S, scores + (dst[i].s[snp] + 1) * S);
     });
-    host_buf_free(sb.p, sb.pinned);
+    host_buf_free(sb);
 }
 
 // ---- Profiler (eval/idash.cpp:935-965) -------------------------------------------------------------------------

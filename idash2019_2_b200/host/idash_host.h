@@ -4,7 +4,7 @@
 // on-disk formats, same error convention ("ERROR: ..." on stdout + abort(), eval/idash.h:12-14).
 //
 // What is different underneath (and why this is not the reference's header):
-//   * a ciphertext file is ONE pinned host slab (`CtSlab`) holding the record stream exactly as it is on disk
+//   * a ciphertext file is ONE host slab (`CtSlab`) holding the record stream exactly as it is on disk
 //     (eval/idash.cpp:540-556, 596-613); the TLweSample objects in the hash maps are views into that slab, so
 //     the C ABI consumes / produces the file image directly (IDASH_B200_LAYOUT_RECORDS) with no
 //     per-polynomial allocation or copy. Containers built by other code (separately allocated samples) still
@@ -91,13 +91,14 @@ struct Model {
     std::unordered_map<FeatBigIndex, std::unordered_map<FeatBigIndex, int32_t>> model;
 };
 
-// One pinned host allocation holding `count` ciphertext records in file layout, preceded by the u64 count:
+// One host allocation holding `count` ciphertext records in file layout, preceded by the u64 count:
 //   image() = { u64 count, count x { u32 index, i32 84, u32 a[1024], u32 b[1024], f64 variance } }
 // image() is 16-byte aligned, hence records() is 8 mod 16 and every word array is 16-byte aligned.
 struct CtSlab {
     uint64_t count = 0;
-    uint8_t *mem = nullptr;                 // idash_b200_host_alloc (pinned); pageable if there is no CUDA device
-    bool pinned = false;
+    uint8_t *mem = nullptr;                 // pre-faulted huge-page mapping (pageable); see host_buf_alloc in idash_host.cpp
+    int mem_kind = 0;
+    size_t mem_bytes = 0;
     std::vector<TLweSample> samples;        // views: samples[i].a[0].coefsT / b->coefsT point into record i
     std::vector<TorusPolynomial> polys;
 
