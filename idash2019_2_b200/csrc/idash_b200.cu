@@ -203,12 +203,42 @@ struct FinalizeParams {
     uint32_t n_ct_slots;
     const uint32_t *slot_of_row;
     double default_var;
+    const double *var_wsum;          // per row: sum of the weights (coefficient^2 of the region-0 entries)
+    const uint64_t *var_uniform;     // device: [0] != 0 -> the input variances are not all equal; [1] = bits of the common value;
+                                     // null -> every input has default_var
 };
+
+// Do all input ciphertexts carry the same variance? (They do when the inputs come from the reference's encrypt: alpha^2 = 2^-50
+// for every ciphertext, eval/idash.cpp:625.) flag[0] is cleared by the launcher; flag[1] receives the bits of slot 0's variance.
+__global__ void variance_scan_kernel(CtView in, uint64_t *flag) {
+    const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= in.count) return;
+    const unsigned long long v0 = in.records ? *reinterpret_cast<const unsigned long long *>(in.words + 8192)
+                                             : (unsigned long long) __double_as_longlong(in.variance[0]);
+    const unsigned long long v = in.records ? *reinterpret_cast<const unsigned long long *>(in.words + i * in.stride + 8192)
+                                            : (unsigned long long) __double_as_longlong(in.variance[i]);
+    if (i == 0) flag[1] = v0;
+    if (v != v0) flag[0] = 1;
+}
 
 __global__ void cloud_finalize_kernel(const FinalizeParams p) {
     const uint64_t r = p.row_lo + (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= p.n_rows) return;
     double var = 0.;
+    // Fast path: one common input variance that is a power of two (or zero). Then sum_e w_e * v = (sum_e w_e) * v EXACTLY (the
+    // weights are integers below 2^53 in total, the scaling is exact), so the per-entry walk -- 151 entries per row at
+    // neighbors = 50, read with a row-length stride -- collapses to one multiply. Anything else takes the general loop.
+    bool fast = false;
+    double v_common = p.default_var;
+    if (p.var_uniform) {
+        const unsigned long long bits = p.var_uniform[1];
+        fast = p.var_uniform[0] == 0 && (bits & 0x000FFFFFFFFFFFFFull) == 0 && ((bits >> 52) & 0x7FFu) != 0x7FFu;
+        v_common = __longlong_as_double((long long) bits);
+    } else {
+        fast = true;
+    }
+    if (fast) var = p.var_wsum[r] * v_common;
+    else
     for (uint64_t e = p.var_ptr[r]; e < p.var_ptr[r + 1]; ++e) {
         const uint32_t ct = p.var_ct[e];
         uint32_t slot = NO_SLOT;
@@ -329,6 +359,7 @@ struct idash_b200_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;     // used by the *_host entry points
     int *d_status = nullptr;
+    uint64_t *d_var_flag = nullptr;    // variance_scan_kernel's result (2 words)
     int *h_status = nullptr;           // pinned
     uint64_t launches = 0;
     int kernel_choice = IDASH_B200_KERNEL_AUTO;
@@ -358,6 +389,7 @@ struct idash_b200_model {
     uint64_t *d_var_ptr = nullptr;
     uint32_t *d_var_ct = nullptr;
     double *d_var_w = nullptr;
+    double *d_var_wsum = nullptr;
     uint32_t *d_out_bidx = nullptr;
     idash_b200_tile *d_tiles = nullptr;      // tensor-core layout (null when not eligible)
     uint32_t *d_tile_rows = nullptr;
@@ -384,6 +416,7 @@ extern "C" int idash_b200_init(idash_b200_ctx **out, int device) {
     c->sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaMalloc(&c->d_status, sizeof(int)));
+    CUDA_TRY(cudaMalloc(&c->d_var_flag, 2 * sizeof(uint64_t)));
     CUDA_TRY(cudaMemset(c->d_status, 0, sizeof(int)));
     CUDA_TRY(cudaMallocHost(&c->h_status, sizeof(int)));
     const int tc_smem_max = (int) tc_smem_bytes(IDASH_B200_TILE_KMAX);
@@ -417,6 +450,7 @@ extern "C" int idash_b200_destroy(idash_b200_ctx *c) {
     for (cudaEvent_t e : c->t_begin) cudaEventDestroy(e);
     for (cudaEvent_t e : c->t_end) cudaEventDestroy(e);
     if (c->d_status) cudaFree(c->d_status);
+    if (c->d_var_flag) cudaFree(c->d_var_flag);
     if (c->h_status) cudaFreeHost(c->h_status);
     delete c;
     return IDASH_B200_OK;
@@ -493,7 +527,7 @@ static int upload(T **dst, const T *src, size_t n) {
 extern "C" int idash_b200_model_free(idash_b200_model *m) {
     if (!m) return IDASH_B200_OK;
     cudaSetDevice(m->device);
-    cudaFree(m->d_groups); cudaFree(m->d_entries); cudaFree(m->d_var_ptr); cudaFree(m->d_var_ct); cudaFree(m->d_var_w);
+    cudaFree(m->d_groups); cudaFree(m->d_entries); cudaFree(m->d_var_ptr); cudaFree(m->d_var_ct); cudaFree(m->d_var_w); cudaFree(m->d_var_wsum);
     cudaFree(m->d_out_bidx);
     cudaFree(m->d_tiles); cudaFree(m->d_tile_rows); cudaFree(m->d_tile_bias); cudaFree(m->d_tile_coef); cudaFree(m->d_tile_used);
     cudaFree(m->d_feat_used);
@@ -514,7 +548,11 @@ extern "C" int idash_b200_model_upload(idash_b200_ctx *c, const idash_b200_model
     m->layout = L;
     m->device = c->device;
     CUDA_TRY(cudaSetDevice(c->device));
-    if ((rc = upload(&m->d_groups, L->groups.data(), L->groups.size())) ||
+    std::vector<double> wsum(L->n_rows, 0.);
+    for (uint64_t r = 0; r < L->n_rows; ++r)
+        for (uint64_t e = L->var_ptr[r]; e < L->var_ptr[r + 1]; ++e) wsum[r] += L->var_w[e];
+    if ((rc = upload(&m->d_var_wsum, wsum.data(), wsum.size())) ||
+        (rc = upload(&m->d_groups, L->groups.data(), L->groups.size())) ||
         (rc = upload(&m->d_entries, L->entries.data(), L->entries.size())) ||
         (rc = upload(&m->d_var_ptr, L->var_ptr.data(), L->var_ptr.size())) ||
         (rc = upload(&m->d_var_ct, L->var_ct.data(), L->var_ct.size())) ||
@@ -635,6 +673,14 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
     f.n_ct_slots = n_ct_slots;
     f.slot_of_row = d_slot_of_row;
     f.default_var = 8.8817841970012523e-16;   // alpha^2 = 2^-50 (eval/idash.cpp:20, tlwe-functions.cpp:38)
+    f.var_wsum = m->d_var_wsum;
+    f.var_uniform = nullptr;
+    if ((in.records || in.variance) && in.count) {
+        CUDA_TRY(cudaMemsetAsync(c->d_var_flag, 0, 2 * sizeof(uint64_t), c->s_aux));
+        variance_scan_kernel<<<(unsigned) ((in.count + 255) / 256), 256, 0, c->s_aux>>>(in, c->d_var_flag);
+        c->launches++;
+        f.var_uniform = c->d_var_flag;
+    }
     cloud_finalize_kernel<<<(unsigned) ((f.n_rows - f.row_lo + 63) / 64), 64, 0, c->s_aux>>>(f);   // 64-thread CTAs fit beside a resident ring CTA
     c->launches++;
     CUDA_TRY(cudaGetLastError());

@@ -77,6 +77,30 @@ def test_cloud_records_reproduces_reference_file(kctx, name):
     m.free()
 
 
+@pytest.mark.parametrize("kind", ["pow2", "zero", "uniform_not_pow2", "one_differs", "packed_no_variance"])
+def test_cloud_output_variance_paths(gpu_ctx, kind):
+    """The serialized variance (tlwe-functions.cpp:175): one multiply when every input carries the same power-of-two variance
+    (the reference's encrypt: 2^-50), the per-entry walk otherwise -- same doubles either way, and as the oracle's."""
+    S = 1004
+    geo, model, cts, var = make_case(S, T=70, G=120, n=20, seed=77)
+    if kind == "zero":
+        var = np.zeros_like(var)
+    elif kind == "uniform_not_pow2":
+        var = var * 3.0
+    elif kind == "one_differs":
+        var = var.copy(); var[len(var) // 2] *= 2.0
+    m = _model(gpu_ctx, S, geo.NR, geo.RS, model.out_bidx, model.row_ptr, model.col, model.coef)
+    out, _, ovar = api.cloud_compute_score(gpu_ctx, m, cts, in_var=None if kind == "packed_no_variance" else var)
+    ref_out, ref_var = _oracle(S, geo, model, cts, var)
+    assert np.array_equal(out, ref_out)
+    assert np.array_equal(ovar, ref_var)
+    image = formats.build_ct_image(np.arange(len(cts), dtype=np.uint32), cts, var)
+    rec = api.cloud_compute_score_records(gpu_ctx, m, image)
+    _, w, v = formats.image_views(rec)
+    assert np.array_equal(w, ref_out) and np.array_equal(v, ref_var)
+    m.free()
+
+
 def test_cloud_permuted_input_slots_and_scattered_outputs(kctx):
     S = 400
     geo, model, cts, var = make_case(S, T=50, G=80, n=5, seed=21)
