@@ -1,5 +1,5 @@
-// K2r: persistent, warp-specialised variant of the tensor-core cloud kernel for NUM_REGIONS == 1
-// (the iDASH-scale configurations). Same arithmetic as cloud_tc.cuh; what changes is the schedule:
+// K2r: persistent, warp-specialised variant of the tensor-core cloud kernel (any NUM_REGIONS: rotations are applied
+// while an input block is staged). Same arithmetic as cloud_tc.cuh; what changes is the schedule:
 //
 //   * grid = 16 slices x C chunks (C = SMs / 16): CTA (slice, chunk) walks the tiles of its chunk in order
 //     for ONE 128-word slice of the ciphertext axis. The 16 CTAs of a chunk advance together, so whole
@@ -56,7 +56,7 @@ struct RingParams {
     const uint32_t *slot_of_ct;
     uint32_t n_ct_slots;
     const uint32_t *slot_of_row;
-    uint32_t S;
+    uint32_t S, NR, RS;            // NUM_SAMPLES, NUM_REGIONS, REGION_SIZE (feature f = ciphertext f / NR rotated by (f % NR) * RS words)
     int *status;
     uint32_t trace_cta;            // 0 = off, else 1 + index of the CTA whose timeline is recorded
     uint32_t tune;                 // experiment switches (IDASH_B200_TUNE): 1 epilogue waits with try_wait, 2 publisher waits with
@@ -195,9 +195,9 @@ __device__ __forceinline__ void ring_ld_chunk(uint32_t taddr, uint32_t (&v0)[8],
 // accumulators), 8 rows per tcgen05.ld group, the loads of group g+1 in flight while group g is recombined and
 // stored. FAST: rows are consecutive output slots with a compile-time stride -> store address = base + immediate.
 // ptr_own / bias_own: lane l holds the output address (0 = no such row) / Constant * 2^18 of row col_base + l.
-template <bool FAST, uint32_t STRIDE, bool BIAS>
+template <bool FAST, uint32_t STRIDE, bool BIAS, bool MASK = false>
 __device__ __forceinline__ void ring_epilogue(uint32_t taddr, uint8_t *base_lane, uint64_t ptr_own, uint32_t bias_own, uint32_t bias_flag,
-                                              uint32_t lane_off, uint32_t knockout) {
+                                              uint32_t lane_off, uint32_t knockout, uint32_t keep_mask = 0xFFFFFFFFu) {
     if (knockout & 4u) return;
     uint32_t v[2][4][8];
     ring_ld_chunk(taddr, v[0][0], v[0][1], v[0][2], v[0][3]);
@@ -210,6 +210,7 @@ __device__ __forceinline__ void ring_epilogue(uint32_t taddr, uint8_t *base_lane
             const uint32_t n = g * 8u + c;
             uint32_t x = ((v[g & 1][3][c] * 256u + v[g & 1][2][c]) * 256u + v[g & 1][1][c]) * 256u + v[g & 1][0][c];
             if (BIAS) x += __shfl_sync(0xFFFFFFFFu, bias_own, n) * bias_flag;
+            if (MASK) x &= keep_mask;                                                  // b[RS..N) = 0 (idash.cpp:839-841)
             if (knockout & 2u) { if (x == 0x9E3779B9u && bias_flag == 77u) stg32_stream(base_lane, x); continue; }
             if (FAST) {
                 stg32_stream(base_lane + (uint64_t) n * STRIDE, x);
@@ -221,6 +222,8 @@ __device__ __forceinline__ void ring_epilogue(uint32_t taddr, uint8_t *base_lane
     }
 }
 
+// ROT = NUM_REGIONS > 1 (rotated loads, masked b tail); the NUM_REGIONS == 1 instantiation carries none of that code
+template <bool ROT>
 __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t a_full[RG_MAX_SLOTS], b_full[RG_MAX_BSTAGES], t_full[2], t_empty[2];
@@ -265,6 +268,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
         const uint32_t word_in_slice = quad * 32u + lane;
         const uint32_t lane_off = 4u * word_in_slice;
         const uint32_t bias_flag = (is_b && i_slice + word_in_slice < p.S) ? 1u : 0u;
+        const uint32_t keep_mask = (is_b && i_slice + word_in_slice >= p.RS) ? 0u : 0xFFFFFFFFu;
         const bool records = p.out.records != 0;
         // Row information (caller row + Constant of row col_base + lane) comes from global memory. It is prefetched TWO
         // tiles ahead into registers that are statically bound to the tile's parity (= its TMEM stage): the loop is
@@ -305,14 +309,14 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                 const uint32_t taddr = tmem + ((quad * 32u) << 16) + st * 4u * TC_TN + col_base;
                 if (fast) {
                     if (records) {
-                        if (is_b) ring_epilogue<true, IDASH_B200_RECORD_BYTES, true>(taddr, base_lane, 0, bias_own, bias_flag, lane_off, p.knockout);
+                        if (is_b) ring_epilogue<true, IDASH_B200_RECORD_BYTES, true, ROT>(taddr, base_lane, 0, bias_own, bias_flag, lane_off, p.knockout, keep_mask);
                         else ring_epilogue<true, IDASH_B200_RECORD_BYTES, false>(taddr, base_lane, 0, 0, 0, lane_off, p.knockout);
                     } else {
-                        if (is_b) ring_epilogue<true, IDASH_B200_CT_BYTES, true>(taddr, base_lane, 0, bias_own, bias_flag, lane_off, p.knockout);
+                        if (is_b) ring_epilogue<true, IDASH_B200_CT_BYTES, true, ROT>(taddr, base_lane, 0, bias_own, bias_flag, lane_off, p.knockout, keep_mask);
                         else ring_epilogue<true, IDASH_B200_CT_BYTES, false>(taddr, base_lane, 0, 0, 0, lane_off, p.knockout);
                     }
                 } else {
-                    ring_epilogue<false, 0, true>(taddr, nullptr, ptr_own, bias_own, bias_flag, lane_off, p.knockout);
+                    ring_epilogue<false, 0, true, ROT>(taddr, nullptr, ptr_own, bias_own, bias_flag, lane_off, p.knockout, keep_mask);
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
@@ -490,24 +494,55 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
             }
             return cur_kb++;
         };
-        // global loads of one block: features k0 and k0 + 16, 16 words each
+        // global loads of one block: features k0 and k0 + 16, 16 words each. NUM_REGIONS > 1: feature f is ciphertext
+        // f / NR multiplied by X^(-(f % NR) RS) (torusPolynomialMulByXai, toruspolynomial-functions.cpp:140-160): the words
+        // are read rotated, with the sign flipped where the index wraps. A slice that lies entirely in b[RS..N) is
+        // written as zeros by the epilogue whatever the accumulators hold, so it loads nothing.
+        const bool slice_masked = ROT && is_b && i_slice >= p.RS;
         auto load_block = [&](uint32_t kb, uint4 (&w)[2][4]) {
             const uint32_t used_word = kb < p.n_feat_words ? __ldg(p.feat_used + kb) : 0u;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const uint32_t k = k0 + 16u * h;
-                const uint32_t ct = kb * 32u + k;
+                const uint32_t f = kb * 32u + k;
+                uint32_t ct = f, shift = 0;
+                if (ROT) { ct = f / p.NR; shift = (f - ct * p.NR) * p.RS; }
                 uint32_t sl = NO_SLOT;
                 if (ct < p.n_ct_slots) sl = p.slot_of_ct ? __ldg(p.slot_of_ct + ct) : ct;
                 if (p.knockout & 8u) sl = NO_SLOT;
-                if (sl == NO_SLOT) {
-                    if (((used_word >> k) & 1u) && !(p.knockout & 8u)) atomicOr(p.status, 1);
+                if (sl == NO_SLOT || slice_masked) {
+                    if (sl == NO_SLOT && ((used_word >> k) & 1u) && !(p.knockout & 8u)) atomicOr(p.status, 1);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) w[h][q] = make_uint4(0, 0, 0, 0);
-                } else {
+                } else if (!ROT) {
                     const uint8_t *src = p.in.words + (uint64_t) sl * p.in.stride + 4u * (w_slice + mg * 16u);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) w[h][q] = ldg128(src + 16 * q);
+                } else {
+                    const uint8_t *poly = p.in.words + (uint64_t) sl * p.in.stride + 4u * (w_slice & POLY_N);
+                    const uint32_t i0 = i_slice + mg * 16u;
+                    // words start .. start + 15 of the negacyclic extension, start = i0 + shift < 2047: five aligned 128-bit loads
+                    // (an aligned group never straddles the wrap at 1024, so the sign is per group), then a word-granular
+                    // realignment by start % 4 in registers -- REGION_SIZE = 341 makes two of three features unaligned, and
+                    // sixteen 32-bit loads per feature made the producers' load/store unit the bottleneck
+                    const uint32_t start = i0 + shift, o = start & 3u, al = start & ~3u;
+                    uint32_t fl[20];
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) {
+                        uint32_t idx = al + 4u * j;
+                        const bool neg = (idx & POLY_N) != 0u;
+                        idx &= POLY_N - 1u;
+                        uint4 v = (j < 4 || o != 0u) ? ldg128(poly + 4u * idx) : make_uint4(0, 0, 0, 0);
+                        if (neg) { v.x = 0u - v.x; v.y = 0u - v.y; v.z = 0u - v.z; v.w = 0u - v.w; }
+                        fl[4 * j] = v.x; fl[4 * j + 1] = v.y; fl[4 * j + 2] = v.z; fl[4 * j + 3] = v.w;
+                    }
+                    uint32_t t1[18];
+#pragma unroll
+                    for (int m = 0; m < 18; ++m) t1[m] = (o & 1u) ? fl[m + 1] : fl[m];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        w[h][q] = make_uint4((o & 2u) ? t1[4 * q + 2] : t1[4 * q], (o & 2u) ? t1[4 * q + 3] : t1[4 * q + 1],
+                                             (o & 2u) ? t1[4 * q + 4] : t1[4 * q + 2], (o & 2u) ? t1[4 * q + 5] : t1[4 * q + 3]);
                 }
             }
         };

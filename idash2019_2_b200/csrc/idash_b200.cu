@@ -427,8 +427,8 @@ extern "C" int idash_b200_init(idash_b200_ctx **out, int device) {
     CUDA_TRY(cudaFuncSetAttribute(decrypt_tc_kernel<IDASH_B200_CT_BYTES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dec_tc_smem_bytes(DT_MAX_SLOTS)));
     CUDA_TRY(cudaFuncSetAttribute(decrypt_tc_kernel<IDASH_B200_RECORD_BYTES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dec_tc_smem_bytes(DT_MAX_SLOTS)));
     CUDA_TRY(cudaFuncSetAttribute(decrypt_tc_kernel<IDASH_B200_RECORD_BYTES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dec_tc_smem_bytes(DT_MAX_SLOTS)));
-    CUDA_TRY(cudaFuncSetAttribute(cloud_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int) RG_SMEM_MAX));
+    CUDA_TRY(cudaFuncSetAttribute(cloud_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) RG_SMEM_MAX));
+    CUDA_TRY(cudaFuncSetAttribute(cloud_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) RG_SMEM_MAX));
     *out = c;
     return IDASH_B200_OK;
 }
@@ -644,7 +644,7 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
                                                  "(a coefficient outside int16 or a band wider than %u features)", IDASH_B200_TILE_KMAX);
     if (c->kernel_choice == IDASH_B200_KERNEL_TENSOR_RING && !L->ring_ok)
         return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: the persistent ring kernel was requested but the model is not eligible "
-                                                 "(needs NUM_REGIONS == 1, forward-moving bands of at most %u features)", IDASH_B200_RING_KMAX);
+                                                 "(needs forward-moving bands of at most %u features)", IDASH_B200_RING_KMAX);
     const bool use_tc = tc_ok && c->kernel_choice != IDASH_B200_KERNEL_IMAD;
     if (c->kernel_choice == IDASH_B200_KERNEL_TENSOR_RING && L->ring_ok && !ring_selected(c, L))
         return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: the persistent ring kernel was requested but the model has too many tiles per chunk");
@@ -713,13 +713,15 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
         if (p.n_bstages < 2) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: internal: ring kernel shared-memory budget");
         p.in = in; p.out = out;
         p.slot_of_ct = d_slot_of_ct; p.n_ct_slots = n_ct_slots; p.slot_of_row = d_slot_of_row;
-        p.S = L->S;
+        p.S = L->S; p.NR = L->NR; p.RS = L->RS;
         p.status = c->d_status;
         if (const char *ko = getenv("IDASH_B200_KNOCKOUT")) p.knockout = (uint32_t) atoi(ko);
         p.tune = 8u;      // warp-converged MMA issue (see cloud_ring.cuh)
         if (const char *tu = getenv("IDASH_B200_TUNE")) p.tune = (uint32_t) atoi(tu);
         if (const char *tr = getenv("IDASH_B200_TRACE")) p.trace_cta = (uint32_t) atoi(tr) + 1u;
-        cloud_ring_kernel<<<16u * p.n_chunks, RG_THREADS, ring_smem_bytes(p.n_slots, p.n_bstages, p.b_stage_bytes, p.max_chunk_tiles), st>>>(p);
+        const size_t ring_smem = ring_smem_bytes(p.n_slots, p.n_bstages, p.b_stage_bytes, p.max_chunk_tiles);
+        if (L->NR == 1) cloud_ring_kernel<false><<<16u * p.n_chunks, RG_THREADS, ring_smem, st>>>(p);
+        else cloud_ring_kernel<true><<<16u * p.n_chunks, RG_THREADS, ring_smem, st>>>(p);
         if (p.trace_cta) {   // debugging only: dump the timeline of the traced CTA to the file named by IDASH_B200_TRACE_FILE
             static unsigned long long h[RG_TRACE_TILES * RG_TRACE_EVENTS];
             CUDA_TRY(cudaStreamSynchronize(st));
@@ -930,8 +932,8 @@ static int cloud_eval_host_pipelined(idash_b200_ctx *c, const idash_b200_model *
         pc.row_hi = std::min<uint64_t>(L->n_rows, (uint64_t) pc.tile_hi * IDASH_B200_TILE_ROWS);
         pc.first = k == 0;
         if (chunked_in) {
-            for (; t_scan < pc.tile_hi; ++t_scan) need = std::max<uint64_t>(need, (uint64_t) L->tiles[t_scan].f_base + L->tiles[t_scan].K);   // NUM_REGIONS == 1
-            const uint64_t upto = std::min<uint64_t>(need, in->count);
+            for (; t_scan < pc.tile_hi; ++t_scan) need = std::max<uint64_t>(need, (uint64_t) L->tiles[t_scan].f_base + L->tiles[t_scan].K);   // features
+            const uint64_t upto = std::min<uint64_t>((need + L->NR - 1) / L->NR, in->count);                                            // ciphertexts
             if (upto > uploaded) {
                 CUDA_TRY(cudaMemcpyAsync((uint8_t *) c->in_buf.p + uploaded * IDASH_B200_CT_BYTES, (const uint8_t *) in->data + uploaded * IDASH_B200_CT_BYTES,
                                          (upto - uploaded) * IDASH_B200_CT_BYTES, cudaMemcpyHostToDevice, c->s_in));

@@ -203,9 +203,8 @@ extern "C" int idash_b200_layout_compile(const idash_b200_model_desc *d, idash_b
                     }
                 if (!ok) break;
                 if (fmin > fmax) fmin = fmax = (t ? L->tiles[t - 1].f_base : 0);   // bias-only tile: stay in place
-                // NUM_REGIONS == 1: bands start on a 32-feature block so that consecutive tiles share whole
-                // staged blocks (persistent ring kernel); otherwise the band starts at its first feature
-                if (NR == 1) fmin &= ~31u;
+                // bands start on a 32-feature block so that consecutive tiles share whole staged blocks (persistent ring kernel)
+                fmin &= ~31u;
                 const uint64_t width = (uint64_t) fmax - fmin + 1;
                 const uint64_t K = (width + 31) / 32 * 32;
                 if (K > IDASH_B200_TILE_KMAX || (uint64_t) fmin + K > 0xFFFFFFFFull) { ok = false; break; }
@@ -247,9 +246,9 @@ extern "C" int idash_b200_layout_compile(const idash_b200_model_desc *d, idash_b
                 L->tiles.clear(); L->tile_rows.clear(); L->tile_bias.clear(); L->tile_coef.clear(); L->tile_used.clear();
                 L->tile_kmax = 0;
             }
-            // persistent ring kernel: NUM_REGIONS == 1, block-aligned bands that only move forward, at most
+            // persistent ring kernel: block-aligned bands that only move forward, at most
             // IDASH_B200_RING_KMAX features wide; feat_used = features some row multiplies by a non-zero coefficient
-            L->ring_ok = ok && NR == 1 && !L->tiles.empty() && L->tile_kmax <= IDASH_B200_RING_KMAX;
+            L->ring_ok = ok && !L->tiles.empty() && L->tile_kmax <= IDASH_B200_RING_KMAX;
             uint64_t f_end = 0;
             for (uint64_t t = 0; t < L->tiles.size() && L->ring_ok; ++t) {
                 const idash_b200_tile &T = L->tiles[t];

@@ -116,7 +116,7 @@ int idash_b200_timing_read(idash_b200_ctx *ctx, float *ms, int *n);
 /* Which cloud kernel idash_b200_cloud_eval_* launches. AUTO = a tensor-core kernel (tcgen05 int8 limb-split
  * GEMM over band tiles) when the model is eligible -- every coefficient fits int16 and every 64-row tile's band
  * is at most 256 features wide -- else the IMAD kernel. TENSOR picks between its two schedules: TENSOR_RING
- * (persistent CTAs, shared-memory ring of staged input blocks; needs NUM_REGIONS == 1 and forward-moving bands
+ * (persistent CTAs, shared-memory ring of staged input blocks; needs forward-moving bands
  * of at most 224 features) and TENSOR_TILE (one CTA per tile x slice; any NUM_REGIONS). All are bit-exact;
  * forcing a kernel on an ineligible model makes cloud_eval fail with IDASH_B200_ERR_INVALID. last_kernel()
  * reports what the last launch used (IMAD, TENSOR_TILE or TENSOR_RING). */

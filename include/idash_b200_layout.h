@@ -68,7 +68,7 @@ typedef struct idash_b200_group {
 #define IDASH_B200_TILE_COEF_MIN (-32896)
 #define IDASH_B200_TILE_COEF_MAX 32639
 #define IDASH_B200_TILE_KMAX 256u   /* widest band (features) a tile may have; wider models use the IMAD kernel */
-/* With NUM_REGIONS == 1 every band starts on a multiple of 32 features (a "block"). When, in addition, bands
+/* Every band starts on a multiple of 32 features (a "block"). When, in addition, bands
  * only move forward from tile to tile and are at most RING_KMAX wide, the persistent kernel keeps the staged
  * blocks of consecutive tiles in a shared-memory ring and stages every input block once per CTA. */
 #define IDASH_B200_RING_KMAX 224u

@@ -29,7 +29,7 @@ def _model(ctx, S, NR, RS, out_bidx, row_ptr, col, coef):
     req = getattr(ctx, "requested", None)
     if req == _lib.KERNEL_TENSOR_RING and not m.info["ring_ok"]:
         m.free()
-        pytest.skip("model not eligible for the persistent ring kernel (needs NUM_REGIONS == 1)")
+        pytest.skip("model not eligible for the persistent ring kernel")
     if req == _lib.KERNEL_TENSOR_TILE and not m.info["n_tiles"]:
         m.free()
         pytest.skip("model not eligible for the tensor-core kernels")
