@@ -24,12 +24,16 @@
 //     lanes that hold one 16-coefficient block split their words into byte planes (PRMT, reversed order), transpose
 //     4 x 4 with 4 shuffles, and each stores one 16-byte row. The operand lives in a shared-memory ring of slots
 //     (128 k' x 128 n, 16.5 KB with the bank-conflict pad).
-//   * TMEM: 2 stages x 2 j blocks x 128 columns = all 512 columns. A group of 32 ciphertexts takes 4 passes
-//     (2 j blocks each) over its 8 ring slots: 256 MMAs ~ 16 k cycles, the same order as the HBM time of the
+//   * TMEM: 4 stages x 128 columns = all 512 columns, one j block each. A group of 32 ciphertexts takes 8 passes
+//     (one j block each) over its 8 ring slots: 256 MMAs ~ 16 k cycles, the same order as the HBM time of the
 //     group's 384 KB (a, b in; scores out), so the kernel sits near both rooflines; measured numbers in DESIGN.md.
-//   * roles (544 threads, one persistent CTA per SM, groups strided over the grid): warps 0-7 epilogue (lane
-//     quadrant = warp % 4, j block of the pass = warp / 4; b is prefetched before the accumulator is ready),
-//     warp 8 MMA issuer + TMEM owner, warps 9-16 producers (four 64-byte loads in flight per thread).
+//     The MMA warp may run three j blocks ahead of the epilogue (with 2 stages of 2 j blocks it stalled 22 % of the
+//     time on a free stage: the epilogue needs ~3650 of the 4096 cycles a pass gives it, and any jitter showed).
+//   * roles (416 threads, 128 registers per thread; one persistent CTA per SM, groups strided over the grid):
+//     warps 0-3 epilogue (warp = TMEM lane quadrant; the b words of the next j block are prefetched into the registers
+//     just consumed), warp 4 MMA issuer + TMEM owner, warps 5-12 producers (six 4 x 16-byte units in flight per thread).
+//     The first version had 8 epilogue warps (544 threads, 96 registers): they idled 78 % of the time while the register
+//     cap limited the producers to 4 units.
 #pragma once
 
 #define DT_CTS 32u                        // ciphertexts per group
@@ -44,8 +48,9 @@
 #define DT_TOEP_CORES 254u
 #define DT_TOEP_BYTES 32768u              // 254 x 128 = 32512, rounded up
 #define DT_MAX_SLOTS 11u
-#define DT_WARP_MMA 8u
-#define DT_WARP_PROD 9u
+#define DT_EPI_WARPS 4u
+#define DT_WARP_MMA 4u
+#define DT_WARP_PROD 5u
 #define DT_PROD_WARPS 8u
 #define DT_THREADS ((DT_WARP_PROD + DT_PROD_WARPS) * 32u)
 
@@ -122,9 +127,9 @@ __device__ __forceinline__ void dec_epilogue_pass(uint32_t (&bw)[DT_CTS], const 
 }
 
 template <uint32_t STRIDE, bool PHASE>
-__global__ void __launch_bounds__(DT_THREADS, 1) decrypt_tc_kernel(const DecTcParams p) {
+__global__ void __launch_bounds__(DT_THREADS, 1) decrypt_tc_kernel(const DecTcParams p) {   // 13 warps: 4 on one SM sub-partition (16 K registers) -> 128 per thread
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t full_bar[DT_MAX_SLOTS], empty_bar[DT_MAX_SLOTS], tfull_bar[2], tempty_bar[2];
+    __shared__ __align__(8) uint64_t full_bar[DT_MAX_SLOTS], empty_bar[DT_MAX_SLOTS], tfull_bar[4], tempty_bar[4];
     __shared__ uint32_t tmem_base_s;
     __shared__ uint32_t key_s[32];
 
@@ -136,7 +141,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decrypt_tc_kernel(const DecTcPa
     if (tid < 32) key_s[tid] = p.key.w[tid];
     if (tid == 0) {
         for (uint32_t i = 0; i < NS; ++i) { mbar_init(&full_bar[i], DT_PROD_WARPS * 32u); mbar_init(&empty_bar[i], 1); }
-        for (uint32_t i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8u * 32u); }
+        for (uint32_t i = 0; i < 4; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], DT_EPI_WARPS * 32u); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == DT_WARP_MMA) {
@@ -164,14 +169,14 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decrypt_tc_kernel(const DecTcPa
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_s;
 
-    if (warp < 8u) {
-        // ---------------- epilogue: phase = b - sum_l 2^(8l) P_l, decode, store
-        const uint32_t qd = warp & 3u, jl = warp >> 2;
-        const uint32_t j_w = jl * 128u + qd * 32u + lane;        // + 256 pass
+    if (warp < DT_EPI_WARPS) {
+        // ---------------- epilogue: phase = b - sum_l 2^(8l) P_l, decode, store. Warp = TMEM lane quadrant; every j block.
+        const uint32_t qd = warp;
+        const uint32_t j_w = qd * 32u + lane;        // + 128 jb
         const bool st_on = !(p.knockout & 2u), ld_on = !(p.knockout & 4u);
-        uint32_t pc = 0;
+        uint32_t pc = 0;                             // j blocks done: TMEM stage pc % 4
         uint32_t bw[DT_CTS];
-        {   // b words of the first pass
+        {   // b words of the first j block
             const uint64_t g = blockIdx.x;
             const uint32_t n0 = (g < p.n_groups && ld_on) ? (uint32_t) min((uint64_t) DT_CTS, p.n_ct - g * DT_CTS) : 0u;
             const uint8_t *bj = p.in.words + g * DT_CTS * STRIDE + 4u * POLY_N + 4u * j_w;
@@ -184,17 +189,17 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decrypt_tc_kernel(const DecTcPa
             const uint64_t g_next = g + gridDim.x;
             const uint32_t n_after = (g_next < p.n_groups && ld_on) ? (uint32_t) min((uint64_t) DT_CTS, p.n_ct - g_next * DT_CTS) : 0u;
 #pragma unroll 1
-            for (uint32_t pass = 0; pass < 4; ++pass, ++pc) {
-                const uint32_t stage = pc & 1u;
-                const uint32_t j = pass * 256u + j_w;
-                const uint32_t taddr = tmem + ((qd * 32u) << 16) + stage * 256u + jl * DT_N;
+            for (uint32_t jb = 0; jb < 8; ++jb, ++pc) {
+                const uint32_t stage = pc & 3u;
+                const uint32_t j = jb * 128u + j_w;
+                const uint32_t taddr = tmem + ((qd * 32u) << 16) + stage * DT_N;
                 float *sc = p.scores ? p.scores + ct0 * p.S + j : nullptr;
                 uint32_t *ph = p.phase ? p.phase + ct0 * POLY_N + j : nullptr;
-                // the pass after this one: same group, next 256 coefficients -- or the first pass of the CTA's next group
-                const uint8_t *bj_next = pass < 3u ? p.in.words + ct0 * STRIDE + 4u * POLY_N + 4u * (j + 256u)
-                                                   : p.in.words + g_next * DT_CTS * STRIDE + 4u * POLY_N + 4u * j_w;
-                const uint32_t n_next = pass < 3u ? (ld_on ? n_here : 0u) : n_after;
-                mbar_wait(&tfull_bar[stage], (pc >> 1) & 1u);
+                // the j block after this one: same group, next 128 coefficients -- or the first j block of the CTA's next group
+                const uint8_t *bj_next = jb < 7u ? p.in.words + ct0 * STRIDE + 4u * POLY_N + 4u * (j + 128u)
+                                                 : p.in.words + g_next * DT_CTS * STRIDE + 4u * POLY_N + 4u * j_w;
+                const uint32_t n_next = jb < 7u ? (ld_on ? n_here : 0u) : n_after;
+                mbar_wait(&tfull_bar[stage], (pc >> 2) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const bool sc_on = sc != nullptr && j < p.S && st_on;
                 if (n_here == DT_CTS) dec_epilogue_pass<STRIDE, PHASE, true>(bw, bj_next, n_next, n_here, taddr, sc, p.S, sc_on, ph, &tempty_bar[stage]);
@@ -209,32 +214,28 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decrypt_tc_kernel(const DecTcPa
         const uint32_t a_lo0 = ((smem_u32(toep) >> 4) & 0x3FFFu) | ((DT_A_LBO >> 4) << 16), a_hi = (DT_A_SBO >> 4) | (1u << 14);
         const uint32_t b_lo0 = ((smem_u32(ring) >> 4) & 0x3FFFu) | ((DT_B_LBO >> 4) << 16), b_hi = (DT_B_SBO >> 4) | (1u << 14);
         auto mk = [](uint32_t lo, uint32_t hi) { uint64_t d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi)); return d; };
-        uint32_t slot0 = 0, ph0 = 0, pc = 0;
+        uint32_t slot0 = 0, ph0 = 0, pc = 0;       // pc counts j blocks: 8 per group, TMEM stage pc % 4
         for (uint64_t g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
 #pragma unroll 1
-            for (uint32_t pass = 0; pass < 4; ++pass, ++pc) {
-                const uint32_t stage = pc & 1u;
-                mbar_wait(&tempty_bar[stage], ((pc >> 1) & 1u) ^ 1u);
+            for (uint32_t jb = 0; jb < 8; ++jb, ++pc) {
+                const uint32_t stage = pc & 3u;
+                mbar_wait(&tempty_bar[stage], ((pc >> 2) & 1u) ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 uint32_t slot = slot0, ph = ph0;
-                uint32_t a_lo = a_lo0 + 256u * pass;          // A tile (jb = 2 pass + q, ks): + 128 q + 32 ks  [16-byte units]
-                const uint32_t d0 = tmem + stage * 256u;
+                uint32_t a_lo = a_lo0 + 128u * jb;            // A tile (jb, ks): + 32 ks  [16-byte units]
+                const uint32_t d0 = tmem + stage * DT_N;
 #pragma unroll 1
                 for (uint32_t s = 0; s < DT_GROUP_SLOTS; ++s, a_lo += 128u) {
-                    if (pass == 0) {
+                    if (jb == 0) {
                         mbar_wait(&full_bar[slot], ph);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     }
                     const uint32_t b_lo = b_lo0 + slot * (DT_SLOT_BYTES >> 4);
                     if (!(p.knockout & 1u))
 #pragma unroll
-                    for (uint32_t kk = 0; kk < 4; ++kk) {
-                        const uint64_t db = mk(b_lo + kk * ((2u * DT_B_LBO) >> 4), b_hi);
-                        const uint32_t acc = (s | kk) != 0u;
-                        tc_mma_p(d0, mk(a_lo + 32u * kk, a_hi), db, dec_idesc(DT_N), acc, leader);
-                        tc_mma_p(d0 + DT_N, mk(a_lo + 32u * kk + 128u, a_hi), db, dec_idesc(DT_N), acc, leader);
-                    }
-                    if (pass == 3 && leader) tc_commit(&empty_bar[slot]);   // the group is done with this slot
+                    for (uint32_t kk = 0; kk < 4; ++kk)
+                        tc_mma_p(d0, mk(a_lo + 32u * kk, a_hi), mk(b_lo + kk * ((2u * DT_B_LBO) >> 4), b_hi), dec_idesc(DT_N), (s | kk) != 0u, leader);
+                    if (jb == 7 && leader) tc_commit(&empty_bar[slot]);   // the group is done with this slot
                     if (++slot == NS) { slot = 0; ph ^= 1u; }
                 }
                 if (leader) tc_commit(&tfull_bar[stage]);
@@ -288,21 +289,25 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decrypt_tc_kernel(const DecTcPa
             mbar_arrive(&full_bar[slot]);
             if (++slot == NS) { slot = 0; ph ^= 1u; }
         };
-        // four units (4 x 16-byte loads each) in flight per thread, register sets bound statically; total is a multiple of 8
-        uint4 w0[4], w1[4], w2[4], w3[4];
+        // six units (4 x 16-byte loads each) in flight per thread, register sets bound statically: with the 3 ring slots beyond
+        // a group that is 9 slots of lookahead -- more than a group, so the first pass of the next group never waits for a
+        // load that was issued only when the previous group released its slots (with 4 units the MMA warp spent ~25 % of its
+        // time waiting for full slots)
+        uint4 w0[4], w1[4], w2[4], w3[4], w4[4], w5[4];
         load_unit(0, w0);
         load_unit(1, w1);
         load_unit(2, w2);
         load_unit(3, w3);
-        for (uint64_t i = 0; i < total; i += 4) {
+        load_unit(4, w4);
+        load_unit(5, w5);
+        for (uint64_t i = 0; i < total; i += 6) {
             store_unit(w0);
-            load_unit(i + 4, w0);
-            store_unit(w1);
-            load_unit(i + 5, w1);
-            store_unit(w2);
-            load_unit(i + 6, w2);
-            store_unit(w3);
-            load_unit(i + 7, w3);
+            load_unit(i + 6, w0);
+            if (i + 1 < total) { store_unit(w1); load_unit(i + 7, w1); }
+            if (i + 2 < total) { store_unit(w2); load_unit(i + 8, w2); }
+            if (i + 3 < total) { store_unit(w3); load_unit(i + 9, w3); }
+            if (i + 4 < total) { store_unit(w4); load_unit(i + 10, w4); }
+            if (i + 5 < total) { store_unit(w5); load_unit(i + 11, w5); }
         }
     }
 
