@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--samples", type=int, default=S)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-decrypt", action="store_true", help="skip the secondary decrypt-kernel timing")
     ap.add_argument("--kernel", default="auto", choices=["auto", "imad", "tensor", "tile", "ring"],
                     help="cloud kernel: auto (tensor-core when the model is eligible), imad, tensor (ring if eligible, "
                          "else tile), tile (one CTA per tile), ring (persistent)")
@@ -319,6 +320,27 @@ def run_b200(args):
     clocks = sampler.stop() if sampler else None
     same = torch.equal(h_out.cuda(), outs[0])   # host path and device path agree on the same input
 
+    # ---- the decrypt stage on the step's own output ciphertexts (secondary: reported beside the headline, not part of it)
+    decrypt = None
+    if rank == 0 and not args.no_decrypt:
+        key = np.random.default_rng(5).integers(0, 2, 1024).astype(np.int32)
+        scores = torch.empty((n_rows, args.samples), dtype=torch.float32, device="cuda")
+        for _ in range(2):
+            api.decrypt_predictions_device(ctx, key, args.samples, outs[0], scores)
+        torch.cuda.synchronize()
+        ctx.timing_enable(5)
+        for _ in range(5):
+            api.decrypt_predictions_device(ctx, key, args.samples, outs[0], scores)
+        torch.cuda.synchronize()
+        d_ms = statistics.mean(ctx.timing_read(5))
+        ctx.timing_enable(0)
+        d_bytes = n_rows * (CT_BYTES + 4 * args.samples)
+        pk, _ = measured_peak_gbs()
+        decrypt = {"kernel": "decrypt_tc_kernel" if ctx.last_decrypt_kernel() == api.DECRYPT_TENSOR else "decrypt_kernel",
+                   "ciphertexts": n_rows, "kernel_ms": d_ms, "ct_per_s": n_rows / (d_ms * 1e-3), "algorithmic_bytes": d_bytes,
+                   "achieved": d_bytes / (d_ms * 1e-3) * 1e-9, "unit": "GB/s", "frac": d_bytes / (d_ms * 1e-3) * 1e-9 / pk,
+                   "int8_mac_per_s": n_rows * 4 * 1024 * 1024 / (d_ms * 1e-3)}
+
     t = torch.tensor([ms_total, t_e2e * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -364,6 +386,8 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if decrypt:
+            line["decrypt"] = decrypt
         if world == 1 and not args.no_cpu_baseline:
             try:
                 run, kind, cores = reference_sample_runner(args, model)

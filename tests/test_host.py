@@ -119,6 +119,25 @@ def test_host_errors_die_dramatically(host_bins, tmp_path):
     assert r.returncode < 0 and "Cannot open file" in r.stderr
 
 
+@pytest.mark.parametrize("env", [{}, {"IDASH_HOST_NO_MMAP": "1"}, {"IDASH_HOST_THREADS": "1"}, {"IDASH_HOST_THREADS": "3", "IDASH_HOST_NO_WARMUP": "1"}])
+def test_host_bench_io_paths(host_bins, tmp_path, env):
+    """host_bench on a golden pipeline directory: every file-level phase runs without a GPU, and the slab image written by
+    the mapped / pwrite paths (any thread count) reads back identical; the result csv is written by the batch formatter."""
+    d = GOLDEN / "s335_nr3"
+    r = subprocess.run([str(host_bins / "host_bench"), str(d), str(d / "model"), str(tmp_path), "csv"], capture_output=True, text=True,
+                       env=dict(os.environ, **env))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "slab image round trip: identical" in r.stdout
+    for phase in ("read_model", "read_encrypted_data", "read_encrypted_predictions", "write (slab image)", "write_decrypted_predictions"):
+        assert phase in r.stdout
+    params = formats.read_params(d / "params.bin")
+    rows = (tmp_path / "result_bypos.csv").read_text().splitlines()
+    assert rows[0] == "Subject ID,target SNP,0,1,2" and len(rows) == 1 + params.NUM_SAMPLES * params.NUM_OUTPUT_POSITIONS
+    s, pos = params.NUM_SAMPLES - 1, int(params.out_positions[-1])
+    sc = [np.float32(_s32(((pos & 0xFFFFFFFF) * 2654435761 + v * 40503 + s * 2246822519) & 0xFFFFFFFF) / 2.0 ** 32) for v in range(3)]
+    assert rows[-1] == f"{s},{pos}," + ",".join(fmt_g(x) for x in sc)
+
+
 def _stage_dir(tmp_path, d):
     for f in ("params.bin", "keys.bin", "encrypted_data.bin"):
         shutil.copy(d / f, tmp_path / f)
