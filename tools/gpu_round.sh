@@ -39,3 +39,10 @@ for spec in ${NCU_SPECS:-auto:5 imad:5 ring:50}; do
       python bench.py --steps 2 --warmup 1 --e2e-steps 1 --no-cpu-baseline --kernel $k --neighbors $n > "$OUT/ncu_full_${k}_n$n.log" 2>&1; echo "ncu full $k n=$n rc=$?"
 done
 ls -la "$OUT"
+# the decrypt kernels at iDASH scale + one full capture of the tensor-core one
+timeout 300 python tools/bench_decrypt.py > "$OUT/decrypt.json" 2> "$OUT/decrypt.err"; echo "bench_decrypt rc=$?"; cat "$OUT/decrypt.json"
+DEC_QUICK=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:decrypt_tc -s 2 -c 1 -f -o "$OUT/prof_decrypt_tc" \
+    python tools/bench_decrypt.py > "$OUT/ncu_full_decrypt.log" 2>&1; echo "ncu decrypt rc=$?"
+# BASELINE configs[3] geometry (335 samples, NUM_REGIONS = 3, neighbors = 20)
+timeout 300 python bench.py --steps 20 --warmup 3 --samples 335 --neighbors 20 --no-cpu-baseline --e2e-steps 2 > "$OUT/bench_cfg4.json" 2> "$OUT/bench_cfg4.err"; echo "bench cfg4 rc=$?"
+ls -la "$OUT"
