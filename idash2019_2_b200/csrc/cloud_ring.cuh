@@ -50,6 +50,8 @@ struct RingParams {
     uint32_t n_slots;              // input-block ring slots (>= widest tile in blocks, + prefetch)
     uint32_t n_bstages;            // coefficient ring stages (one tile each)
     uint32_t b_stage_bytes;        // bytes of one coefficient stage = widest tile's image
+    uint64_t coef_bytes;           // size of the coefficient image array (bound for the L2 prefetch)
+    uint32_t coef_prefetch;        // the loader prefetches the images this many tiles ahead into L2 (0 = off)
     uint32_t hdr_off;              // byte offset (dynamic shared memory) of the CTA's tile-header table
     uint32_t max_chunk_tiles;      // capacity of that table (tiles per chunk, rounded up)
     CtView in, out;
@@ -454,6 +456,14 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                              ::"r"(smem_u32(sB + bstage * p.b_stage_bytes)), "l"(p.tile_coef + b_off), "r"(bytes), "r"(smem_u32(&b_full[bstage]))
                              : "memory");
                 b_off += bytes;
+                // With only n_bstages tile-sized stages the copy of tile t + n_bstages starts when tile t's MMAs are complete, and
+                // its HBM/L2 latency (measured ~1800 cycles for a 28 KB image at neighbors = 50) is then on the critical path of the
+                // TMEM stage. The images are contiguous, so the ones a few tiles ahead are pulled into L2 now.
+                if (p.coef_prefetch) {
+                    const uint64_t pf = b_off + (uint64_t) p.coef_prefetch * bytes;
+                    if (pf + bytes <= p.coef_bytes)
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.tile_coef + pf), "r"(bytes) : "memory");
+                }
                 if (++bstage == p.n_bstages) bstage = 0;
             }
         }

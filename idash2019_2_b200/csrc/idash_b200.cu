@@ -714,6 +714,9 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
         p.in = in; p.out = out;
         p.slot_of_ct = d_slot_of_ct; p.n_ct_slots = n_ct_slots; p.slot_of_row = d_slot_of_row;
         p.S = L->S; p.NR = L->NR; p.RS = L->RS;
+        p.coef_bytes = L->tile_coef.size();
+        p.coef_prefetch = max_nb >= 5u ? 2u : 0u;     // measured: 0.673 -> 0.640 ms at neighbors = 50 (7 blocks), nothing to gain on narrow bands
+        if (const char *cp = getenv("IDASH_B200_COEF_PREFETCH")) p.coef_prefetch = (uint32_t) atoi(cp);
         p.status = c->d_status;
         if (const char *ko = getenv("IDASH_B200_KNOCKOUT")) p.knockout = (uint32_t) atoi(ko);
         p.tune = 8u;      // warp-converged MMA issue (see cloud_ring.cuh)
