@@ -506,68 +506,82 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
         };
         // global loads of one block: features k0 and k0 + 16, 16 words each. NUM_REGIONS > 1: feature f is ciphertext
         // f / NR multiplied by X^(-(f % NR) RS) (torusPolynomialMulByXai, toruspolynomial-functions.cpp:140-160): the words
-        // are read rotated, with the sign flipped where the index wraps. A slice that lies entirely in b[RS..N) is
-        // written as zeros by the epilogue whatever the accumulators hold, so it loads nothing.
-        const bool slice_masked = ROT && is_b && i_slice >= p.RS;
-        auto load_block = [&](uint32_t kb, uint4 (&w)[2][4]) {
+        // are read rotated, with the sign flipped where the index wraps.
+        // Rotated reads: words start .. start + 15 of the negacyclic extension, start = i0 + shift < 2047, as FIVE ALIGNED
+        // 128-bit loads (REGION_SIZE = 341 makes two of three features unaligned; sixteen 32-bit loads per feature made the
+        // producers' load/store unit the bottleneck). load_block only ISSUES the loads and keeps the raw groups; the sign
+        // flip and the word-granular realignment by start % 4 happen in store_block -- consuming the data right after
+        // the loads made every block wait out its own HBM latency and arrive ~2000 cycles after its tile was ready.
+        constexpr int NW = ROT ? 5 : 4;
+        // A slice that lies entirely in b[RS..N) is stored as zeros whatever its accumulators hold, yet it stages its inputs like
+        // every other slice: skipping the loads (tune bit 16) lets those CTAs run ahead of the rest of their chunk, the 16 segments
+        // of an output ciphertext are then written at different times, and the kernel gets SLOWER (0.642 vs 0.571 ms, cfg 4).
+        const bool slice_masked = ROT && is_b && i_slice >= p.RS && (p.tune & 16u);
+        auto rot_start = [&](uint32_t f) -> uint32_t {       // first word of this thread's window in the negacyclic extension
+            const uint32_t ct = f / p.NR;
+            return i_slice + mg * 16u + (f - ct * p.NR) * p.RS;
+        };
+        auto load_block = [&](uint32_t kb, uint4 (&w)[2][NW]) {
             const uint32_t used_word = kb < p.n_feat_words ? __ldg(p.feat_used + kb) : 0u;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const uint32_t k = k0 + 16u * h;
                 const uint32_t f = kb * 32u + k;
-                uint32_t ct = f, shift = 0;
-                if (ROT) { ct = f / p.NR; shift = (f - ct * p.NR) * p.RS; }
+                const uint32_t ct = ROT ? f / p.NR : f;
                 uint32_t sl = NO_SLOT;
                 if (ct < p.n_ct_slots) sl = p.slot_of_ct ? __ldg(p.slot_of_ct + ct) : ct;
                 if (p.knockout & 8u) sl = NO_SLOT;
                 if (sl == NO_SLOT || slice_masked) {
                     if (sl == NO_SLOT && ((used_word >> k) & 1u) && !(p.knockout & 8u)) atomicOr(p.status, 1);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) w[h][q] = make_uint4(0, 0, 0, 0);
+                    for (int q = 0; q < NW; ++q) w[h][q] = make_uint4(0, 0, 0, 0);
                 } else if (!ROT) {
                     const uint8_t *src = p.in.words + (uint64_t) sl * p.in.stride + 4u * (w_slice + mg * 16u);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) w[h][q] = ldg128(src + 16 * q);
                 } else {
                     const uint8_t *poly = p.in.words + (uint64_t) sl * p.in.stride + 4u * (w_slice & POLY_N);
-                    const uint32_t i0 = i_slice + mg * 16u;
-                    // words start .. start + 15 of the negacyclic extension, start = i0 + shift < 2047: five aligned 128-bit loads
-                    // (an aligned group never straddles the wrap at 1024, so the sign is per group), then a word-granular
-                    // realignment by start % 4 in registers -- REGION_SIZE = 341 makes two of three features unaligned, and
-                    // sixteen 32-bit loads per feature made the producers' load/store unit the bottleneck
-                    const uint32_t start = i0 + shift, o = start & 3u, al = start & ~3u;
+                    const uint32_t start = rot_start(f), al = start & ~3u;
+#pragma unroll
+                    for (int q = 0; q < NW; ++q)
+                        w[h][q] = (q < 4 || (start & 3u) != 0u) ? ldg128(poly + 4u * ((al + 4u * q) & (POLY_N - 1u))) : make_uint4(0, 0, 0, 0);
+                }
+            }
+        };
+        // split into byte planes and store into the ring slot, once the slot's previous block has been released
+        auto store_block = [&](uint32_t kb, const uint4 (&w)[2][NW]) {
+            if (seq >= p.n_slots) progress_wait(&blocks_freed_s, seq - p.n_slots + 1u);
+            uint8_t *blk = sA + slot * RG_BLOCK_BYTES;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t k = k0 + 16u * h;
+                uint4 v[4];
+                if (!ROT) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[q] = w[h][q];
+                } else {
+                    const uint32_t start = rot_start(kb * 32u + k), o = start & 3u, al = start & ~3u;
                     uint32_t fl[20];
 #pragma unroll
                     for (int j = 0; j < 5; ++j) {
-                        uint32_t idx = al + 4u * j;
-                        const bool neg = (idx & POLY_N) != 0u;
-                        idx &= POLY_N - 1u;
-                        uint4 v = (j < 4 || o != 0u) ? ldg128(poly + 4u * idx) : make_uint4(0, 0, 0, 0);
-                        if (neg) { v.x = 0u - v.x; v.y = 0u - v.y; v.z = 0u - v.z; v.w = 0u - v.w; }
-                        fl[4 * j] = v.x; fl[4 * j + 1] = v.y; fl[4 * j + 2] = v.z; fl[4 * j + 3] = v.w;
+                        const bool neg = ((al + 4u * j) & POLY_N) != 0u;     // an aligned group never straddles the wrap at 1024
+                        uint4 x = w[h][j];
+                        if (neg) { x.x = 0u - x.x; x.y = 0u - x.y; x.z = 0u - x.z; x.w = 0u - x.w; }
+                        fl[4 * j] = x.x; fl[4 * j + 1] = x.y; fl[4 * j + 2] = x.z; fl[4 * j + 3] = x.w;
                     }
                     uint32_t t1[18];
 #pragma unroll
                     for (int m = 0; m < 18; ++m) t1[m] = (o & 1u) ? fl[m + 1] : fl[m];
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
-                        w[h][q] = make_uint4((o & 2u) ? t1[4 * q + 2] : t1[4 * q], (o & 2u) ? t1[4 * q + 3] : t1[4 * q + 1],
-                                             (o & 2u) ? t1[4 * q + 4] : t1[4 * q + 2], (o & 2u) ? t1[4 * q + 5] : t1[4 * q + 3]);
+                        v[q] = make_uint4((o & 2u) ? t1[4 * q + 2] : t1[4 * q], (o & 2u) ? t1[4 * q + 3] : t1[4 * q + 1],
+                                          (o & 2u) ? t1[4 * q + 4] : t1[4 * q + 2], (o & 2u) ? t1[4 * q + 5] : t1[4 * q + 3]);
                 }
-            }
-        };
-        // split into byte planes and store into the ring slot, once the slot's previous block has been released
-        auto store_block = [&](const uint4 (&w)[2][4]) {
-            if (seq >= p.n_slots) progress_wait(&blocks_freed_s, seq - p.n_slots + 1u);
-            uint8_t *blk = sA + slot * RG_BLOCK_BYTES;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t k = k0 + 16u * h;
                 uint32_t limb[4][4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const uint32_t x0 = __byte_perm(w[h][q].x, w[h][q].y, 0x5140), x1 = __byte_perm(w[h][q].x, w[h][q].y, 0x7362);
-                    const uint32_t x2 = __byte_perm(w[h][q].z, w[h][q].w, 0x5140), x3 = __byte_perm(w[h][q].z, w[h][q].w, 0x7362);
+                    const uint32_t x0 = __byte_perm(v[q].x, v[q].y, 0x5140), x1 = __byte_perm(v[q].x, v[q].y, 0x7362);
+                    const uint32_t x2 = __byte_perm(v[q].z, v[q].w, 0x5140), x3 = __byte_perm(v[q].z, v[q].w, 0x7362);
                     limb[0][q] = __byte_perm(x0, x2, 0x5410);
                     limb[1][q] = __byte_perm(x0, x2, 0x7632);
                     limb[2][q] = __byte_perm(x1, x3, 0x5410);
@@ -586,17 +600,17 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
         };
         // Two blocks in flight per thread (register sets A and B, statically alternated): the loads of the next block are
         // issued before the current one is split and stored, so the ~1 us HBM latency of a block overlaps the previous one.
-        uint4 wA[2][4], wB[2][4];
+        uint4 wA[2][NW], wB[2][NW];
         uint32_t kbA = next_block();
         if (kbA != 0xFFFFFFFFu) load_block(kbA, wA);
         while (kbA != 0xFFFFFFFFu) {
             const uint32_t kbB = next_block();
             if (kbB != 0xFFFFFFFFu) load_block(kbB, wB);
-            store_block(wA);
+            store_block(kbA, wA);
             if (kbB == 0xFFFFFFFFu) break;
             kbA = next_block();
             if (kbA != 0xFFFFFFFFu) load_block(kbA, wA);
-            store_block(wB);
+            store_block(kbB, wB);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
