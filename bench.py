@@ -108,6 +108,26 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """One process per GPU: run on the CPU cores NVML reports as local to that GPU, so that the pinned staging buffers of the
+    end-to-end leg are first touched on the GPU's own NUMA node (a buffer on the other socket makes every PCIe copy cross
+    the inter-socket link). Best effort: returns the core count bound to, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cores = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1}
+        cores &= os.sched_getaffinity(0)
+        if cores:
+            os.sched_setaffinity(0, cores)
+            return len(cores)
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak_gbs():
     f = ROOT / "MEASURED_PEAKS.json"
     if f.exists():
@@ -223,6 +243,7 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -375,7 +396,8 @@ def run_b200(args):
                        "neighbors": args.neighbors, "batches": n_batches, "targets_per_gpu": t_hi - t_lo,
                        "in_ct_per_gpu_batch": slab, "out_ct_per_gpu_batch": n_rows,
                        "l2": "inputs+outputs per step (2.4 GB) exceed the 126 MB L2; no explicit flush",
-                       "streams": "batches of a step round-robin on 2 side streams" if side else "single stream"},
+                       "streams": "batches of a step round-robin on 2 side streams" if side else "single stream",
+                       "numa_local_cores": numa},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(kernel_name, args, world),
                          "kernel": kernel_name, "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes,
