@@ -1,32 +1,28 @@
 // cloud -- the `cloud <model_dir>` stage (eval/cloud.cpp:3-28) on the B200 host layer: same inputs in the working
 // directory (params.bin, encrypted_data.bin), same output (encrypted_prediction.bin), same BENCHMARK block on stdout
-// (eval/parse_log.py:14-41 keeps working), plus one line with the time spent inside the GPU call.
+// (eval/parse_log.py:14-41 keeps working), plus one line with the time spent inside the GPU calls.
 #include "idash_host.h"
 
-int main(int argc, char **argv) {
-    Profiler profiler;
-    std::string modelFile = MODEL_FILE;
-    if (argc >= 2) modelFile = argv[1];
-    std::cout << "using model dir: " << modelFile << std::endl;
-
+namespace {
+struct CloudRun {
     IdashParams params;
     Model model;
-    EncryptedData enc_data;
-    EncryptedPredictions enc_preds;
-    read_params(params, PARAMS_FILE);
-    read_model(model, params, modelFile);
-    read_encrypted_data(enc_data, params, ENCRYPTED_DATA_FILE);
-    const double t_cloud0 = profiler.walltime();
-    cloud_compute_score(enc_preds, enc_data, model, params);
-    const double t_cloud1 = profiler.walltime();
-    write_encrypted_predictions(enc_preds, params, ENCRYPTED_PREDICTION_FILE);
-    const double t_end = profiler.walltime();
+    EncryptedData inputs;
+    EncryptedPredictions outputs;
+};
+}  // namespace
 
-    std::cout << "----------------- BENCHMARK ----------------- " << std::endl;
-    std::cout << "fhe wall time (seconds)..........: " << t_cloud1 - t_cloud0 << std::endl;
-    std::cout << "serialization wall time (seconds): " << t_end - t_cloud1 + t_cloud0 << std::endl;
-    std::cout << "total wall time (seconds)........: " << t_end << std::endl;
-    std::cout << "RAM usage (MB)...................: " << profiler.maxrss() / 1e6 << std::endl;
-    std::cout << "gpu call wall time (seconds).....: " << idash_host_last_gpu_seconds() << std::endl;
+int main(int argc, char **argv) {
+    const StageClock clock;
+    const std::string model_dir = argc > 1 ? argv[1] : MODEL_FILE;
+    std::cout << "using model dir: " << model_dir << std::endl;
+
+    CloudRun run;
+    read_params(run.params, PARAMS_FILE);          // also starts the CUDA context on a helper thread
+    read_model(run.model, run.params, model_dir);  // ... and the allocation of the output slab
+    read_encrypted_data(run.inputs, run.params, ENCRYPTED_DATA_FILE);
+    const double stage_s = clock.time([&] { cloud_compute_score(run.outputs, run.inputs, run.model, run.params); });
+    write_encrypted_predictions(run.outputs, run.params, ENCRYPTED_PREDICTION_FILE);
+    clock.print_benchmark("fhe wall time (seconds)..........: ", stage_s);
     return 0;
 }

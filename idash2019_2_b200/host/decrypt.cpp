@@ -3,25 +3,17 @@
 #include "idash_host.h"
 
 int main(int argc, char **) {
-    Profiler profiler;
+    const StageClock clock;
+    const bool by_position = argc > 1;
     IdashKey key;
-    EncryptedPredictions enc_predictions;
-    DecryptedPredictions dec_predictions;
+    EncryptedPredictions ciphertexts;
+    DecryptedPredictions scores;
 
     read_key(key, KEYS_FILE);
-    read_encrypted_predictions(enc_predictions, *key.idashParams, ENCRYPTED_PREDICTION_FILE);
-    const double t0 = profiler.walltime();
-    decrypt_predictions(dec_predictions, enc_predictions, key);
-    const double t1 = profiler.walltime();
-    if (argc == 1) write_decrypted_predictions(dec_predictions, *key.idashParams, RESULT_FILE, true);
-    else write_decrypted_predictions(dec_predictions, *key.idashParams, RESULT_BYPOS_FILE, false);
-    const double t_end = profiler.walltime();
-
-    std::cout << "----------------- BENCHMARK ----------------- " << std::endl;
-    std::cout << "decrypt wall time (seconds)......: " << t1 - t0 << std::endl;
-    std::cout << "serialization wall time (seconds): " << t_end - t1 + t0 << std::endl;
-    std::cout << "total wall time (seconds)........: " << t_end << std::endl;
-    std::cout << "RAM usage (MB)...................: " << profiler.maxrss() / 1e6 << std::endl;
-    std::cout << "gpu call wall time (seconds).....: " << idash_host_last_gpu_seconds() << std::endl;
+    const IdashParams &params = *key.idashParams;
+    read_encrypted_predictions(ciphertexts, params, ENCRYPTED_PREDICTION_FILE);
+    const double stage_s = clock.time([&] { decrypt_predictions(scores, ciphertexts, key); });
+    write_decrypted_predictions(scores, params, by_position ? RESULT_BYPOS_FILE : RESULT_FILE, !by_position);
+    clock.print_benchmark("decrypt wall time (seconds)......: ", stage_s);
     return 0;
 }

@@ -680,6 +680,16 @@ void decrypt_predictions(DecryptedPredictions &predictions, const EncryptedPredi
     host_buf_free(sb);
 }
 
+void StageClock::print_benchmark(const char *stage_label, double stage_seconds) const {
+    const double total = profiler.walltime();
+    std::cout << "----------------- BENCHMARK ----------------- " << std::endl;
+    std::cout << stage_label << stage_seconds << std::endl;
+    std::cout << "serialization wall time (seconds): " << total - stage_seconds << std::endl;
+    std::cout << "total wall time (seconds)........: " << total << std::endl;
+    std::cout << "RAM usage (MB)...................: " << profiler.maxrss() / 1e6 << std::endl;
+    std::cout << "gpu call wall time (seconds).....: " << idash_host_last_gpu_seconds() << std::endl;
+}
+
 // ---- Profiler (eval/idash.cpp:935-965) -------------------------------------------------------------------------
 Profiler::Profiler() : tw0(universalWallTime()), tc0(universalClockTime()) {}
 double Profiler::universalWallTime() {

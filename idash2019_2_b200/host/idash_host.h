@@ -178,4 +178,21 @@ private:
     const double tw0, tc0;
 };
 
+
+// Timing of a stage binary in the reference's BENCHMARK format (eval/cloud.cpp:21-26, eval/decrypt.cpp:42-47,
+// parsed by eval/parse_log.py): the stage itself, everything else as "serialization", the total, the peak RSS --
+// plus the time spent inside the C-ABI calls.
+class StageClock {
+public:
+    template <class F>
+    double time(F &&stage) const {
+        const double t0 = profiler.walltime();
+        stage();
+        return profiler.walltime() - t0;
+    }
+    void print_benchmark(const char *stage_label, double stage_seconds) const;
+private:
+    Profiler profiler;
+};
+
 #endif
