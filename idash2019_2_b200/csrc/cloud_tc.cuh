@@ -23,8 +23,10 @@
 #pragma once
 
 #define TC_TN IDASH_B200_TILE_ROWS   // 64 rows per tile
+#ifndef TC_A_SBO
 #define TC_A_SBO 144u                // bytes between 16-word groups of one 8-feature core-matrix row block (128 + 16 pad:
                                      // conflict-free 128-bit stores, verified by tools/umma_probe.cu)
+#endif
 #define TC_A_LBO (8u * TC_A_SBO)     // bytes between 8-feature groups
 #define TC_B_SBO 128u                // 8 rows x 16 bytes
 #define TC_B_LBO (2u * TC_TN * 16u)  // bytes between 16-feature halves of the [c_lo | c_hi] operand

@@ -708,6 +708,7 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
             return used >= RG_SMEM_MAX ? 0u : (RG_SMEM_MAX - used) / p.b_stage_bytes;
         };
         while (p.n_slots > max_nb + 2u && stages_for(p.n_slots) < 4u) --p.n_slots;
+        if (const char *rs = getenv("IDASH_B200_RING_SLOTS")) p.n_slots = std::max<uint32_t>(max_nb + 1u, std::min<uint32_t>(RG_MAX_SLOTS, (uint32_t) atoi(rs)));   // experiments
         p.n_bstages = std::min<uint32_t>(RG_MAX_BSTAGES, stages_for(p.n_slots));
         p.hdr_off = p.n_slots * RG_BLOCK_BYTES + p.n_bstages * p.b_stage_bytes;
         if (p.n_bstages < 2) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: internal: ring kernel shared-memory budget");
