@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decrypt", action="store_true", help="skip the secondary decrypt-kernel timing")
+    ap.add_argument("--batches", type=int, default=0, help="(debug) batches per step; default = number of GPUs")
+    ap.add_argument("--no-batched", action="store_true", help="N > 1: one launch per batch instead of one batched launch per step")
     ap.add_argument("--kernel", default="auto", choices=["auto", "imad", "tensor", "tile", "ring"],
                     help="cloud kernel: auto (tensor-core when the model is eligible), imad, tensor (ring if eligible, "
                          "else tile), tile (one CTA per tile), ring (persistent)")
@@ -261,7 +263,7 @@ def run_b200(args):
     sh = shard_mod.make_shard(model, NR, args.targets, rank, world)     # contiguous target range + the input slab it reads
     sub, slab, t_lo, t_hi = sh.model, sh.n_ct, sh.target_lo, sh.target_hi
     n_rows = sub.n_out
-    n_batches = world
+    n_batches = args.batches or world
     ctx = api.Context(local_rank)
     ctx.set_kernel({"auto": api.KERNEL_AUTO, "imad": api.KERNEL_IMAD, "tensor": api.KERNEL_TENSOR,
                     "tile": api.KERNEL_TENSOR_TILE, "ring": api.KERNEL_TENSOR_RING}[args.kernel])
@@ -271,11 +273,18 @@ def run_b200(args):
            for _ in range(n_batches)]
     outs = [torch.empty((n_rows, 2048), dtype=torch.int32, device="cuda") for _ in range(n_batches)]
 
-    # The batches of a step are independent evaluations. With more than one they are issued round-robin on two side
-    # streams (fork/join around the main stream), so that the ramp-up and tail of consecutive persistent launches overlap.
-    side = [torch.cuda.Stream() for _ in range(2)] if n_batches > 1 else []
+    # The batches of a step are independent evaluations of the same model on the rank's target range. With more than one they
+    # go through the batched entry point: ONE launch of the persistent kernel walks the tiles of every batch, so the kernel's
+    # ramp-up and tail are paid once per step and not once per batch (--no-batched: one launch per batch, round-robin on two
+    # side streams, the round's earlier scheme).
+    batched = n_batches > 1 and not args.no_batched
+    side = [torch.cuda.Stream() for _ in range(2)] if n_batches > 1 and not batched else []
+    launches_per_step = 1 if (batched or n_batches == 1) else n_batches
 
     def step():
+        if batched:
+            api.cloud_compute_score_device_batched(ctx, m, ins, outs)
+            return
         if not side:
             api.cloud_compute_score_device(ctx, m, ins[0], outs[0])
             return
@@ -303,7 +312,7 @@ def run_b200(args):
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = ctx.kernel_launches()
-    ctx.timing_enable(args.steps * n_batches)
+    ctx.timing_enable(args.steps * launches_per_step)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     if sampler:
@@ -314,7 +323,7 @@ def run_b200(args):
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
-    kernel_ms = ctx.timing_read(args.steps * n_batches)
+    kernel_ms = ctx.timing_read(args.steps * launches_per_step)
     ctx.timing_enable(0)
     launches = ctx.kernel_launches() - launches0
     kernel_used = ctx.last_kernel()
@@ -372,14 +381,14 @@ def run_b200(args):
         ct_per_step = args.targets * 3 * n_batches
         value = slots_per_step * args.steps / (ms_total * 1e-3)
         k_ms = statistics.mean(kernel_ms) if kernel_ms else float("nan")
-        alg_bytes = CT_BYTES * (slab + n_rows)            # per launch: every input ct read once, every output written once
+        alg_bytes = CT_BYTES * (slab + n_rows) * (n_batches // launches_per_step)   # per launch: every input ct read once, every output written once
         peak, peak_src = measured_peak_gbs()
         achieved = alg_bytes / (k_ms * 1e-3) * 1e-9
         how = "algorithmic bytes of one launch / its mean duration (CUDA events on the launch stream)"
         if side:
             # the launches of a step overlap on two streams, so a launch's own duration includes the time it shared the SMs:
             # the GPU's HBM rate is the bytes of all launches of the step over the step time
-            achieved = n_batches * alg_bytes / (ms_total / args.steps * 1e-3) * 1e-9
+            achieved = launches_per_step * alg_bytes / (ms_total / args.steps * 1e-3) * 1e-9
             how = f"{n_batches} launches per step overlap on 2 streams: algorithmic bytes of the step's launches / step time"
         h2d = n_batches * (slab * CT_BYTES)
         d2h = n_batches * (n_rows * (CT_BYTES + 4 + 8))
@@ -396,12 +405,13 @@ def run_b200(args):
                        "neighbors": args.neighbors, "batches": n_batches, "targets_per_gpu": t_hi - t_lo,
                        "in_ct_per_gpu_batch": slab, "out_ct_per_gpu_batch": n_rows,
                        "l2": "inputs+outputs per step (2.4 GB) exceed the 126 MB L2; no explicit flush",
-                       "streams": "batches of a step round-robin on 2 side streams" if side else "single stream",
+                       "streams": ("batches of a step round-robin on 2 side streams" if side else
+                                   f"single stream, one batched launch of {n_batches} batches per step" if batched else "single stream"),
                        "numa_local_cores": numa},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(kernel_name, args, world),
                          "kernel": kernel_name, "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes,
-                         "peak_source": peak_src, "kernel_share_of_step": k_ms * n_batches / (ms_total / args.steps), "how": how},
+                         "peak_source": peak_src, "kernel_share_of_step": k_ms * launches_per_step / (ms_total / args.steps), "how": how},
             "e2e": {"value": slots_per_step * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
                     "matches_device_path": bool(same)},

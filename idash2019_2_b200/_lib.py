@@ -83,6 +83,7 @@ EXPORTS = {
     "idash_b200_cloud_eval_host": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Cts), C.POINTER(Cts), C.c_void_p]),
     "idash_b200_cloud_eval_device": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Cts), C.POINTER(Cts), C.c_void_p,
                                                C.c_void_p]),
+    "idash_b200_cloud_eval_device_batched": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(Cts), C.POINTER(Cts), C.c_void_p]),
     "idash_b200_check_device_status": (C.c_int, [C.c_void_p]),
     "idash_b200_decrypt_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(Cts), C.c_void_p, C.c_void_p]),
     "idash_b200_decrypt_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(Cts), C.c_void_p, C.c_void_p,

@@ -180,6 +180,23 @@ def cloud_compute_score_device(ctx: Context, model: Model, in_ct, out_ct, in_ind
                                                  C.c_void_p(stream)))
 
 
+def cloud_compute_score_device_batched(ctx: Context, model: Model, in_cts, out_cts, stream=None) -> None:
+    """The same model on several (input, output) sets of torch CUDA tensors [n, 2048] int32, PACKED, identity order, in one
+    call (idash_b200_cloud_eval_device_batched): one launch of the ring kernel when it takes the model."""
+    import torch
+    if stream is None:
+        stream = torch.cuda.current_stream().cuda_stream
+    n = len(in_cts)
+    if n != len(out_cts):
+        raise ValueError("in_cts / out_cts length mismatch")
+    cin = (L.Cts * n)()
+    cout = (L.Cts * n)()
+    for b in range(n):
+        cin[b] = L.Cts(LAYOUT_PACKED, in_cts[b].data_ptr(), in_cts[b].numel() // CT_WORDS, None, None)
+        cout[b] = L.Cts(LAYOUT_PACKED, out_cts[b].data_ptr(), out_cts[b].numel() // CT_WORDS, None, None)
+    L.check(L.lib().idash_b200_cloud_eval_device_batched(ctx.handle, model.handle, n, cin, cout, C.c_void_p(stream)))
+
+
 def decrypt_predictions(ctx: Context, key, S: int, ct: np.ndarray, want_phase: bool = False):
     """PACKED host path. key [1024] in {0,1}; ct [n, 2048]. Returns scores [n, S] float32 (and phase [n, 1024])."""
     key = np.ascontiguousarray(key, np.int32)

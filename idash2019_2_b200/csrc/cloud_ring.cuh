@@ -35,6 +35,8 @@
 #define RG_PLANE_BYTES (4u * TC_A_LBO)
 #define RG_MAX_SLOTS 9
 #define RG_MAX_BSTAGES 8
+#define RG_MAX_BATCHES 8u
+#define RG_BATCH_SHIFT 14u                       // input blocks per batch < 2^14 (features < 524 288) in a batched launch
 #define RG_SMEM_MAX (226u * 1024u)               // dynamic shared memory budget of the one resident CTA
 
 struct RingParams {
@@ -55,6 +57,12 @@ struct RingParams {
     uint32_t hdr_off;              // byte offset (dynamic shared memory) of the CTA's tile-header table
     uint32_t max_chunk_tiles;      // capacity of that table (tiles per chunk, rounded up)
     CtView in, out;
+    // Batched launch (n_batches > 1): the same tiles are evaluated for several input / output sets that share the model. The CTAs
+    // walk VIRTUAL tiles v = batch * n_tiles + tile; a batch's input blocks get the virtual index batch << RG_BATCH_SHIFT | block, so
+    // the band still only moves forward (a batch boundary looks like a gap) and no role needs to know about batches except where
+    // it forms a global address. in / out describe batch 0 (layout, stride, count are common to all batches).
+    uint32_t n_batches;
+    unsigned long long batch_in[RG_MAX_BATCHES], batch_out[RG_MAX_BATCHES];   // words pointers of every batch
     const uint32_t *slot_of_ct;
     uint32_t n_ct_slots;
     const uint32_t *slot_of_row;
@@ -224,8 +232,9 @@ __device__ __forceinline__ void ring_epilogue(uint32_t taddr, uint8_t *base_lane
     }
 }
 
-// ROT = NUM_REGIONS > 1 (rotated loads, masked b tail); the NUM_REGIONS == 1 instantiation carries none of that code
-template <bool ROT>
+// ROT = NUM_REGIONS > 1 (rotated loads, masked b tail), BATCHED = several input / output sets in one launch: the plain
+// instantiation carries none of that code (a run-time `batched` flag alone cost the single-set launch 5 %)
+template <bool ROT, bool BATCHED>
 __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t a_full[RG_MAX_SLOTS], b_full[RG_MAX_BSTAGES], t_full[2], t_empty[2];
@@ -235,14 +244,26 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t slice = blockIdx.x & 15u, chunk = blockIdx.x >> 4;
-    const uint32_t t_begin = p.tile_base + (uint32_t) ((uint64_t) p.n_tiles * chunk / p.n_chunks);
-    const uint32_t t_end = p.tile_base + (uint32_t) ((uint64_t) p.n_tiles * (chunk + 1) / p.n_chunks);
+    // virtual tiles of this chunk: v in [t_begin, t_end), real tile = tile_base + v % n_tiles, batch = v / n_tiles
+    const uint32_t n_virtual = p.n_tiles * p.n_batches;
+    const uint32_t t_begin = (uint32_t) ((uint64_t) n_virtual * chunk / p.n_chunks);
+    const uint32_t t_end = (uint32_t) ((uint64_t) n_virtual * (chunk + 1) / p.n_chunks);
     if (t_begin >= t_end) return;
+    constexpr bool batched = BATCHED;
+    uint32_t *hdr_s = reinterpret_cast<uint32_t *>(smem + p.hdr_off);
+    const uint32_t *const hdr_s_ = hdr_s;
+    // (after the header table is built: the batch of a virtual tile of this chunk is read back from its header -- the roles
+    // below map tiles to batches once per tile, and an integer division there cost the epilogue warps 18 % at neighbors = 5)
+    auto batch_of = [&](uint32_t v) -> uint32_t { return batched ? (hdr_s_[v - t_begin] & ((1u << RG_HDR_A_BITS) - 1u)) >> RG_BATCH_SHIFT : 0u; };
+    auto real_tile = [&](uint32_t v) -> uint32_t { return p.tile_base + v - batch_of(v) * p.n_tiles; };
     uint8_t *sA = smem;
     uint8_t *sB = smem + p.n_slots * RG_BLOCK_BYTES;
-    uint32_t *hdr_s = reinterpret_cast<uint32_t *>(smem + p.hdr_off);
+
     const uint32_t n_my = t_end - t_begin;             // <= p.max_chunk_tiles
-    for (uint32_t i = tid; i < n_my; i += RG_THREADS) hdr_s[i] = ring_pack_hdr(p.tiles + t_begin + i);
+    for (uint32_t i = tid; i < n_my; i += RG_THREADS) {
+        const uint32_t v = t_begin + i, b = batched ? v / p.n_tiles : 0u;
+        hdr_s[i] = ring_pack_hdr(p.tiles + p.tile_base + (v - b * p.n_tiles)) + (b << RG_BATCH_SHIFT);
+    }
     const uint32_t w_slice = slice * 128u;
     const bool is_b = (w_slice & POLY_N) != 0;
     const uint32_t i_slice = w_slice & (POLY_N - 1);
@@ -279,7 +300,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
         int32_t bias_q[2];
 #pragma unroll
         for (uint32_t u = 0; u < 2; ++u) {
-            const uint32_t tt = min(t_begin + u, t_end - 1);
+            const uint32_t tt = real_tile(min(t_begin + u, t_end - 1));
             row_q[u] = __ldg(p.tile_rows + (uint64_t) tt * TC_TN + col_base + lane);
             bias_q[u] = __ldg(p.tile_bias + (uint64_t) tt * TC_TN + col_base + lane);
         }
@@ -294,14 +315,15 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                 const bool fast = ring_hdr(hdr_s, it).fast && p.slot_of_row == nullptr;
                 uint64_t ptr_own = 0;
                 uint8_t *base_lane = nullptr;
+                uint8_t *const out_words = batched ? reinterpret_cast<uint8_t *>(p.batch_out[batch_of(t)]) : p.out.words;
                 if (fast) {
                     const uint32_t row0 = __shfl_sync(0xFFFFFFFFu, row, 0);     // caller row of tile row col_base
-                    base_lane = p.out.words + (uint64_t) row0 * p.out.stride + 4u * w_slice + lane_off;
+                    base_lane = out_words + (uint64_t) row0 * p.out.stride + 4u * w_slice + lane_off;
                 } else if (row != IDASH_B200_NO_ROW) {
-                    ptr_own = (uint64_t) (p.out.words + (uint64_t) (p.slot_of_row ? __ldg(p.slot_of_row + row) : row) * p.out.stride + 4u * w_slice);
+                    ptr_own = (uint64_t) (out_words + (uint64_t) (p.slot_of_row ? __ldg(p.slot_of_row + row) : row) * p.out.stride + 4u * w_slice);
                 }
                 {   // prefetch for tile t + 2 (same parity): consumed a whole tile pair later
-                    const uint32_t tt = min(t + 2u, t_end - 1);
+                    const uint32_t tt = real_tile(min(t + 2u, t_end - 1));
                     row_q[u] = __ldg(p.tile_rows + (uint64_t) tt * TC_TN + col_base + lane);
                     bias_q[u] = __ldg(p.tile_bias + (uint64_t) tt * TC_TN + col_base + lane);
                 }
@@ -443,10 +465,14 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
         if (lane == 0) {
             uint32_t bstage = 0, it = 0;
             // the coefficient images of consecutive tiles are contiguous (layout.cpp): b_off advances by the tile's size
-            const uint4 h0 = __ldg(reinterpret_cast<const uint4 *>(p.tiles + t_begin));
+            const uint4 h0 = __ldg(reinterpret_cast<const uint4 *>(p.tiles + real_tile(t_begin)));
             uint64_t b_off = (uint64_t) h0.z | ((uint64_t) h0.w << 32);
             for (uint32_t t = t_begin; t < t_end; ++t, ++it) {
                 const RingTile T = ring_hdr(hdr_s, it);
+                if (batched && t != t_begin && real_tile(t) == p.tile_base) {     // next batch: back to the first image
+                    const uint4 hb = __ldg(reinterpret_cast<const uint4 *>(p.tiles + p.tile_base));
+                    b_off = (uint64_t) hb.z | ((uint64_t) hb.w << 32);
+                }
                 // the stage was last used by tile it - n_bstages: its MMAs must be complete
                 if (it >= p.n_bstages) progress_wait(&tiles_done_s, it - p.n_bstages + 1u);
                 const uint32_t bytes = T.nb * TC_B_CHUNK;
@@ -521,7 +547,9 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
             const uint32_t ct = f / p.NR;
             return i_slice + mg * 16u + (f - ct * p.NR) * p.RS;
         };
-        auto load_block = [&](uint32_t kb, uint4 (&w)[2][NW]) {
+        auto load_block = [&](uint32_t kbv, uint4 (&w)[2][NW]) {
+            const uint32_t kb = batched ? kbv & ((1u << RG_BATCH_SHIFT) - 1u) : kbv;
+            const uint8_t *const in_words = batched ? reinterpret_cast<const uint8_t *>(p.batch_in[kbv >> RG_BATCH_SHIFT]) : p.in.words;
             const uint32_t used_word = kb < p.n_feat_words ? __ldg(p.feat_used + kb) : 0u;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -536,11 +564,11 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
 #pragma unroll
                     for (int q = 0; q < NW; ++q) w[h][q] = make_uint4(0, 0, 0, 0);
                 } else if (!ROT) {
-                    const uint8_t *src = p.in.words + (uint64_t) sl * p.in.stride + 4u * (w_slice + mg * 16u);
+                    const uint8_t *src = in_words + (uint64_t) sl * p.in.stride + 4u * (w_slice + mg * 16u);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) w[h][q] = ldg128(src + 16 * q);
                 } else {
-                    const uint8_t *poly = p.in.words + (uint64_t) sl * p.in.stride + 4u * (w_slice & POLY_N);
+                    const uint8_t *poly = in_words + (uint64_t) sl * p.in.stride + 4u * (w_slice & POLY_N);
                     const uint32_t start = rot_start(f), al = start & ~3u;
 #pragma unroll
                     for (int q = 0; q < NW; ++q)
@@ -549,7 +577,8 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
             }
         };
         // split into byte planes and store into the ring slot, once the slot's previous block has been released
-        auto store_block = [&](uint32_t kb, const uint4 (&w)[2][NW]) {
+        auto store_block = [&](uint32_t kbv, const uint4 (&w)[2][NW]) {
+            const uint32_t kb = batched ? kbv & ((1u << RG_BATCH_SHIFT) - 1u) : kbv;
             if (seq >= p.n_slots) progress_wait(&blocks_freed_s, seq - p.n_slots + 1u);
             uint8_t *blk = sA + slot * RG_BLOCK_BYTES;
 #pragma unroll

@@ -427,8 +427,10 @@ extern "C" int idash_b200_init(idash_b200_ctx **out, int device) {
     CUDA_TRY(cudaFuncSetAttribute(decrypt_tc_kernel<IDASH_B200_CT_BYTES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dec_tc_smem_bytes(DT_MAX_SLOTS)));
     CUDA_TRY(cudaFuncSetAttribute(decrypt_tc_kernel<IDASH_B200_RECORD_BYTES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dec_tc_smem_bytes(DT_MAX_SLOTS)));
     CUDA_TRY(cudaFuncSetAttribute(decrypt_tc_kernel<IDASH_B200_RECORD_BYTES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dec_tc_smem_bytes(DT_MAX_SLOTS)));
-    CUDA_TRY(cudaFuncSetAttribute(cloud_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) RG_SMEM_MAX));
-    CUDA_TRY(cudaFuncSetAttribute(cloud_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) RG_SMEM_MAX));
+    CUDA_TRY(cudaFuncSetAttribute(cloud_ring_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) RG_SMEM_MAX));
+    CUDA_TRY(cudaFuncSetAttribute(cloud_ring_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) RG_SMEM_MAX));
+    CUDA_TRY(cudaFuncSetAttribute(cloud_ring_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) RG_SMEM_MAX));
+    CUDA_TRY(cudaFuncSetAttribute(cloud_ring_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) RG_SMEM_MAX));
     *out = c;
     return IDASH_B200_OK;
 }
@@ -610,8 +612,11 @@ static int make_view(const idash_b200_cts *a, bool is_output, CtView *v, const c
 
 static bool ring_selected(const idash_b200_ctx *c, const idash_b200_layout *L);
 
+// n_batches > 1 (batched launch): ins / outs hold the views of every batch (in == ins[0], out == outs[0]); the caller has checked
+// that the ring kernel takes the model and that the inputs are in identity order.
 static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtView &in, const CtView &out,
-                        const uint32_t *d_slot_of_row, cudaStream_t st, const Piece *piece = nullptr) {
+                        const uint32_t *d_slot_of_row, cudaStream_t st, const Piece *piece = nullptr,
+                        uint32_t n_batches = 1, const CtView *ins = nullptr, const CtView *outs = nullptr) {
     const idash_b200_layout *L = m->layout;
     if (out.count != L->n_rows) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: out->count (%llu) != model rows (%llu)",
                                                  (unsigned long long) out.count, (unsigned long long) L->n_rows);
@@ -674,16 +679,19 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
     f.slot_of_row = d_slot_of_row;
     f.default_var = 8.8817841970012523e-16;   // alpha^2 = 2^-50 (eval/idash.cpp:20, tlwe-functions.cpp:38)
     f.var_wsum = m->d_var_wsum;
-    f.var_uniform = nullptr;
-    if ((in.records || in.variance) && in.count) {
-        CUDA_TRY(cudaMemsetAsync(c->d_var_flag, 0, 2 * sizeof(uint64_t), c->s_aux));
-        variance_scan_kernel<<<(unsigned) ((in.count + 255) / 256), 256, 0, c->s_aux>>>(in, c->d_var_flag);
+    for (uint32_t b = 0; b < n_batches; ++b) {
+        if (n_batches > 1) { f.in = ins[b]; f.out = outs[b]; }
+        f.var_uniform = nullptr;
+        if ((f.in.records || f.in.variance) && f.in.count) {
+            CUDA_TRY(cudaMemsetAsync(c->d_var_flag, 0, 2 * sizeof(uint64_t), c->s_aux));
+            variance_scan_kernel<<<(unsigned) ((f.in.count + 255) / 256), 256, 0, c->s_aux>>>(f.in, c->d_var_flag);
+            c->launches++;
+            f.var_uniform = c->d_var_flag;
+        }
+        cloud_finalize_kernel<<<(unsigned) ((f.n_rows - f.row_lo + 63) / 64), 64, 0, c->s_aux>>>(f);   // 64-thread CTAs fit beside a resident ring CTA
         c->launches++;
-        f.var_uniform = c->d_var_flag;
+        CUDA_TRY(cudaGetLastError());
     }
-    cloud_finalize_kernel<<<(unsigned) ((f.n_rows - f.row_lo + 63) / 64), 64, 0, c->s_aux>>>(f);   // 64-thread CTAs fit beside a resident ring CTA
-    c->launches++;
-    CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->ev_join, c->s_aux));
 
     const bool timed = c->t_used < (int) c->t_begin.size();
@@ -699,7 +707,9 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
         p.n_chunks = (uint32_t) c->sm_count / 16u;
         const uint32_t max_nb = L->tile_kmax / 32u;
         p.b_stage_bytes = max_nb * TC_B_CHUNK;
-        p.max_chunk_tiles = (p.n_tiles + p.n_chunks - 1u) / p.n_chunks + 1u;
+        p.n_batches = n_batches;
+        for (uint32_t b = 0; b < n_batches && n_batches > 1; ++b) { p.batch_in[b] = (unsigned long long) ins[b].words; p.batch_out[b] = (unsigned long long) outs[b].words; }
+        p.max_chunk_tiles = (p.n_tiles * n_batches + p.n_chunks - 1u) / p.n_chunks + 1u;
         // as many input-block slots as fit next to at least 4 (else 2) coefficient stages: slots beyond the widest tile
         // (+ 2) are what lets the block producers run ahead of the MMAs
         p.n_slots = RG_MAX_SLOTS;
@@ -724,8 +734,14 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
         if (const char *tu = getenv("IDASH_B200_TUNE")) p.tune = (uint32_t) atoi(tu);
         if (const char *tr = getenv("IDASH_B200_TRACE")) p.trace_cta = (uint32_t) atoi(tr) + 1u;
         const size_t ring_smem = ring_smem_bytes(p.n_slots, p.n_bstages, p.b_stage_bytes, p.max_chunk_tiles);
-        if (L->NR == 1) cloud_ring_kernel<false><<<16u * p.n_chunks, RG_THREADS, ring_smem, st>>>(p);
-        else cloud_ring_kernel<true><<<16u * p.n_chunks, RG_THREADS, ring_smem, st>>>(p);
+        const dim3 grid(16u * p.n_chunks);
+        if (n_batches > 1) {
+            if (L->NR == 1) cloud_ring_kernel<false, true><<<grid, RG_THREADS, ring_smem, st>>>(p);
+            else cloud_ring_kernel<true, true><<<grid, RG_THREADS, ring_smem, st>>>(p);
+        } else {
+            if (L->NR == 1) cloud_ring_kernel<false, false><<<grid, RG_THREADS, ring_smem, st>>>(p);
+            else cloud_ring_kernel<true, false><<<grid, RG_THREADS, ring_smem, st>>>(p);
+        }
         if (p.trace_cta) {   // debugging only: dump the timeline of the traced CTA to the file named by IDASH_B200_TRACE_FILE
             static unsigned long long h[RG_TRACE_TILES * RG_TRACE_EVENTS];
             CUDA_TRY(cudaStreamSynchronize(st));
@@ -811,6 +827,40 @@ extern "C" int idash_b200_cloud_eval_device(idash_b200_ctx *c, const idash_b200_
     if ((rc = make_view(in, false, &vin, "cloud_eval_device(in)"))) return rc;
     if ((rc = make_view(out, true, &vout, "cloud_eval_device(out)"))) return rc;
     return launch_cloud(c, m, vin, vout, slot_of_row, (cudaStream_t) stream);
+}
+
+// The same model on several input / output sets in ONE launch of the persistent ring kernel (eval/idash.cpp:763-848 once per
+// set). This is what a GPU that evaluates its target range for several sample batches wants: N launches over 1/N of the targets
+// each pay the kernel's ramp-up and tail N times. Sets the ring kernel cannot take in one launch are evaluated one after another.
+extern "C" int idash_b200_cloud_eval_device_batched(idash_b200_ctx *c, const idash_b200_model *m, uint32_t n_batches,
+                                                    const idash_b200_cts *in, const idash_b200_cts *out, void *stream) {
+    clear_error();
+    if (!c || !m || !in || !out) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_device_batched: null argument");
+    if (n_batches == 0) return IDASH_B200_OK;
+    if (m->device != c->device) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_device_batched: model lives on device %d, ctx on %d", m->device, c->device);
+    CUDA_TRY(cudaSetDevice(c->device));
+    const idash_b200_layout *L = m->layout;
+    std::vector<CtView> vin(n_batches), vout(n_batches);
+    int rc;
+    bool one_launch = n_batches > 1 && n_batches <= RG_MAX_BATCHES && ring_selected(c, L);
+    for (uint32_t b = 0; b < n_batches; ++b) {
+        if ((rc = make_view(&in[b], false, &vin[b], "cloud_eval_device_batched(in)"))) return rc;
+        if ((rc = make_view(&out[b], true, &vout[b], "cloud_eval_device_batched(out)"))) return rc;
+        // one launch: every set in the same layout and size, inputs in identity order (slot = ciphertext index)
+        one_launch = one_launch && !vin[b].records && vin[b].index == nullptr && vin[b].count == vin[0].count && vin[b].stride == vin[0].stride &&
+                     (vin[b].variance != nullptr) == (vin[0].variance != nullptr) &&
+                     vout[b].records == vout[0].records && vout[b].count == vout[0].count && vout[b].stride == vout[0].stride &&
+                     (vout[b].index != nullptr) == (vout[0].index != nullptr) && (vout[b].variance != nullptr) == (vout[0].variance != nullptr);
+    }
+    if (one_launch) {
+        const uint64_t chunk_tiles = (L->tiles.size() * n_batches + c->sm_count / 16 - 1) / (c->sm_count / 16) + 1;
+        const uint64_t blocks = L->tiles.empty() ? 0 : (L->tiles.back().f_base >> 5) + IDASH_B200_TILE_KMAX / 32u;
+        one_launch = chunk_tiles * 4u <= 32768u && blocks < (1u << RG_BATCH_SHIFT);
+    }
+    if (one_launch) return launch_cloud(c, m, vin[0], vout[0], nullptr, (cudaStream_t) stream, nullptr, n_batches, vin.data(), vout.data());
+    for (uint32_t b = 0; b < n_batches; ++b)
+        if ((rc = launch_cloud(c, m, vin[b], vout[b], nullptr, (cudaStream_t) stream))) return rc;
+    return IDASH_B200_OK;
 }
 
 extern "C" int idash_b200_check_device_status(idash_b200_ctx *c) {

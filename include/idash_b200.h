@@ -143,6 +143,13 @@ int idash_b200_cloud_eval_host(idash_b200_ctx *ctx, const idash_b200_model *mode
                                const idash_b200_cts *out, const uint32_t *slot_of_row);
 int idash_b200_cloud_eval_device(idash_b200_ctx *ctx, const idash_b200_model *model, const idash_b200_cts *in,
                                  const idash_b200_cts *out, const uint32_t *slot_of_row, void *cuda_stream);
+/* The same model on n_batches input / output sets (in[b] -> out[b], b < n_batches) in one call: what a GPU that owns a target
+ * range does for several sample batches (BASELINE configs[4]). When the ring kernel takes the model, all sets are PACKED
+ * with inputs in identity order (index == NULL) and have the same sizes, they are evaluated by ONE launch (n_batches <= 8);
+ * otherwise one after another on the same stream. Results are identical to n_batches calls of cloud_eval_device. */
+int idash_b200_cloud_eval_device_batched(idash_b200_ctx *ctx, const idash_b200_model *model, uint32_t n_batches,
+                                         const idash_b200_cts *in, const idash_b200_cts *out, void *cuda_stream);
+
 /* After a *_device call and a stream synchronise: IDASH_B200_ERR_MISSING_INPUT if a kernel met a model
  * entry whose ciphertext was not supplied, else IDASH_B200_OK. Clears the flag. */
 int idash_b200_check_device_status(idash_b200_ctx *ctx);

@@ -101,6 +101,37 @@ def test_cloud_output_variance_paths(gpu_ctx, kind):
     m.free()
 
 
+@pytest.mark.parametrize("S,n_batches,G", [(1004, 2, 3000), (1004, 5, 2600), (335, 3, 2600), (1004, 8, 700), (400, 9, 300)])
+def test_cloud_batched_launch_matches_single_launches(gpu_ctx, S, n_batches, G):
+    """idash_b200_cloud_eval_device_batched: several input sets through the same model in ONE launch of the ring kernel
+    (virtual tiles; batch boundaries inside a chunk) == one cloud_eval_device call per set == the oracle on a sample. More
+    than 8 sets (or an ineligible model) falls back to one launch per set."""
+    import torch
+    geo, model, cts, var = make_case(S, T=500, G=G, n=5, seed=S + n_batches)
+    m = api.Model(gpu_ctx, S, geo.NR, geo.RS, model.out_bidx, model.row_ptr, model.col, model.coef)
+    gpu_ctx.set_kernel(api.KERNEL_AUTO)
+    g = torch.Generator(device="cuda").manual_seed(n_batches)
+    ins = [torch.from_numpy(cts.view(np.int32)).cuda()] + \
+          [torch.randint(-2 ** 31, 2 ** 31, cts.shape, dtype=torch.int32, device="cuda", generator=g) for _ in range(n_batches - 1)]
+    outs_b = [torch.zeros((model.n_out, 2048), dtype=torch.int32, device="cuda") for _ in range(n_batches)]
+    outs_s = [torch.zeros((model.n_out, 2048), dtype=torch.int32, device="cuda") for _ in range(n_batches)]
+    l0 = gpu_ctx.kernel_launches()
+    api.cloud_compute_score_device_batched(gpu_ctx, m, ins, outs_b)
+    l1 = gpu_ctx.kernel_launches()
+    for b in range(n_batches):
+        api.cloud_compute_score_device(gpu_ctx, m, ins[b], outs_s[b])
+    torch.cuda.synchronize()
+    gpu_ctx.check_device_status()
+    if m.info["ring_ok"] and m.info["n_tiles"] * n_batches >= 1 and n_batches <= 8:
+        assert gpu_ctx.last_kernel() == _lib.KERNEL_TENSOR_RING
+    for b in range(n_batches):
+        assert torch.equal(outs_b[b], outs_s[b]), b
+    ref_out, _ = _oracle(S, geo, model, cts, var)
+    assert np.array_equal(outs_b[0].cpu().numpy().view(np.uint32), ref_out)
+    assert l1 > l0
+    m.free()
+
+
 def test_cloud_permuted_input_slots_and_scattered_outputs(kctx):
     S = 400
     geo, model, cts, var = make_case(S, T=50, G=80, n=5, seed=21)
