@@ -22,6 +22,9 @@
 //     serial waits the MMA warp, not HBM, set the tile rate.)
 //   * TMEM: 2 stages x 4 accumulators x 64 columns = all 512 columns, so the MMAs of tile t+1 overlap the
 //     epilogue of tile t.
+//   * batched launches (template parameter BATCHED): the same model on several input / output sets -- what a GPU that
+//     owns a target range does for several sample batches. The tile list is walked once per set as VIRTUAL tiles;
+//     see RingParams::n_batches. One launch instead of N pays the ramp-up and the tail of the persistent grid once.
 #pragma once
 
 #define RG_THREADS 512
