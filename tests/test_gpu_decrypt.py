@@ -92,6 +92,34 @@ def test_decrypt_golden_prediction_file(gpu_ctx, name):
     assert ((ref_sc == scores[order]) | (ref_sc == lo) | (ref_sc == hi)).all()
 
 
+def test_decrypt_device_path_properties_at_scale(gpu_ctx, decrypt_kernel):
+    """BASELINE size (242 646 ciphertexts, S = 1004) on device tensors, through properties that need no oracle pass over 2 GB:
+    the phase is linear in the ciphertext (mod 2^32), the zero key returns b, scores are the decode of the phases, and a
+    strided sample equals the exact oracle."""
+    import torch
+    if decrypt_kernel == api.DECRYPT_IADD:
+        pytest.skip("the CUDA-core kernel takes 17 ms per pass; the property run is for the tensor-core kernel")
+    n, S = 242646, 1004
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randint(-2 ** 31, 2 ** 31, (n, 2048), dtype=torch.int32, device="cuda", generator=g)
+    y = torch.randint(-2 ** 31, 2 ** 31, (n, 2048), dtype=torch.int32, device="cuda", generator=g)
+    key = np.random.default_rng(3).integers(0, 2, 1024).astype(np.int32)
+    ph = [torch.empty((n, 1024), dtype=torch.int32, device="cuda") for _ in range(3)]
+    sc = torch.empty((n, S), dtype=torch.float32, device="cuda")
+    api.decrypt_predictions_device(gpu_ctx, key, S, x, sc, ph[0])
+    api.decrypt_predictions_device(gpu_ctx, key, S, y, None, ph[1])
+    api.decrypt_predictions_device(gpu_ctx, key, S, x + y, None, ph[2])        # int32 adds wrap: the sum mod 2^32
+    torch.cuda.synchronize()
+    assert torch.equal(ph[2], ph[0] + ph[1])
+    assert torch.equal(sc, (ph[0][:, :S].to(torch.float64) / 2.0 ** 32).to(torch.float32))
+    api.decrypt_predictions_device(gpu_ctx, np.zeros(1024, np.int32), S, x, None, ph[1])
+    torch.cuda.synchronize()
+    assert torch.equal(ph[1], x[:, 1024:])
+    idx = torch.arange(0, n, 4099, device="cuda")
+    ref = po.phase_exact_port(key, x[idx].cpu().numpy().view(np.uint32))
+    assert np.array_equal(ph[0][idx].cpu().numpy().view(np.uint32), ref)
+
+
 def test_decrypt_empty(gpu_ctx):
     s = api.decrypt_predictions(gpu_ctx, np.zeros(1024, np.int32), 16, np.zeros((0, 2048), np.uint32))
     assert s.shape == (0, 16)
