@@ -11,8 +11,11 @@ from pathlib import Path
 
 import numpy as np
 
+import os
+
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "lib" / "libidash_b200.so"
+# tools/ (tuning sweeps, knock-out and trace runs) load the profiling build, which honours the IDASH_B200_* debug variables
+LIB_PATH = PKG / "lib" / ("libidash_b200_prof.so" if os.environ.get("IDASH_B200_USE_PROFILE_LIB") == "1" else "libidash_b200.so")
 
 N = 1024
 CT_WORDS = 2048

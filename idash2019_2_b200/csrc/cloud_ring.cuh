@@ -37,10 +37,11 @@
 #define RG_BLOCK_BYTES (16u * TC_A_LBO)          // 4 planes x 4 feature groups x 1152 B = 18432
 #define RG_PLANE_BYTES (4u * TC_A_LBO)
 #define RG_MAX_SLOTS 9
-#define RG_MAX_BSTAGES 8
+#define RG_BBARS 8u                              // per-tile "coefficients landed" barriers (tile it uses b_full[it % 8])
 #define RG_MAX_BATCHES 8u
 #define RG_BATCH_SHIFT 14u                       // input blocks per batch < 2^14 (features < 524 288) in a batched launch
 #define RG_SMEM_MAX (226u * 1024u)               // dynamic shared memory budget of the one resident CTA
+#define RG_TUNE_DEFAULT 8u                       // RingParams::tune of the production library
 
 struct RingParams {
     const idash_b200_tile *tiles;
@@ -51,10 +52,11 @@ struct RingParams {
     uint32_t n_feat_words;
     uint32_t n_tiles;              // tiles of this launch: [tile_base, tile_base + n_tiles)
     uint32_t tile_base;
-    uint32_t n_chunks;             // gridDim.x = 16 * n_chunks
+    uint32_t n_chunks;             // gridDim.x = n_slices * n_chunks
+    uint32_t n_slices;             // 128-word slices of the ciphertext axis that are COMPUTED: 16, or 8 + ceil(RS / 128) when
+                                   // NUM_REGIONS > 1 (b[RS..N) is zero, eval/idash.cpp:839-841: those slices are only zero-filled)
     uint32_t n_slots;              // input-block ring slots (>= widest tile in blocks, + prefetch)
-    uint32_t n_bstages;            // coefficient ring stages (one tile each)
-    uint32_t b_stage_bytes;        // bytes of one coefficient stage = widest tile's image
+    uint32_t n_bchunks;            // coefficient ring: 4096-byte chunks (one 32-feature K step each), a tile takes K / 32 of them
     uint64_t coef_bytes;           // size of the coefficient image array (bound for the L2 prefetch)
     uint32_t coef_prefetch;        // the loader prefetches the images this many tiles ahead into L2 (0 = off)
     uint32_t hdr_off;              // byte offset (dynamic shared memory) of the CTA's tile-header table
@@ -72,14 +74,15 @@ struct RingParams {
     uint32_t S, NR, RS;            // NUM_SAMPLES, NUM_REGIONS, REGION_SIZE (feature f = ciphertext f / NR rotated by (f % NR) * RS words)
     int *status;
     uint32_t trace_cta;            // 0 = off, else 1 + index of the CTA whose timeline is recorded
-    uint32_t tune;                 // experiment switches (IDASH_B200_TUNE): 1 epilogue waits with try_wait, 2 publisher waits with
-                                   // try_wait, 4 MMA warp polls without nanosleep, 8 warp-converged MMA issue (uniform operands)
+    uint32_t tune;                 // schedule switches: 1 epilogue waits with try_wait, 2 publisher waits with try_wait, 4 MMA warp polls
+                                   // without nanosleep, 8 warp-converged MMA issue (uniform operands), 32 the two MMA warps issue their
+                                   // tiles strictly in tile order, 64 the epilogue frees its TMEM stage after its last tcgen05.ld
     uint32_t knockout;             // profiling aid (IDASH_B200_KNOCKOUT, results are wrong when non-zero):
                                    // 1 no MMAs, 2 no output stores, 4 no epilogue TMEM loads, 8 no input loads
 };
 
-__host__ __device__ constexpr uint32_t ring_smem_bytes(uint32_t n_slots, uint32_t n_bstages, uint32_t b_stage_bytes, uint32_t max_chunk_tiles) {
-    return n_slots * RG_BLOCK_BYTES + n_bstages * b_stage_bytes + 4u * max_chunk_tiles;
+__host__ __device__ constexpr uint32_t ring_smem_bytes(uint32_t n_slots, uint32_t n_bchunks, uint32_t max_chunk_tiles) {
+    return n_slots * RG_BLOCK_BYTES + n_bchunks * TC_B_CHUNK + 4u * max_chunk_tiles;
 }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -208,16 +211,24 @@ __device__ __forceinline__ void ring_ld_chunk(uint32_t taddr, uint32_t (&v0)[8],
 // accumulators), 8 rows per tcgen05.ld group, the loads of group g+1 in flight while group g is recombined and
 // stored. FAST: rows are consecutive output slots with a compile-time stride -> store address = base + immediate.
 // ptr_own / bias_own: lane l holds the output address (0 = no such row) / Constant * 2^18 of row col_base + l.
+// release_bar: the TMEM stage's t_empty barrier when the stage is to be handed back as soon as the last tcgen05.ld of this warp
+// has completed (the accumulators are in registers then; the recombine + stores of the last group no longer need TMEM), or
+// nullptr when the caller arrives after the whole epilogue. Returns true if it has arrived.
 template <bool FAST, uint32_t STRIDE, bool BIAS, bool MASK = false>
-__device__ __forceinline__ void ring_epilogue(uint32_t taddr, uint8_t *base_lane, uint64_t ptr_own, uint32_t bias_own, uint32_t bias_flag,
-                                              uint32_t lane_off, uint32_t knockout, uint32_t keep_mask = 0xFFFFFFFFu) {
-    if (knockout & 4u) return;
+__device__ __forceinline__ bool ring_epilogue(uint32_t taddr, uint8_t *base_lane, uint64_t ptr_own, uint32_t bias_own, uint32_t bias_flag,
+                                              uint32_t lane_off, uint32_t knockout, uint32_t keep_mask, uint64_t *release_bar) {
+    if (knockout & 4u) return false;
     uint32_t v[2][4][8];
     ring_ld_chunk(taddr, v[0][0], v[0][1], v[0][2], v[0][3]);
 #pragma unroll
     for (uint32_t g = 0; g < 4; ++g) {
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (g + 1 < 4) ring_ld_chunk(taddr + (g + 1) * 8u, v[(g + 1) & 1][0], v[(g + 1) & 1][1], v[(g + 1) & 1][2], v[(g + 1) & 1][3]);
+        else if (release_bar) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if ((threadIdx.x & 31u) == 0) mbar_arrive(release_bar);
+        }
 #pragma unroll
         for (uint32_t c = 0; c < 8; ++c) {
             const uint32_t n = g * 8u + c;
@@ -233,6 +244,11 @@ __device__ __forceinline__ void ring_epilogue(uint32_t taddr, uint8_t *base_lane
             }
         }
     }
+    return release_bar != nullptr;
+}
+
+__device__ __forceinline__ void stg128_zero_stream(void *p) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1, %1, %1, %1};" ::"l"(p), "r"(0u) : "memory");
 }
 
 // ROT = NUM_REGIONS > 1 (rotated loads, masked b tail), BATCHED = several input / output sets in one launch: the plain
@@ -240,13 +256,14 @@ __device__ __forceinline__ void ring_epilogue(uint32_t taddr, uint8_t *base_lane
 template <bool ROT, bool BATCHED>
 __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t a_full[RG_MAX_SLOTS], b_full[RG_MAX_BSTAGES], t_full[2], t_empty[2];
+    __shared__ __align__(8) uint64_t a_full[RG_MAX_SLOTS], b_full[RG_BBARS], t_full[2], t_empty[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ uint32_t tiles_done_s;       // tiles of this CTA whose MMAs are complete
     __shared__ uint32_t blocks_freed_s;     // input blocks (in staging order) that no pending MMA reads any more
+    __shared__ uint32_t mma_issued_s;       // tiles of this CTA whose MMAs have all been handed to the tensor pipe (tune & 32)
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t slice = blockIdx.x & 15u, chunk = blockIdx.x >> 4;
+    const uint32_t chunk = blockIdx.x / p.n_slices, slice = blockIdx.x - chunk * p.n_slices;
     // virtual tiles of this chunk: v in [t_begin, t_end), real tile = tile_base + v % n_tiles, batch = v / n_tiles
     const uint32_t n_virtual = p.n_tiles * p.n_batches;
     const uint32_t t_begin = (uint32_t) ((uint64_t) n_virtual * chunk / p.n_chunks);
@@ -273,10 +290,11 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
 
     if (tid == 0) {
         for (uint32_t s = 0; s < p.n_slots; ++s) mbar_init(&a_full[s], 4);
-        for (uint32_t s = 0; s < p.n_bstages; ++s) mbar_init(&b_full[s], 1);
+        for (uint32_t s = 0; s < RG_BBARS; ++s) mbar_init(&b_full[s], 1);
         for (uint32_t s = 0; s < 2; ++s) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], RG_EPI_WARPS + 1); }   // 8 epilogue warps + the publisher
         tiles_done_s = 0;
         blocks_freed_s = 0;
+        mma_issued_s = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == RG_WARP_MMA) {
@@ -296,6 +314,12 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
         const uint32_t bias_flag = (is_b && i_slice + word_in_slice < p.S) ? 1u : 0u;
         const uint32_t keep_mask = (is_b && i_slice + word_in_slice >= p.RS) ? 0u : 0xFFFFFFFFu;
         const bool records = p.out.records != 0;
+        const bool early = (p.tune & 64u) != 0u;
+        // NUM_REGIONS > 1: the 16 - n_slices slices that lie entirely in b[RS..N) are not computed by anyone; the epilogue warps
+        // of the n_slices computing CTAs zero-fill them, 512 bytes (one slice of one row) per warp instruction, tile by tile, so
+        // that all 8 KB of an output ciphertext are still written at about the same time
+        const uint32_t n_zero_seg = ROT ? 16u - p.n_slices : 0u;
+        const uint32_t zero_units = n_zero_seg * TC_TN, zero_workers = p.n_slices * RG_EPI_WARPS, zero_me = slice * RG_EPI_WARPS + warp;
         // Row information (caller row + Constant of row col_base + lane) comes from global memory. It is prefetched TWO
         // tiles ahead into registers that are statically bound to the tile's parity (= its TMEM stage): the loop is
         // unrolled by two, so no register is shifted between tiles and nothing waits for a load that was just issued.
@@ -334,21 +358,37 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (tid == 0) RG_TRACE(6, it);
                 const uint32_t taddr = tmem + ((quad * 32u) << 16) + st * 4u * TC_TN + col_base;
+                uint64_t *const rel = early ? &t_empty[st] : nullptr;
+                bool arrived;
                 if (fast) {
                     if (records) {
-                        if (is_b) ring_epilogue<true, IDASH_B200_RECORD_BYTES, true, ROT>(taddr, base_lane, 0, bias_own, bias_flag, lane_off, p.knockout, keep_mask);
-                        else ring_epilogue<true, IDASH_B200_RECORD_BYTES, false>(taddr, base_lane, 0, 0, 0, lane_off, p.knockout);
+                        if (is_b) arrived = ring_epilogue<true, IDASH_B200_RECORD_BYTES, true, ROT>(taddr, base_lane, 0, bias_own, bias_flag, lane_off, p.knockout, keep_mask, rel);
+                        else arrived = ring_epilogue<true, IDASH_B200_RECORD_BYTES, false>(taddr, base_lane, 0, 0, 0, lane_off, p.knockout, 0xFFFFFFFFu, rel);
                     } else {
-                        if (is_b) ring_epilogue<true, IDASH_B200_CT_BYTES, true, ROT>(taddr, base_lane, 0, bias_own, bias_flag, lane_off, p.knockout, keep_mask);
-                        else ring_epilogue<true, IDASH_B200_CT_BYTES, false>(taddr, base_lane, 0, 0, 0, lane_off, p.knockout);
+                        if (is_b) arrived = ring_epilogue<true, IDASH_B200_CT_BYTES, true, ROT>(taddr, base_lane, 0, bias_own, bias_flag, lane_off, p.knockout, keep_mask, rel);
+                        else arrived = ring_epilogue<true, IDASH_B200_CT_BYTES, false>(taddr, base_lane, 0, 0, 0, lane_off, p.knockout, 0xFFFFFFFFu, rel);
                     }
                 } else {
-                    ring_epilogue<false, 0, true, ROT>(taddr, nullptr, ptr_own, bias_own, bias_flag, lane_off, p.knockout, keep_mask);
+                    arrived = ring_epilogue<false, 0, true, ROT>(taddr, nullptr, ptr_own, bias_own, bias_flag, lane_off, p.knockout, keep_mask, rel);
                 }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
+                if (!arrived) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&t_empty[st]);      // one arrival per epilogue warp
+                }
+                if (ROT && zero_units && !(p.knockout & 2u)) {
+                    // zero fill of b[128 n_slices - 1024 .. 1024) of this tile's rows: unit u = (tile row u / n_zero_seg, segment u % n_zero_seg)
+                    const uint32_t row_lane0 = __shfl_sync(0xFFFFFFFFu, row, 0);       // caller row of tile row col_base
+                    const uint32_t tt = real_tile(t);
+                    for (uint32_t u = zero_me; u < zero_units; u += zero_workers) {
+                        const uint32_t n = u / n_zero_seg, seg = u - n * n_zero_seg;
+                        uint32_t r = fast ? row_lane0 - col_base + n : __ldg(p.tile_rows + (uint64_t) tt * TC_TN + n);
+                        if (r == IDASH_B200_NO_ROW) continue;
+                        if (p.slot_of_row) r = __ldg(p.slot_of_row + r);
+                        stg128_zero_stream(out_words + (uint64_t) r * p.out.stride + 512u * (p.n_slices + seg) + 16u * lane);
+                    }
+                }
                 if (tid == 0) RG_TRACE(8, it);
-                if (lane == 0) mbar_arrive(&t_empty[st]);      // one arrival per epilogue warp
             }
         }
     } else if (warp == RG_WARP_MMA || warp == RG_WARP_MMA2) {
@@ -358,18 +398,18 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
         // MMAs, commit, ring bookkeeping) and was what bounded the tile rate; the two stages are independent chains, so
         // they get one stream each. Both warps walk every tile to keep the ring state, but wait and issue only for their own.
         const uint32_t q = warp == RG_WARP_MMA2 ? 1u : 0u;
-        const uint32_t n_slots = p.n_slots, n_bstages = p.n_bstages;
+        const uint32_t n_slots = p.n_slots, n_bchunks = p.n_bchunks;
+        const bool fifo = (p.tune & 32u) != 0u;
         const uint64_t da_base = tc_desc(smem_u32(sA), TC_A_LBO, TC_A_SBO);
         const uint64_t db_base = tc_desc(smem_u32(sB), TC_B_LBO, TC_B_SBO);
         uint32_t it = 0;
         uint32_t next_slot = 0, next_par = 0;       // slot / phase parity of the next input block to be staged
         uint32_t first_slot = 0;                    // slot of block T.a
-        uint32_t bstage = 0, bpar = 0;              // coefficient ring position
+        uint32_t bpos = 0;                          // coefficient ring position (chunk) of the tile's first K step
         uint32_t prev_fn = 0, prev_bt = 0, prev_slot = 0, prev_par = 0;   // new blocks of the previous tile: [prev_fn, prev_bt) from prev_slot
         RingWalk walk;
         walk.init(ring_hdr(hdr_s, 0).a);
         const uint32_t tmem_u = __shfl_sync(0xFFFFFFFFu, tmem, 0);
-        const uint32_t bsb_u = p.b_stage_bytes;
         const uint32_t leader = elect_one();
         for (uint32_t t = t_begin; t < t_end; ++t, ++it) {
             const bool has_next = t + 1 < t_end;
@@ -389,7 +429,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                 uint64_t *bar = nullptr;
                 uint32_t par = 0;
                 if (lane == 0) { bar = &t_empty[st]; par = ((it >> 1) & 1u) ^ 1u; }
-                else if (lane == 1) { bar = &b_full[bstage]; par = bpar; }
+                else if (lane == 1) { bar = &b_full[it & (RG_BBARS - 1u)]; par = (it / RG_BBARS) & 1u; }
                 else if (lane - 2u < n_new) {
                     uint32_t s = next_slot + (lane - 2u);
                     par = next_par;
@@ -403,10 +443,23 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                 }
                 // warp-uniform polling loop: lanes without a barrier count as done
                 const uint32_t bar_addr = bar ? smem_u32(bar) : 0u;
-                uint32_t done = bar ? 0u : 1u;
+                // lane 31 (tune & 32): the other warp has handed ALL MMAs of the previous tile to the tensor pipe. The pipe executes
+                // in issue order; without this the two warps' MMAs interleave, both tiles complete late and at the same time, and
+                // the two TMEM stages run in step (MMA phase, then epilogue phase) instead of overlapping.
+                const bool order_lane = fifo && lane == 31u && it != 0u;
+                uint32_t done = (bar || order_lane) ? 0u : 1u;
                 long long t_done = 0;
                 for (;;) {
-                    if (!done) { done = mbar_test(bar_addr, par); if (done && p.trace_cta) t_done = clock64(); }
+                    if (!done) {
+                        if (order_lane) {
+                            uint32_t v;
+                            asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(&mma_issued_s)) : "memory");
+                            done = (int32_t) (v - it) >= 0 ? 1u : 0u;
+                        } else {
+                            done = mbar_test(bar_addr, par);
+                        }
+                        if (done && p.trace_cta) t_done = clock64();
+                    }
                     if (__all_sync(0xFFFFFFFFu, done)) break;
                     if (!(p.tune & 4u)) __nanosleep(40);      // polling hot next to running MMAs slows them down (measured)
                 }
@@ -427,34 +480,40 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                 const uint32_t nb_u = __shfl_sync(0xFFFFFFFFu, T.nb, 0);
                 uint32_t aslot = __shfl_sync(0xFFFFFFFFu, first_slot, 0);
                 const uint32_t d0 = tmem_u + st * 4u * TC_TN;
-                const uint64_t db = db_base + (uint64_t) ((bstage * bsb_u) >> 4);
+                uint32_t bchunk = __shfl_sync(0xFFFFFFFFu, bpos, 0);
                 if (!(p.knockout & 1u)) {
                     for (uint32_t ks = 0; ks < nb_u; ++ks) {
                         tc_mma_kstep_p(d0, da_base + (uint64_t) ((aslot * RG_BLOCK_BYTES) >> 4), RG_PLANE_BYTES >> 4,
-                                       db + (uint64_t) ((ks * TC_B_CHUNK) >> 4), ks == 0, leader);
+                                       db_base + (uint64_t) ((bchunk * TC_B_CHUNK) >> 4), ks == 0, leader);
                         if (++aslot == n_slots) aslot = 0;
+                        if (++bchunk == n_bchunks) bchunk = 0;
                     }
                 }
-                if (leader) tc_commit(&t_full[st]);
+                if (leader) {
+                    if (fifo) progress_publish(&mma_issued_s, it + 1u);
+                    tc_commit(&t_full[st]);
+                }
                 if (lane == 0) RG_TRACE(5, it);
             } else
             if (lane == 0) {
                 const uint32_t d0 = tmem + st * 4u * TC_TN;
-                const uint64_t db = db_base + (uint64_t) ((bstage * p.b_stage_bytes) >> 4);
-                uint32_t aslot = first_slot;
+                uint32_t aslot = first_slot, bchunk = bpos;
                 if (!(p.knockout & 1u)) {
                     for (uint32_t ks = 0; ks < T.nb; ++ks) {
                         tc_mma_kstep(d0, da_base + (uint64_t) ((aslot * RG_BLOCK_BYTES) >> 4), RG_PLANE_BYTES >> 4,
-                                     db + (uint64_t) ((ks * TC_B_CHUNK) >> 4), ks == 0);
+                                     db_base + (uint64_t) ((bchunk * TC_B_CHUNK) >> 4), ks == 0);
                         if (++aslot == n_slots) aslot = 0;
+                        if (++bchunk == n_bchunks) bchunk = 0;
                     }
                 }
+                if (fifo) progress_publish(&mma_issued_s, it + 1u);
                 tc_commit(&t_full[st]);     // the only commit of the tile: epilogue and publisher wait on it
                 RG_TRACE(5, it);
             }
             __syncwarp();
             }
-            if (++bstage == n_bstages) { bstage = 0; bpar ^= 1u; }
+            bpos += T.nb;
+            if (bpos >= n_bchunks) bpos -= n_bchunks;
             uint32_t rb, re;
             walk.advance(T, Tn, has_next, rb, re);
             // slot of the next tile's first block
@@ -464,9 +523,12 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
             }
         }
     } else if (warp == RG_WARP_BLOAD) {
-        // ================= coefficient loader: one bulk copy per tile =================
+        // ================= coefficient loader: the tile's image into a ring of 4096-byte chunks =================
+        // A tile takes K / 32 consecutive chunks (wrapping), so narrow tiles do not reserve the widest tile's size and the image of
+        // tile t + 2 can be on its way while tiles t and t + 1 still hold theirs. One mbarrier per tile (b_full[it % 8]) collects the
+        // bytes of its (at most two) bulk copies.
         if (lane == 0) {
-            uint32_t bstage = 0, it = 0;
+            uint32_t it = 0, cpos = 0, loaded = 0, freed = 0, done_it = 0;
             // the coefficient images of consecutive tiles are contiguous (layout.cpp): b_off advances by the tile's size
             const uint4 h0 = __ldg(reinterpret_cast<const uint4 *>(p.tiles + real_tile(t_begin)));
             uint64_t b_off = (uint64_t) h0.z | ((uint64_t) h0.w << 32);
@@ -476,24 +538,37 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                     const uint4 hb = __ldg(reinterpret_cast<const uint4 *>(p.tiles + p.tile_base));
                     b_off = (uint64_t) hb.z | ((uint64_t) hb.w << 32);
                 }
-                // the stage was last used by tile it - n_bstages: its MMAs must be complete
-                if (it >= p.n_bstages) progress_wait(&tiles_done_s, it - p.n_bstages + 1u);
+                // ring space: chunks of tiles whose MMAs are complete are free again
+                while (loaded + T.nb - freed > p.n_bchunks) {
+                    progress_wait(&tiles_done_s, done_it + 1u);
+                    freed += ring_hdr(hdr_s, done_it).nb;
+                    ++done_it;
+                }
+                // the barrier was last used by tile it - 8: its MMAs (hence its waiters) must be past it
+                if (it >= RG_BBARS) progress_wait(&tiles_done_s, it - RG_BBARS + 1u);
                 const uint32_t bytes = T.nb * TC_B_CHUNK;
+                uint64_t *const bar = &b_full[it & (RG_BBARS - 1u)];
                 RG_TRACE(10, it);
-                mbar_arrive_expect_tx(&b_full[bstage], bytes);
+                mbar_arrive_expect_tx(bar, bytes);
+                const uint32_t first = min(T.nb, p.n_bchunks - cpos) * TC_B_CHUNK;
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(smem_u32(sB + bstage * p.b_stage_bytes)), "l"(p.tile_coef + b_off), "r"(bytes), "r"(smem_u32(&b_full[bstage]))
+                             ::"r"(smem_u32(sB + cpos * TC_B_CHUNK)), "l"(p.tile_coef + b_off), "r"(first), "r"(smem_u32(bar))
                              : "memory");
+                if (first < bytes)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(smem_u32(sB)), "l"(p.tile_coef + b_off + first), "r"(bytes - first), "r"(smem_u32(bar))
+                                 : "memory");
+                cpos += T.nb;
+                if (cpos >= p.n_bchunks) cpos -= p.n_bchunks;
+                loaded += T.nb;
                 b_off += bytes;
-                // With only n_bstages tile-sized stages the copy of tile t + n_bstages starts when tile t's MMAs are complete, and
-                // its HBM/L2 latency (measured ~1800 cycles for a 28 KB image at neighbors = 50) is then on the critical path of the
-                // TMEM stage. The images are contiguous, so the ones a few tiles ahead are pulled into L2 now.
+                // The images are contiguous, so the ones a few tiles ahead are pulled into L2 now: a copy that starts when ring space
+                // frees up then pays the L2 latency, not HBM's (measured at neighbors = 50: 0.673 -> 0.640 ms).
                 if (p.coef_prefetch) {
                     const uint64_t pf = b_off + (uint64_t) p.coef_prefetch * bytes;
                     if (pf + bytes <= p.coef_bytes)
                         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.tile_coef + pf), "r"(bytes) : "memory");
                 }
-                if (++bstage == p.n_bstages) bstage = 0;
             }
         }
     } else if (warp == RG_WARP_PUB) {
@@ -542,10 +617,6 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
         // flip and the word-granular realignment by start % 4 happen in store_block -- consuming the data right after
         // the loads made every block wait out its own HBM latency and arrive ~2000 cycles after its tile was ready.
         constexpr int NW = ROT ? 5 : 4;
-        // A slice that lies entirely in b[RS..N) is stored as zeros whatever its accumulators hold, yet it stages its inputs like
-        // every other slice: skipping the loads (tune bit 16) lets those CTAs run ahead of the rest of their chunk, the 16 segments
-        // of an output ciphertext are then written at different times, and the kernel gets SLOWER (0.642 vs 0.571 ms, cfg 4).
-        const bool slice_masked = ROT && is_b && i_slice >= p.RS && (p.tune & 16u);
         auto rot_start = [&](uint32_t f) -> uint32_t {       // first word of this thread's window in the negacyclic extension
             const uint32_t ct = f / p.NR;
             return i_slice + mg * 16u + (f - ct * p.NR) * p.RS;
@@ -562,7 +633,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                 uint32_t sl = NO_SLOT;
                 if (ct < p.n_ct_slots) sl = p.slot_of_ct ? __ldg(p.slot_of_ct + ct) : ct;
                 if (p.knockout & 8u) sl = NO_SLOT;
-                if (sl == NO_SLOT || slice_masked) {
+                if (sl == NO_SLOT) {
                     if (sl == NO_SLOT && ((used_word >> k) & 1u) && !(p.knockout & 8u)) atomicOr(p.status, 1);
 #pragma unroll
                     for (int q = 0; q < NW; ++q) w[h][q] = make_uint4(0, 0, 0, 0);

@@ -610,7 +610,22 @@ static int make_view(const idash_b200_cts *a, bool is_output, CtView *v, const c
     return IDASH_B200_OK;
 }
 
+// Launch geometry of the persistent ring kernel for a model on this device (shared by the eligibility checks and the launch, so
+// that a shape whose shared-memory budget does not work out selects another kernel / per-batch launches instead of failing).
+struct RingPlan { uint32_t n_slices, n_chunks, n_slots, n_bchunks, max_chunk_tiles; };
+static bool ring_plan(const idash_b200_ctx *c, const idash_b200_layout *L, uint64_t n_tiles, uint32_t n_batches, RingPlan *rp);
 static bool ring_selected(const idash_b200_ctx *c, const idash_b200_layout *L);
+
+// Debug / tuning environment variables are only honoured by the profiling build (-DIDASH_B200_PROFILE, libidash_b200_prof.so):
+// a stray variable must not change what the production library computes or launches.
+static inline const char *debug_env(const char *name) {
+#ifdef IDASH_B200_PROFILE
+    return getenv(name);
+#else
+    (void) name;
+    return nullptr;
+#endif
+}
 
 // n_batches > 1 (batched launch): ins / outs hold the views of every batch (in == ins[0], out == outs[0]); the caller has checked
 // that the ring kernel takes the model and that the inputs are in identity order.
@@ -704,37 +719,26 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
         p.n_feat_words = (uint32_t) L->feat_used.size();
         p.n_tiles = piece ? piece->tile_hi - piece->tile_lo : (uint32_t) L->tiles.size();
         p.tile_base = piece ? piece->tile_lo : 0u;
-        p.n_chunks = (uint32_t) c->sm_count / 16u;
+        RingPlan rp;
+        if (!ring_plan(c, L, p.n_tiles, n_batches, &rp)) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: internal: ring kernel shared-memory budget");
+        p.n_slices = rp.n_slices; p.n_chunks = rp.n_chunks; p.n_slots = rp.n_slots; p.n_bchunks = rp.n_bchunks; p.max_chunk_tiles = rp.max_chunk_tiles;
         const uint32_t max_nb = L->tile_kmax / 32u;
-        p.b_stage_bytes = max_nb * TC_B_CHUNK;
         p.n_batches = n_batches;
         for (uint32_t b = 0; b < n_batches && n_batches > 1; ++b) { p.batch_in[b] = (unsigned long long) ins[b].words; p.batch_out[b] = (unsigned long long) outs[b].words; }
-        p.max_chunk_tiles = (p.n_tiles * n_batches + p.n_chunks - 1u) / p.n_chunks + 1u;
-        // as many input-block slots as fit next to at least 4 (else 2) coefficient stages: slots beyond the widest tile
-        // (+ 2) are what lets the block producers run ahead of the MMAs
-        p.n_slots = RG_MAX_SLOTS;
-        const auto stages_for = [&](uint32_t slots) {
-            const uint32_t used = slots * RG_BLOCK_BYTES + 4u * p.max_chunk_tiles;
-            return used >= RG_SMEM_MAX ? 0u : (RG_SMEM_MAX - used) / p.b_stage_bytes;
-        };
-        while (p.n_slots > max_nb + 2u && stages_for(p.n_slots) < 4u) --p.n_slots;
-        if (const char *rs = getenv("IDASH_B200_RING_SLOTS")) p.n_slots = std::max<uint32_t>(max_nb + 1u, std::min<uint32_t>(RG_MAX_SLOTS, (uint32_t) atoi(rs)));   // experiments
-        p.n_bstages = std::min<uint32_t>(RG_MAX_BSTAGES, stages_for(p.n_slots));
-        p.hdr_off = p.n_slots * RG_BLOCK_BYTES + p.n_bstages * p.b_stage_bytes;
-        if (p.n_bstages < 2) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: internal: ring kernel shared-memory budget");
+        p.hdr_off = p.n_slots * RG_BLOCK_BYTES + p.n_bchunks * TC_B_CHUNK;
         p.in = in; p.out = out;
         p.slot_of_ct = d_slot_of_ct; p.n_ct_slots = n_ct_slots; p.slot_of_row = d_slot_of_row;
         p.S = L->S; p.NR = L->NR; p.RS = L->RS;
         p.coef_bytes = L->tile_coef.size();
         p.coef_prefetch = max_nb >= 5u ? 2u : 0u;     // measured: 0.673 -> 0.640 ms at neighbors = 50 (7 blocks), nothing to gain on narrow bands
-        if (const char *cp = getenv("IDASH_B200_COEF_PREFETCH")) p.coef_prefetch = (uint32_t) atoi(cp);
+        if (const char *cp = debug_env("IDASH_B200_COEF_PREFETCH")) p.coef_prefetch = (uint32_t) atoi(cp);
         p.status = c->d_status;
-        if (const char *ko = getenv("IDASH_B200_KNOCKOUT")) p.knockout = (uint32_t) atoi(ko);
-        p.tune = 8u;      // warp-converged MMA issue (see cloud_ring.cuh)
-        if (const char *tu = getenv("IDASH_B200_TUNE")) p.tune = (uint32_t) atoi(tu);
-        if (const char *tr = getenv("IDASH_B200_TRACE")) p.trace_cta = (uint32_t) atoi(tr) + 1u;
-        const size_t ring_smem = ring_smem_bytes(p.n_slots, p.n_bstages, p.b_stage_bytes, p.max_chunk_tiles);
-        const dim3 grid(16u * p.n_chunks);
+        if (const char *ko = debug_env("IDASH_B200_KNOCKOUT")) p.knockout = (uint32_t) atoi(ko);
+        p.tune = RG_TUNE_DEFAULT;
+        if (const char *tu = debug_env("IDASH_B200_TUNE")) p.tune = (uint32_t) atoi(tu);
+        if (const char *tr = debug_env("IDASH_B200_TRACE")) p.trace_cta = (uint32_t) atoi(tr) + 1u;
+        const size_t ring_smem = ring_smem_bytes(p.n_slots, p.n_bchunks, p.max_chunk_tiles);
+        const dim3 grid(p.n_slices * p.n_chunks);
         if (n_batches > 1) {
             if (L->NR == 1) cloud_ring_kernel<false, true><<<grid, RG_THREADS, ring_smem, st>>>(p);
             else cloud_ring_kernel<true, true><<<grid, RG_THREADS, ring_smem, st>>>(p);
@@ -746,7 +750,7 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
             static unsigned long long h[RG_TRACE_TILES * RG_TRACE_EVENTS];
             CUDA_TRY(cudaStreamSynchronize(st));
             CUDA_TRY(cudaMemcpyFromSymbol(h, g_ring_trace, sizeof(h)));
-            const char *fn = getenv("IDASH_B200_TRACE_FILE");
+            const char *fn = debug_env("IDASH_B200_TRACE_FILE");
             if (FILE *f = fopen(fn ? fn : "ring_trace.txt", "w")) {
                 for (int i = 0; i < RG_TRACE_TILES; ++i) {
                     for (int e = 0; e < RG_TRACE_EVENTS; ++e) fprintf(f, "%llu ", h[i * RG_TRACE_EVENTS + e]);
@@ -802,18 +806,49 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
     CUDA_TRY(cudaGetLastError());
 
     CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join, 0));     // join: the launch is complete when both kernels are
-    c->launches++;
     CUDA_TRY(cudaGetLastError());
     return IDASH_B200_OK;
 }
 
+static bool ring_plan(const idash_b200_ctx *c, const idash_b200_layout *L, uint64_t n_tiles, uint32_t n_batches, RingPlan *rp) {
+    // NUM_REGIONS > 1: b[RS..N) of every output is zero (eval/idash.cpp:839-841), so only the 8 slices of polynomial a and the
+    // ceil(RS / 128) slices of b that hold kept words are computed; the CTAs zero-fill the rest. Fewer slices = more chunks = fewer
+    // tiles per CTA (NUM_REGIONS = 3: 11 x 13 CTAs instead of 16 x 9).
+    rp->n_slices = L->NR == 1 ? 16u : 8u + (L->RS + 127u) / 128u;
+    if ((uint32_t) c->sm_count < rp->n_slices || n_tiles == 0 || L->tile_kmax == 0) return false;
+    rp->n_chunks = (uint32_t) c->sm_count / rp->n_slices;
+    const uint64_t chunk_tiles = (n_tiles * n_batches + rp->n_chunks - 1u) / rp->n_chunks + 1u;
+    if (chunk_tiles * 4u > 65536u) return false;
+    rp->max_chunk_tiles = (uint32_t) chunk_tiles;
+    const uint32_t max_nb = L->tile_kmax / 32u;
+    const auto chunks_for = [&](uint32_t slots) -> uint32_t {
+        const uint32_t used = slots * RG_BLOCK_BYTES + 4u * rp->max_chunk_tiles;
+        return used >= RG_SMEM_MAX ? 0u : std::min<uint32_t>(64u, (RG_SMEM_MAX - used) / TC_B_CHUNK);
+    };
+    // as many input-block slots as leave room for the coefficient images of almost three tiles of the widest band (the image of tile
+    // t + 2 is then in flight while t and t + 1 are resident); failing that, two tiles
+    const uint32_t lo = max_nb + 1u;
+    uint32_t slots = 0;
+    for (uint32_t s = RG_MAX_SLOTS; s >= lo && !slots; --s) if (chunks_for(s) >= std::max(3u * max_nb - 1u, 4u)) slots = s;
+    for (uint32_t s = RG_MAX_SLOTS; s >= lo && !slots; --s) if (chunks_for(s) >= 2u * max_nb) slots = s;
+    if (!slots) return false;
+    if (const char *rs = debug_env("IDASH_B200_RING_SLOTS")) {   // experiments
+        const uint32_t s = (uint32_t) atoi(rs);
+        if (s >= lo && s <= RG_MAX_SLOTS && chunks_for(s) >= 2u * max_nb) slots = s;
+    }
+    rp->n_slots = slots;
+    rp->n_bchunks = chunks_for(slots);
+    if (const char *bc = debug_env("IDASH_B200_RING_BCHUNKS")) rp->n_bchunks = std::max(2u * max_nb, std::min(rp->n_bchunks, (uint32_t) atoi(bc)));
+    return true;
+}
+
 // Would launch_cloud pick the persistent ring kernel for this model under the ctx's kernel choice?
 static bool ring_selected(const idash_b200_ctx *c, const idash_b200_layout *L) {
-    if (L->tiles.empty() || !L->ring_ok || c->sm_count < 16) return false;
+    if (L->tiles.empty() || !L->ring_ok) return false;
     if (c->kernel_choice == IDASH_B200_KERNEL_IMAD || c->kernel_choice == IDASH_B200_KERNEL_TENSOR_TILE) return false;
+    RingPlan rp;
     // the ring kernel keeps a 4-byte header per tile of a chunk in shared memory (first block in 20 bits)
-    const uint64_t chunk_tiles = (L->tiles.size() + c->sm_count / 16 - 1) / (c->sm_count / 16) + 1;
-    return chunk_tiles * 4u <= 32768u && (L->tiles.back().f_base >> 5) + IDASH_B200_TILE_KMAX / 32u < (1u << RG_HDR_A_BITS);
+    return ring_plan(c, L, L->tiles.size(), 1, &rp) && (L->tiles.back().f_base >> 5) + IDASH_B200_TILE_KMAX / 32u < (1u << RG_HDR_A_BITS);
 }
 
 extern "C" int idash_b200_cloud_eval_device(idash_b200_ctx *c, const idash_b200_model *m, const idash_b200_cts *in,
@@ -853,9 +888,9 @@ extern "C" int idash_b200_cloud_eval_device_batched(idash_b200_ctx *c, const ida
                      (vout[b].index != nullptr) == (vout[0].index != nullptr) && (vout[b].variance != nullptr) == (vout[0].variance != nullptr);
     }
     if (one_launch) {
-        const uint64_t chunk_tiles = (L->tiles.size() * n_batches + c->sm_count / 16 - 1) / (c->sm_count / 16) + 1;
+        RingPlan rp;
         const uint64_t blocks = L->tiles.empty() ? 0 : (L->tiles.back().f_base >> 5) + IDASH_B200_TILE_KMAX / 32u;
-        one_launch = chunk_tiles * 4u <= 32768u && blocks < (1u << RG_BATCH_SHIFT);
+        one_launch = ring_plan(c, L, L->tiles.size(), n_batches, &rp) && blocks < (1u << RG_BATCH_SHIFT);
     }
     if (one_launch) return launch_cloud(c, m, vin[0], vout[0], nullptr, (cudaStream_t) stream, nullptr, n_batches, vin.data(), vout.data());
     for (uint32_t b = 0; b < n_batches; ++b)
@@ -1115,9 +1150,9 @@ static int launch_decrypt(idash_b200_ctx *c, const KeyBits &kb, uint32_t S, cons
         p.phase = d_phase;
         p.key = kb;
         uint64_t grid = std::min<uint64_t>(p.n_groups, (uint64_t) c->sm_count);
-        if (const char *gs = getenv("IDASH_B200_DECRYPT_GRID")) grid = std::max<uint64_t>(1, std::min<uint64_t>(grid, (uint64_t) atoi(gs)));   // tests: many groups per CTA
-        if (const char *ns = getenv("IDASH_B200_DECRYPT_SLOTS")) p.n_slots = std::max<uint32_t>(DT_GROUP_SLOTS, std::min<uint32_t>(DT_MAX_SLOTS, (uint32_t) atoi(ns)));
-        if (const char *ko = getenv("IDASH_B200_DECRYPT_KNOCKOUT")) p.knockout = (uint32_t) atoi(ko);
+        if (const char *gs = debug_env("IDASH_B200_DECRYPT_GRID")) grid = std::max<uint64_t>(1, std::min<uint64_t>(grid, (uint64_t) atoi(gs)));   // tests: many groups per CTA
+        if (const char *ns = debug_env("IDASH_B200_DECRYPT_SLOTS")) p.n_slots = std::max<uint32_t>(DT_GROUP_SLOTS, std::min<uint32_t>(DT_MAX_SLOTS, (uint32_t) atoi(ns)));
+        if (const char *ko = debug_env("IDASH_B200_DECRYPT_KNOCKOUT")) p.knockout = (uint32_t) atoi(ko);
         const size_t smem = dec_tc_smem_bytes(p.n_slots);
         if (in.stride == IDASH_B200_RECORD_BYTES) {
             if (d_phase) decrypt_tc_kernel<IDASH_B200_RECORD_BYTES, true><<<(unsigned) grid, DT_THREADS, smem, st>>>(p);
