@@ -50,7 +50,8 @@ class ModelInfo(C.Structure):
     _fields_ = [("n_rows", C.c_uint64), ("nnz", C.c_uint64), ("n_groups", C.c_uint64), ("n_entries", C.c_uint64),
                 ("ct_min", C.c_uint32), ("ct_max", C.c_uint32), ("max_entries_per_group", C.c_uint32),
                 ("shifts_aligned", C.c_uint32), ("device_bytes", C.c_uint64), ("n_tiles", C.c_uint64),
-                ("tile_kmax", C.c_uint32), ("ring_ok", C.c_uint32)]
+                ("tile_kmax", C.c_uint32), ("ring_ok", C.c_uint32), ("n_overflow_rows", C.c_uint64), ("groups_all", C.c_uint32),
+                ("pad", C.c_uint32)]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
@@ -62,7 +63,8 @@ GROUP_DTYPE = np.dtype([("entry_begin", "<u4"), ("n_a", "<u4"), ("n_ab", "<u4"),
 TILE_DTYPE = np.dtype([("f_base", "<u4"), ("K", "<u4"), ("b_off", "<u8"), ("used_off", "<u4"), ("n_valid", "<u4"),
                        ("flags", "<u4"), ("pad", "<u4")])
 assert ENTRY_DTYPE.itemsize == 32 and GROUP_DTYPE.itemsize == 64 and TILE_DTYPE.itemsize == 32
-TILE_ROWS, TILE_KMAX = 64, 256
+TILE_ROWS, TILE_KMAX, RING_KMAX = 64, 256, 224
+COMPILE_DEFAULT, COMPILE_GROUPS_ALL = 0, 1
 KERNEL_AUTO, KERNEL_IMAD, KERNEL_TENSOR, KERNEL_TENSOR_TILE, KERNEL_TENSOR_RING = 0, 1, 2, 3, 4
 DECRYPT_AUTO, DECRYPT_IADD, DECRYPT_TENSOR = 0, 1, 2
 
@@ -81,6 +83,7 @@ EXPORTS = {
     "idash_b200_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "idash_b200_host_free": (C.c_int, [C.c_void_p]),
     "idash_b200_model_upload": (C.c_int, [C.c_void_p, C.POINTER(ModelDesc), C.POINTER(C.c_void_p)]),
+    "idash_b200_model_upload_layout": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "idash_b200_model_free": (C.c_int, [C.c_void_p]),
     "idash_b200_model_get_info": (C.c_int, [C.c_void_p, C.POINTER(ModelInfo)]),
     "idash_b200_cloud_eval_host": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Cts), C.POINTER(Cts), C.c_void_p]),
@@ -92,6 +95,16 @@ EXPORTS = {
     "idash_b200_decrypt_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(Cts), C.c_void_p, C.c_void_p,
                                             C.c_void_p]),
     "idash_b200_layout_compile": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(C.c_void_p)]),
+    "idash_b200_layout_compile_ex": (C.c_int, [C.POINTER(ModelDesc), C.c_uint32, C.POINTER(C.c_void_p)]),
+    "idash_b200_layout_ensure_groups_all": (C.c_int, [C.c_void_p]),
+    "idash_b200_layout_save": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64]),
+    "idash_b200_layout_load": (C.c_int, [C.c_char_p, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "idash_b200_layout_feat_ptr": (C.c_void_p, [C.c_void_p]),
+    "idash_b200_layout_feat_bidx": (C.c_void_p, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "idash_b200_layout_feat_coef": (C.c_void_p, [C.c_void_p]),
+    "idash_b200_layout_bias": (C.c_void_p, [C.c_void_p]),
+    "idash_b200_layout_overflow_groups": (C.c_void_p, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "idash_b200_layout_overflow_entries": (C.c_void_p, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "idash_b200_layout_free": (C.c_int, [C.c_void_p]),
     "idash_b200_layout_get_info": (C.c_int, [C.c_void_p, C.POINTER(ModelInfo)]),
     "idash_b200_layout_groups": (C.c_void_p, [C.c_void_p, C.POINTER(C.c_uint64)]),

@@ -18,8 +18,9 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib as L
-from ._lib import (CONSTANT_BIDX, CT_BYTES, CT_WORDS, DECRYPT_AUTO, DECRYPT_IADD, DECRYPT_TENSOR, KERNEL_AUTO, KERNEL_IMAD, KERNEL_TENSOR,  # noqa: F401
-                   KERNEL_TENSOR_RING, KERNEL_TENSOR_TILE, LAYOUT_PACKED, LAYOUT_RECORDS, N, RECORD_BYTES, IdashB200Error)
+from ._lib import (COMPILE_DEFAULT, COMPILE_GROUPS_ALL, CONSTANT_BIDX, CT_BYTES, CT_WORDS, DECRYPT_AUTO, DECRYPT_IADD, DECRYPT_TENSOR,  # noqa: F401
+                   KERNEL_AUTO, KERNEL_IMAD, KERNEL_TENSOR, KERNEL_TENSOR_RING, KERNEL_TENSOR_TILE, LAYOUT_PACKED, LAYOUT_RECORDS, N,
+                   RECORD_BYTES, IdashB200Error)
 
 
 class Context:
@@ -92,6 +93,22 @@ class Model:
         self.out_bidx = keep[0]
         self._h = C.c_void_p()
         L.check(L.lib().idash_b200_model_upload(ctx.handle, C.byref(desc), C.byref(self._h)))
+        self._read_info()
+
+    @classmethod
+    def from_cache(cls, ctx: Context, path, key: int) -> "Model":
+        """The cached packed model (idash_b200_layout_load + idash_b200_model_upload_layout); raises if the file does not match."""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        lay = C.c_void_p()
+        L.check(L.lib().idash_b200_layout_load(str(path).encode(), int(key), C.byref(lay)))
+        self._h = C.c_void_p()
+        L.check(L.lib().idash_b200_model_upload_layout(ctx.handle, lay, C.byref(self._h)))
+        self._read_info()
+        self.out_bidx = None
+        return self
+
+    def _read_info(self):
         info = L.ModelInfo()
         L.check(L.lib().idash_b200_model_get_info(self._h, C.byref(info)))
         self.info = info.as_dict()
@@ -250,14 +267,38 @@ class Layout:
     tile_bias: np.ndarray   # [n_tiles * 64]
     tile_coef: np.ndarray   # uint8 coefficient images
     tile_used: np.ndarray   # uint32 masks
+    overflow_groups: np.ndarray = None    # IMAD groups of the rows no tile holds
+    overflow_entries: np.ndarray = None
+    feat_ptr: np.ndarray = None           # the model as the layout keeps it: per caller row, entries sorted by input bigIndex
+    feat_bidx: np.ndarray = None
+    feat_coef: np.ndarray = None
+    bias: np.ndarray = None
 
 
-def compile_layout(S, NR, RS, out_bidx, row_ptr, col, coef) -> Layout:
+def compile_layout(S, NR, RS, out_bidx, row_ptr, col, coef, flags: int = COMPILE_GROUPS_ALL, save_to=None, key: int = 0) -> Layout:
     """Runs the host-side model compiler only (no GPU) and copies the layout out as numpy arrays."""
     lib = L.lib()
     desc, keep = L.make_desc(S, NR, RS, out_bidx, row_ptr, col, coef)
     h = C.c_void_p()
-    L.check(lib.idash_b200_layout_compile(C.byref(desc), C.byref(h)))
+    L.check(lib.idash_b200_layout_compile_ex(C.byref(desc), int(flags), C.byref(h)))
+    if save_to is not None:
+        try:
+            L.check(lib.idash_b200_layout_save(h, str(save_to).encode(), int(key)))
+        except Exception:
+            lib.idash_b200_layout_free(h)
+            raise
+    return _export_layout(h)
+
+
+def load_layout(path, key: int) -> Layout:
+    """idash_b200_layout_load: the cached packed model as numpy arrays (raises IdashB200Error if it does not match)."""
+    h = C.c_void_p()
+    L.check(L.lib().idash_b200_layout_load(str(path).encode(), int(key), C.byref(h)))
+    return _export_layout(h)
+
+
+def _export_layout(h) -> Layout:
+    lib = L.lib()
     try:
         info = L.ModelInfo()
         L.check(lib.idash_b200_layout_get_info(h, C.byref(info)))
@@ -293,6 +334,17 @@ def compile_layout(S, NR, RS, out_bidx, row_ptr, col, coef) -> Layout:
         nu = C.c_uint64()
         up = lib.idash_b200_layout_tile_used(h, C.byref(nu))
         t_used = arr(up, C.c_uint32, nu.value, np.uint32)
-        return Layout(info.as_dict(), groups, entries, vp, vc, vw, ob, tiles, t_rows, t_bias, t_coef, t_used)
+        n = C.c_uint64()
+        ogp = lib.idash_b200_layout_overflow_groups(h, C.byref(n))
+        o_groups = arr(ogp, C.c_uint8, n.value * 64, L.GROUP_DTYPE)
+        oep = lib.idash_b200_layout_overflow_entries(h, C.byref(n))
+        o_entries = arr(oep, C.c_uint8, n.value * 32, L.ENTRY_DTYPE)
+        f_ptr = arr(lib.idash_b200_layout_feat_ptr(h), C.c_uint64, n_rows + 1, np.uint64)
+        fb_p = lib.idash_b200_layout_feat_bidx(h, C.byref(n))
+        f_bidx = arr(fb_p, C.c_uint32, n.value, np.uint32)
+        f_coef = arr(lib.idash_b200_layout_feat_coef(h), C.c_int32, n.value, np.int32)
+        bias = arr(lib.idash_b200_layout_bias(h), C.c_int32, n_rows, np.int32)
+        return Layout(info.as_dict(), groups, entries, vp, vc, vw, ob, tiles, t_rows, t_bias, t_coef, t_used, o_groups, o_entries,
+                      f_ptr, f_bidx, f_coef, bias)
     finally:
         lib.idash_b200_layout_free(h)

@@ -76,7 +76,8 @@ struct RingParams {
     uint32_t trace_cta;            // 0 = off, else 1 + index of the CTA whose timeline is recorded
     uint32_t tune;                 // schedule switches: 1 epilogue waits with try_wait, 2 publisher waits with try_wait, 4 MMA warp polls
                                    // without nanosleep, 8 warp-converged MMA issue (uniform operands), 32 the two MMA warps issue their
-                                   // tiles strictly in tile order, 64 the epilogue frees its TMEM stage after its last tcgen05.ld
+                                   // tiles strictly in tile order, 64 the epilogue frees its TMEM stage after its last tcgen05.ld, 128 weight-stationary MMAs (the
+                                   // coefficient chunk of a K step is read from shared memory once, tcgen05.mma.ws + collector buffer)
     uint32_t knockout;             // profiling aid (IDASH_B200_KNOCKOUT, results are wrong when non-zero):
                                    // 1 no MMAs, 2 no output stores, 4 no epilogue TMEM loads, 8 no input loads
 };
@@ -133,6 +134,34 @@ __device__ __forceinline__ void tc_mma_kstep_p(uint32_t d0, uint64_t da, uint32_
     tc_mma_p(d0 + 2 * TC_TN, da + 2 * (uint64_t) plane_units, db, tc_idesc(2 * TC_TN), acc, leader);
     tc_mma_p(d0 + 1 * TC_TN, da + 1 * (uint64_t) plane_units, db, tc_idesc(2 * TC_TN), 1u, leader);
     tc_mma_p(d0 + 3 * TC_TN, da + 3 * (uint64_t) plane_units, db, tc_idesc(TC_TN), 1u, leader);
+}
+// Weight-stationary form (tune & 128): the four MMAs of a K step multiply four different limb planes by the SAME coefficient chunk.
+// tcgen05.mma.ws keeps the B operand in a collector buffer of the tensor core (fill -> use -> lastuse), so the chunk is read from
+// shared memory once per K step instead of three times: an N = 128, K = 32 i8 MMA reads 8 KB of operands in its 64 cycles -- all
+// of the 128 B/clk the shared-memory pipe has -- and every other shared-memory access of the CTA (TMA writes of the coefficient
+// images, the producers' operand stores) slows the MMAs down (measured in the kernel: 84 cycles per MMA instead of 64).
+// BUF: collector buffer of the issuing warp (the two MMA warps interleave in the pipe and must not share one).
+#define TC_MMA_WS(BUFSTR, USAGE)                                                                                            \
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"                               \
+                 "@q tcgen05.mma.ws.cta_group::1.kind::i8.collector::" BUFSTR "::" USAGE " [%0], %1, %2, %3, p;\n\t}\n"          \
+                 ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(leader) : "memory")
+template <int BUF, int USAGE>   // USAGE 0 fill, 1 use, 2 lastuse, 3 discard
+__device__ __forceinline__ void tc_mma_ws_p(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate, uint32_t leader) {
+    if (BUF == 0) {
+        if (USAGE == 0) TC_MMA_WS("b0", "fill"); else if (USAGE == 1) TC_MMA_WS("b0", "use");
+        else if (USAGE == 2) TC_MMA_WS("b0", "lastuse"); else TC_MMA_WS("b0", "discard");
+    } else {
+        if (USAGE == 0) TC_MMA_WS("b1", "fill"); else if (USAGE == 1) TC_MMA_WS("b1", "use");
+        else if (USAGE == 2) TC_MMA_WS("b1", "lastuse"); else TC_MMA_WS("b1", "discard");
+    }
+}
+template <int BUF>
+__device__ __forceinline__ void tc_mma_kstep_ws_p(uint32_t d0, uint64_t da, uint32_t plane_units, uint64_t db, bool first, uint32_t leader) {
+    const uint32_t acc = first ? 0u : 1u;
+    tc_mma_ws_p<BUF, 0>(d0 + 0 * TC_TN, da + 0 * (uint64_t) plane_units, db, tc_idesc(2 * TC_TN), acc, leader);
+    tc_mma_ws_p<BUF, 1>(d0 + 2 * TC_TN, da + 2 * (uint64_t) plane_units, db, tc_idesc(2 * TC_TN), acc, leader);
+    tc_mma_ws_p<BUF, 2>(d0 + 1 * TC_TN, da + 1 * (uint64_t) plane_units, db, tc_idesc(2 * TC_TN), 1u, leader);
+    tc_mma_ws_p<BUF, 3>(d0 + 3 * TC_TN, da + 3 * (uint64_t) plane_units, db, tc_idesc(TC_TN), 1u, leader);
 }
 // monotonic progress counters in shared memory
 __device__ __forceinline__ void progress_publish(uint32_t *ctr, uint32_t v) {
@@ -318,7 +347,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
         // NUM_REGIONS > 1: the 16 - n_slices slices that lie entirely in b[RS..N) are not computed by anyone; the epilogue warps
         // of the n_slices computing CTAs zero-fill them, 512 bytes (one slice of one row) per warp instruction, tile by tile, so
         // that all 8 KB of an output ciphertext are still written at about the same time
-        const uint32_t n_zero_seg = ROT ? 16u - p.n_slices : 0u;
+        const uint32_t n_zero_seg = 16u - p.n_slices;
         const uint32_t zero_units = n_zero_seg * TC_TN, zero_workers = p.n_slices * RG_EPI_WARPS, zero_me = slice * RG_EPI_WARPS + warp;
         // Row information (caller row + Constant of row col_base + lane) comes from global memory. It is prefetched TWO
         // tiles ahead into registers that are statically bound to the tile's parity (= its TMEM stage): the loop is
@@ -482,6 +511,15 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                 const uint32_t d0 = tmem_u + st * 4u * TC_TN;
                 uint32_t bchunk = __shfl_sync(0xFFFFFFFFu, bpos, 0);
                 if (!(p.knockout & 1u)) {
+                    if (p.tune & 128u) {
+                        for (uint32_t ks = 0; ks < nb_u; ++ks) {
+                            const uint64_t da = da_base + (uint64_t) ((aslot * RG_BLOCK_BYTES) >> 4), db = db_base + (uint64_t) ((bchunk * TC_B_CHUNK) >> 4);
+                            if (q) tc_mma_kstep_ws_p<1>(d0, da, RG_PLANE_BYTES >> 4, db, ks == 0, leader);
+                            else tc_mma_kstep_ws_p<0>(d0, da, RG_PLANE_BYTES >> 4, db, ks == 0, leader);
+                            if (++aslot == n_slots) aslot = 0;
+                            if (++bchunk == n_bchunks) bchunk = 0;
+                        }
+                    } else
                     for (uint32_t ks = 0; ks < nb_u; ++ks) {
                         tc_mma_kstep_p(d0, da_base + (uint64_t) ((aslot * RG_BLOCK_BYTES) >> 4), RG_PLANE_BYTES >> 4,
                                        db_base + (uint64_t) ((bchunk * TC_B_CHUNK) >> 4), ks == 0, leader);

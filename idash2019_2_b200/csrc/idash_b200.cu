@@ -384,8 +384,10 @@ struct Piece { uint32_t tile_lo, tile_hi; uint64_t row_lo, row_hi; bool first; }
 struct idash_b200_model {
     idash_b200_layout *layout = nullptr;
     int device = 0;
-    idash_b200_group *d_groups = nullptr;
+    idash_b200_group *d_groups = nullptr;      // IMAD groups of the overflow rows (rows no tile holds)
     idash_b200_entry *d_entries = nullptr;
+    mutable idash_b200_group *d_groups_full = nullptr;   // IMAD groups of every row: uploaded when the IMAD kernel evaluates the whole model
+    mutable idash_b200_entry *d_entries_full = nullptr;
     uint64_t *d_var_ptr = nullptr;
     uint32_t *d_var_ct = nullptr;
     double *d_var_w = nullptr;
@@ -529,7 +531,7 @@ static int upload(T **dst, const T *src, size_t n) {
 extern "C" int idash_b200_model_free(idash_b200_model *m) {
     if (!m) return IDASH_B200_OK;
     cudaSetDevice(m->device);
-    cudaFree(m->d_groups); cudaFree(m->d_entries); cudaFree(m->d_var_ptr); cudaFree(m->d_var_ct); cudaFree(m->d_var_w); cudaFree(m->d_var_wsum);
+    cudaFree(m->d_groups); cudaFree(m->d_entries); cudaFree(m->d_groups_full); cudaFree(m->d_entries_full); cudaFree(m->d_var_ptr); cudaFree(m->d_var_ct); cudaFree(m->d_var_w); cudaFree(m->d_var_wsum);
     cudaFree(m->d_out_bidx);
     cudaFree(m->d_tiles); cudaFree(m->d_tile_rows); cudaFree(m->d_tile_bias); cudaFree(m->d_tile_coef); cudaFree(m->d_tile_used);
     cudaFree(m->d_feat_used);
@@ -538,42 +540,90 @@ extern "C" int idash_b200_model_free(idash_b200_model *m) {
     return IDASH_B200_OK;
 }
 
+extern "C" int idash_b200_model_upload_layout(idash_b200_ctx *c, idash_b200_layout *L, idash_b200_model **out) {
+    clear_error();
+    if (!c || !L || !out) { idash_b200_layout_free(L); return set_error(IDASH_B200_ERR_INVALID, "model_upload_layout: null argument"); }
+    *out = nullptr;
+    idash_b200_model *m = new (std::nothrow) idash_b200_model();
+    if (!m) { idash_b200_layout_free(L); return set_error(IDASH_B200_ERR_NOMEM, "model_upload: out of memory"); }
+    m->layout = L;
+    m->device = c->device;
+    int rc = IDASH_B200_OK;
+    if (cudaSetDevice(c->device) != cudaSuccess) rc = set_error(IDASH_B200_ERR_CUDA, "model_upload: cudaSetDevice(%d) failed", c->device);
+    if (rc ||
+        (rc = upload(&m->d_var_wsum, L->var_wsum.data(), L->var_wsum.size())) ||
+        (rc = upload(&m->d_var_ptr, L->var_ptr.data(), L->var_ptr.size())) ||
+        (rc = upload(&m->d_var_ct, L->var_ct.data(), L->var_ct.size())) ||
+        (rc = upload(&m->d_var_w, L->var_w.data(), L->var_w.size())) ||
+        (rc = upload(&m->d_out_bidx, L->out_bidx.data(), L->out_bidx.size())) ||
+        (!L->groups.empty() && ((rc = upload(&m->d_groups, L->groups.data(), L->groups.size())) ||
+                                (rc = upload(&m->d_entries, L->entries.data(), L->entries.size())))) ||
+        (L->groups_all && ((rc = upload(&m->d_groups_full, L->groups_full.data(), L->groups_full.size())) ||
+                           (rc = upload(&m->d_entries_full, L->entries_full.data(), L->entries_full.size())))) ||
+        (!L->tiles.empty() &&
+         ((rc = upload(&m->d_tiles, L->tiles.data(), L->tiles.size())) ||
+          (rc = upload(&m->d_tile_rows, L->tile_rows.data(), L->tile_rows.size())) ||
+          (rc = upload(&m->d_tile_bias, L->tile_bias.data(), L->tile_bias.size())) ||
+          (rc = upload(&m->d_tile_coef, L->tile_coef.data(), L->tile_coef.size())) ||
+          (rc = upload(&m->d_tile_used, L->tile_used.data(), L->tile_used.size())) ||
+          (L->ring_ok && (rc = upload(&m->d_feat_used, L->feat_used.data(), L->feat_used.size())))))) {
+        idash_b200_model_free(m);
+        return rc;
+    }
+    *out = m;
+    return IDASH_B200_OK;
+}
+
 extern "C" int idash_b200_model_upload(idash_b200_ctx *c, const idash_b200_model_desc *desc, idash_b200_model **out) {
     clear_error();
     if (!c || !desc || !out) return set_error(IDASH_B200_ERR_INVALID, "model_upload: null argument");
     *out = nullptr;
     idash_b200_layout *L = nullptr;
-    int rc = idash_b200_layout_compile(desc, &L);
+    // the IMAD groups of every row are only built when that kernel has been chosen for the whole model (or later, on demand)
+    const uint32_t flags = c->kernel_choice == IDASH_B200_KERNEL_IMAD ? IDASH_B200_COMPILE_GROUPS_ALL : IDASH_B200_COMPILE_DEFAULT;
+    int rc = idash_b200_layout_compile_ex(desc, flags, &L);
     if (rc) return rc;
-    idash_b200_model *m = new (std::nothrow) idash_b200_model();
-    if (!m) { idash_b200_layout_free(L); return set_error(IDASH_B200_ERR_NOMEM, "model_upload: out of memory"); }
-    m->layout = L;
-    m->device = c->device;
-    CUDA_TRY(cudaSetDevice(c->device));
-    std::vector<double> wsum(L->n_rows, 0.);
-    for (uint64_t r = 0; r < L->n_rows; ++r)
-        for (uint64_t e = L->var_ptr[r]; e < L->var_ptr[r + 1]; ++e) wsum[r] += L->var_w[e];
-    if ((rc = upload(&m->d_var_wsum, wsum.data(), wsum.size())) ||
-        (rc = upload(&m->d_groups, L->groups.data(), L->groups.size())) ||
-        (rc = upload(&m->d_entries, L->entries.data(), L->entries.size())) ||
-        (rc = upload(&m->d_var_ptr, L->var_ptr.data(), L->var_ptr.size())) ||
-        (rc = upload(&m->d_var_ct, L->var_ct.data(), L->var_ct.size())) ||
-        (rc = upload(&m->d_var_w, L->var_w.data(), L->var_w.size())) ||
-        (rc = upload(&m->d_out_bidx, L->out_bidx.data(), L->out_bidx.size()))) {
-        idash_b200_model_free(m);
-        return rc;
-    }
-    if (!L->tiles.empty() &&
-        ((rc = upload(&m->d_tiles, L->tiles.data(), L->tiles.size())) ||
-         (rc = upload(&m->d_tile_rows, L->tile_rows.data(), L->tile_rows.size())) ||
-         (rc = upload(&m->d_tile_bias, L->tile_bias.data(), L->tile_bias.size())) ||
-         (rc = upload(&m->d_tile_coef, L->tile_coef.data(), L->tile_coef.size())) ||
-         (rc = upload(&m->d_tile_used, L->tile_used.data(), L->tile_used.size())) ||
-         (L->ring_ok && (rc = upload(&m->d_feat_used, L->feat_used.data(), L->feat_used.size()))))) {
-        idash_b200_model_free(m);
-        return rc;
-    }
-    *out = m;
+    return idash_b200_model_upload_layout(c, L, out);
+}
+
+// IMAD groups of every row on the device (built and uploaded on first use)
+static int ensure_full_groups(const idash_b200_model *m) {
+    if (m->d_groups_full) return IDASH_B200_OK;
+    int rc = idash_b200_layout_ensure_groups_all(m->layout);
+    if (rc) return rc;
+    if ((rc = upload(&m->d_groups_full, m->layout->groups_full.data(), m->layout->groups_full.size()))) return rc;
+    return upload(&m->d_entries_full, m->layout->entries_full.data(), m->layout->entries_full.size());
+}
+
+// The IMAD kernel over a list of groups
+static int launch_imad(idash_b200_ctx *c, const idash_b200_layout *L, const idash_b200_group *d_groups, const idash_b200_entry *d_entries,
+                       uint64_t n_groups, const CtView &in, const CtView &out, const uint32_t *d_slot_of_ct, uint32_t n_ct_slots,
+                       const uint32_t *d_slot_of_row, cudaStream_t st) {
+    if (n_groups == 0) return IDASH_B200_OK;
+    const int mode = (L->NR == 1) ? 0 : (L->shifts_aligned ? 1 : 2);
+    CloudParams p;
+    memset(&p, 0, sizeof(p));
+    p.groups = d_groups;
+    p.entries = d_entries;
+    p.n_groups = (uint32_t) n_groups;
+    p.in = in;
+    p.out = out;
+    p.slot_of_ct = d_slot_of_ct;
+    p.n_ct_slots = n_ct_slots;
+    p.slot_of_row = d_slot_of_row;
+    p.S = L->S;
+    p.RS = L->RS;
+    p.status = c->d_status;
+    // enough CTAs for >= ~8 waves of 8 resident CTAs/SM, at most 16 consecutive groups per CTA
+    uint32_t gpc = 16;
+    while (gpc > 1 && (uint64_t) ((p.n_groups + gpc - 1) / gpc) * 4 < (uint64_t) c->sm_count * 64) gpc >>= 1;
+    p.groups_per_cta = gpc;
+    const unsigned grid = ((p.n_groups + gpc - 1) / gpc) * 4;
+    if (mode == 0) cloud_eval_kernel<0><<<grid, 128, 0, st>>>(p);
+    else if (mode == 1) cloud_eval_kernel<1><<<grid, 128, 0, st>>>(p);
+    else cloud_eval_kernel<2><<<grid, 128, 0, st>>>(p);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
     return IDASH_B200_OK;
 }
 
@@ -660,8 +710,8 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
     const int mode = (L->NR == 1) ? 0 : (L->shifts_aligned ? 1 : 2);
     const bool tc_ok = !L->tiles.empty();
     if (c->kernel_choice >= IDASH_B200_KERNEL_TENSOR && !tc_ok)
-        return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: the tensor-core kernel was requested but the model is not eligible "
-                                                 "(a coefficient outside int16 or a band wider than %u features)", IDASH_B200_TILE_KMAX);
+        return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: the tensor-core kernel was requested but no row of the model is eligible "
+                                                 "(coefficients outside int16 or windows wider than %u features)", IDASH_B200_RING_KMAX);
     if (c->kernel_choice == IDASH_B200_KERNEL_TENSOR_RING && !L->ring_ok)
         return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: the persistent ring kernel was requested but the model is not eligible "
                                                  "(needs forward-moving bands of at most %u features)", IDASH_B200_RING_KMAX);
@@ -669,7 +719,14 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
     if (c->kernel_choice == IDASH_B200_KERNEL_TENSOR_RING && L->ring_ok && !ring_selected(c, L))
         return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: the persistent ring kernel was requested but the model has too many tiles per chunk");
     const bool use_ring = ring_selected(c, L);
-    if (piece && !use_ring) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: internal: partial launches need the ring kernel");
+    if (piece && (!use_ring || L->n_overflow_rows)) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: internal: partial launches need the ring kernel");
+    if (!use_tc && L->n_overflow_rows != L->n_rows) { int rc = ensure_full_groups(m); if (rc) return rc; }
+    // rows no tile holds (an outlier window, a coefficient outside the limb range): the IMAD kernel evaluates them beside the
+    // tensor-core kernel -- queued first, it is a few CTAs that finish while the persistent grid ramps up
+    if (use_tc && L->n_overflow_rows) {
+        int rc = launch_imad(c, L, m->d_groups, m->d_entries, L->groups.size(), in, out, d_slot_of_ct, n_ct_slots, d_slot_of_row, st);
+        if (rc) return rc;
+    }
     // Per-row variance / record headers: independent of the main kernel's words, so it is forked onto its own stream
     // (after the slot table is ready on `st`) and joined at the end -- it hides behind the main kernel.
     if (!c->s_aux) {
@@ -778,27 +835,11 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
         else cloud_tc_kernel<2><<<grid, TC_THREADS, smem, st>>>(p);
         c->last_kernel = IDASH_B200_KERNEL_TENSOR_TILE;
     } else {
-        CloudParams p;
-        memset(&p, 0, sizeof(p));
-        p.groups = m->d_groups;
-        p.entries = m->d_entries;
-        p.n_groups = (uint32_t) L->groups.size();
-        p.in = in;
-        p.out = out;
-        p.slot_of_ct = d_slot_of_ct;
-        p.n_ct_slots = n_ct_slots;
-        p.slot_of_row = d_slot_of_row;
-        p.S = L->S;
-        p.RS = L->RS;
-        p.status = c->d_status;
-        // enough CTAs for >= ~8 waves of 8 resident CTAs/SM, at most 16 consecutive groups per CTA
-        uint32_t gpc = 16;
-        while (gpc > 1 && (uint64_t) ((p.n_groups + gpc - 1) / gpc) * 4 < (uint64_t) c->sm_count * 64) gpc >>= 1;
-        p.groups_per_cta = gpc;
-        const unsigned grid = ((p.n_groups + gpc - 1) / gpc) * 4;
-        if (mode == 0) cloud_eval_kernel<0><<<grid, 128, 0, st>>>(p);
-        else if (mode == 1) cloud_eval_kernel<1><<<grid, 128, 0, st>>>(p);
-        else cloud_eval_kernel<2><<<grid, 128, 0, st>>>(p);
+        const bool all_overflow = L->n_overflow_rows == L->n_rows;
+        int rc = launch_imad(c, L, all_overflow ? m->d_groups : m->d_groups_full, all_overflow ? m->d_entries : m->d_entries_full,
+                             all_overflow ? L->groups.size() : L->groups_full.size(), in, out, d_slot_of_ct, n_ct_slots, d_slot_of_row, st);
+        if (rc) return rc;
+        c->launches--;     // counted below
         c->last_kernel = IDASH_B200_KERNEL_IMAD;
     }
     c->launches++;
@@ -877,7 +918,7 @@ extern "C" int idash_b200_cloud_eval_device_batched(idash_b200_ctx *c, const ida
     const idash_b200_layout *L = m->layout;
     std::vector<CtView> vin(n_batches), vout(n_batches);
     int rc;
-    bool one_launch = n_batches > 1 && n_batches <= RG_MAX_BATCHES && ring_selected(c, L);
+    bool one_launch = n_batches > 1 && n_batches <= RG_MAX_BATCHES && ring_selected(c, L) && L->n_overflow_rows == 0;
     for (uint32_t b = 0; b < n_batches; ++b) {
         if ((rc = make_view(&in[b], false, &vin[b], "cloud_eval_device_batched(in)"))) return rc;
         if ((rc = make_view(&out[b], true, &vout[b], "cloud_eval_device_batched(out)"))) return rc;

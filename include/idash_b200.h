@@ -95,6 +95,9 @@ typedef struct idash_b200_model_info {
     uint64_t n_tiles;         /* band tiles of the tensor-core kernel; 0 = model not eligible (see idash_b200_layout.h) */
     uint32_t tile_kmax;       /* widest tile band (features) */
     uint32_t ring_ok;         /* 1 if the persistent ring variant of the tensor-core kernel applies */
+    uint64_t n_overflow_rows; /* rows no tile holds (evaluated by the IMAD kernel beside the tensor-core kernel) */
+    uint32_t groups_all;      /* 1 if the IMAD groups of every row have been built (n_groups / n_entries then count those) */
+    uint32_t pad;
 } idash_b200_model_info;
 
 typedef struct idash_b200_ctx idash_b200_ctx;
@@ -131,6 +134,10 @@ int idash_b200_host_free(void *ptr);
 /* ---- model: replaces the per-call deep copy of Model (eval/idash.cpp:772) by a one-time compile of
  *      the coefficient maps into a device-resident block-banded layout ---------------------------- */
 int idash_b200_model_upload(idash_b200_ctx *ctx, const idash_b200_model_desc *desc, idash_b200_model **model);
+/* Uploads a layout that was compiled (idash_b200_layout_compile_ex) or loaded from the model cache (idash_b200_layout_load)
+ * beforehand; the model takes ownership of `layout` (also on failure). struct idash_b200_layout is declared in idash_b200_layout.h. */
+struct idash_b200_layout;
+int idash_b200_model_upload_layout(idash_b200_ctx *ctx, struct idash_b200_layout *layout, idash_b200_model **model);
 int idash_b200_model_free(idash_b200_model *model);
 int idash_b200_model_get_info(const idash_b200_model *model, idash_b200_model_info *info);
 

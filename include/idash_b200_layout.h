@@ -78,16 +78,41 @@ typedef struct idash_b200_tile {
     uint32_t K;         /* band width in features, multiple of 32, <= IDASH_B200_TILE_KMAX */
     uint64_t b_off;     /* byte offset of the tile's coefficient image (16-byte aligned) */
     uint32_t used_off;  /* offset (uint32 words) of the K/32-word mask of features with a non-zero coefficient */
-    uint32_t n_valid;   /* rows of the tile that exist (the last tile may be partial) */
+    uint32_t n_valid;   /* row slots of the tile (the last tile may be partial); a slot whose row was evicted holds NO_ROW */
     uint32_t flags;     /* bit 0: full tile whose caller rows are consecutive integers starting at tile_rows[64 t] */
     uint32_t pad;
 } idash_b200_tile;      /* 32 bytes */
 
 typedef struct idash_b200_layout idash_b200_layout;
 
+/* Compiles the model. Every pass is a parallel loop over rows or tiles (IDASH_B200_THREADS host threads, default: all).
+ * A row that no tile can hold -- a coefficient outside [TILE_COEF_MIN, TILE_COEF_MAX], or a window that does not fit into its tile's
+ * band of at most RING_KMAX features -- is EVICTED from its tile (tile_rows = NO_ROW there) and listed in the OVERFLOW groups, which
+ * the IMAD kernel evaluates beside the tensor-core kernel: one outlier window never changes the kernel for the other rows.
+ * flags: IDASH_B200_COMPILE_GROUPS_ALL also builds the IMAD groups of EVERY row (what idash_b200_layout_groups returns and what
+ * forcing IDASH_B200_KERNEL_IMAD needs; built on demand otherwise). idash_b200_layout_compile = compile_ex with that flag. */
+#define IDASH_B200_COMPILE_DEFAULT 0u
+#define IDASH_B200_COMPILE_GROUPS_ALL 1u
+int idash_b200_layout_compile_ex(const idash_b200_model_desc *desc, uint32_t flags, idash_b200_layout **layout);
 int idash_b200_layout_compile(const idash_b200_model_desc *desc, idash_b200_layout **layout);
+int idash_b200_layout_ensure_groups_all(idash_b200_layout *layout);
 int idash_b200_layout_free(idash_b200_layout *layout);
+/* The cached packed model ("models.bin"): the compiled layout as one file, so that a later run skips the 3 G
+ * .hr text files (eval/parse_vw.cpp:8-30, eval/idash.cpp:66-90) and the compile. `key` is the caller's fingerprint of what the model
+ * was compiled from (the host layer hashes params.bin and the model directory listing); load fails with IDASH_B200_ERR_INVALID when
+ * the file is missing, truncated, from another library version or saved under another key. */
+int idash_b200_layout_save(const idash_b200_layout *layout, const char *path, uint64_t key);
+int idash_b200_layout_load(const char *path, uint64_t key, idash_b200_layout **layout);
+/* the model itself as the layout keeps it (per caller row: Constant + entries sorted by input bigIndex) */
+const uint64_t *idash_b200_layout_feat_ptr(const idash_b200_layout *layout);
+const uint32_t *idash_b200_layout_feat_bidx(const idash_b200_layout *layout, uint64_t *n);
+const int32_t *idash_b200_layout_feat_coef(const idash_b200_layout *layout);
+const int32_t *idash_b200_layout_bias(const idash_b200_layout *layout);
+/* IMAD groups of the overflow rows only */
+const idash_b200_group *idash_b200_layout_overflow_groups(const idash_b200_layout *layout, uint64_t *n_groups);
+const idash_b200_entry *idash_b200_layout_overflow_entries(const idash_b200_layout *layout, uint64_t *n_entries);
 int idash_b200_layout_get_info(const idash_b200_layout *layout, idash_b200_model_info *info);
+/* IMAD groups of every row (*n = 0 unless compiled with COMPILE_GROUPS_ALL / after layout_ensure_groups_all) */
 const idash_b200_group *idash_b200_layout_groups(const idash_b200_layout *layout, uint64_t *n_groups);
 const idash_b200_entry *idash_b200_layout_entries(const idash_b200_layout *layout, uint64_t *n_entries);
 /* variance CSR: var_ptr[n_rows+1] (uint64), var_ct[nv] (uint32), var_w[nv] (double) */
@@ -96,9 +121,8 @@ const uint32_t *idash_b200_layout_var_ct(const idash_b200_layout *layout, uint64
 const double *idash_b200_layout_var_w(const idash_b200_layout *layout);
 /* output bigIndex per caller row (copy of desc->out_bidx) */
 const uint32_t *idash_b200_layout_out_bidx(const idash_b200_layout *layout);
-/* band tiles. *n_tiles = 0 when the model is not eligible for the tensor-core kernel (a coefficient outside
- * int16, or a tile whose band is wider than IDASH_B200_TILE_KMAX). tile_rows / tile_bias: [n_tiles * TILE_ROWS]
- * caller row (IDASH_B200_NO_ROW = padding) and Constant of every tile row. */
+/* band tiles. *n_tiles = 0 when no row is eligible for the tensor-core kernels. tile_rows / tile_bias: [n_tiles * TILE_ROWS]
+ * caller row (IDASH_B200_NO_ROW = padding or an evicted row) and Constant of every tile row. */
 const idash_b200_tile *idash_b200_layout_tiles(const idash_b200_layout *layout, uint64_t *n_tiles);
 const uint32_t *idash_b200_layout_tile_rows(const idash_b200_layout *layout);
 const int32_t *idash_b200_layout_tile_bias(const idash_b200_layout *layout);

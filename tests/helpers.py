@@ -29,18 +29,20 @@ def rot(poly: np.ndarray, shift: int) -> np.ndarray:
     return out
 
 
-def interpret_layout(layout, S, RS, in_ct, in_var, slot_of_ct=None):
-    """-> (out_ct [n_rows, 2048] in caller row order, out_var [n_rows])."""
+def interpret_layout(layout, S, RS, in_ct, in_var, slot_of_ct=None, overflow=False):
+    """-> (out_ct [n_rows, 2048] in caller row order, out_var [n_rows]). overflow=True: the groups of the rows no tile holds
+    only; returns (out_ct, seen [n_rows] bool) instead."""
     n_rows = layout.info["n_rows"]
     out = np.zeros((n_rows, 2048), np.uint32)
     seen = np.zeros(n_rows, bool)
-    for G in layout.groups:
+    entries = layout.overflow_entries if overflow else layout.entries
+    for G in (layout.overflow_groups if overflow else layout.groups):
         acc = np.zeros((6, 2048), np.uint32)
         e = int(G["entry_begin"])
         for cls, cnt in ((0, int(G["n_a"])), (1, int(G["n_ab"])), (2, int(G["n_b"]))):
             rows = {0: (0, 1, 2), 1: (0, 1, 2, 3, 4, 5), 2: (3, 4, 5)}[cls]
             for _ in range(cnt):
-                E = layout.entries[e]
+                E = entries[e]
                 e += 1
                 ct = int(E["ct"])
                 slot = ct if slot_of_ct is None else slot_of_ct[ct]
@@ -62,6 +64,8 @@ def interpret_layout(layout, S, RS, in_ct, in_var, slot_of_ct=None):
             assert not seen[row]
             seen[row] = True
             out[row] = v
+    if overflow:
+        return out, seen
     assert seen.all()
     var = np.zeros(n_rows)
     for r in range(n_rows):
@@ -72,7 +76,7 @@ def interpret_layout(layout, S, RS, in_ct, in_var, slot_of_ct=None):
     return out, var
 
 
-def interpret_tiles(layout, S, NR, RS, in_ct, slot_of_ct=None):
+def interpret_tiles(layout, S, NR, RS, in_ct, slot_of_ct=None, partial=False):
     """Executes the band-tile layout the way cloud_tc_kernel is specified to (include/idash_b200_layout.h):
     u8 limb planes of the rotated inputs times the (c_lo u8, c_hi s8) coefficient images, four int32
     accumulators P_w recombined with shifts. -> out_ct [n_rows, 2048] in caller row order."""
@@ -109,7 +113,8 @@ def interpret_tiles(layout, S, NR, RS, in_ct, slot_of_ct=None):
         for n in range(TN):
             row = int(layout.tile_rows[t * TN + n])
             if row == NO_ROW:
-                assert n >= int(T["n_valid"])
+                assert partial or n >= int(T["n_valid"])
+                assert not img[:, :, :, n, :].any(), "a hole of a tile carries coefficients"
                 continue
             v = acc[n].copy()
             v[N:N + S] += np.uint32((int(layout.tile_bias[t * TN + n]) * ONE_IN_T32) & 0xFFFFFFFF)
@@ -117,6 +122,8 @@ def interpret_tiles(layout, S, NR, RS, in_ct, slot_of_ct=None):
             assert not seen[row]
             seen[row] = True
             out[row] = v
+    if partial:
+        return out, seen
     assert seen.all()
     return out
 

@@ -170,6 +170,46 @@ def test_cloud_int32_range_coefficients_wrap(gpu_ctx):
     m.free()
 
 
+def test_cloud_outlier_window_does_not_change_the_kernel(gpu_ctx):
+    """Per-tile eligibility: one 400-feature-wide window (a tile band holds 224) and one coefficient outside int16 in an otherwise
+    neighbors = 5 model. The two rows go to the IMAD kernel (overflow groups), the other 3 790-odd rows stay on the persistent
+    ring kernel, and every output word still equals the oracle -- through the device entry point, the host entry point with
+    scattered output slots, and a batched call (which falls back to one launch per set when there are overflow rows)."""
+    import torch
+    S = 1004
+    geo, model, cts, var = make_case(S, T=900, G=4000, n=5, seed=23)
+    rp, col, coef = model.row_ptr.astype(np.int64), model.col.copy(), model.coef.copy()
+    wide, big = 5000, 9001
+    a, b = int(rp[wide]), int(rp[wide + 1])
+    real = np.nonzero(col[a:b] != 0xFFFFFFFF)[0]
+    col[a + real[-1]] = col[a + real[0]] + 399
+    a, b = int(rp[big]), int(rp[big + 1])
+    real = np.nonzero(col[a:b] != 0xFFFFFFFF)[0]
+    coef[a + real[0]] = -70000
+    gpu_ctx.set_kernel(_lib.KERNEL_AUTO)
+    m = api.Model(gpu_ctx, S, 1, 1024, model.out_bidx, model.row_ptr, col, coef)
+    assert m.info["n_overflow_rows"] == 2 and m.info["ring_ok"] == 1 and m.info["n_tiles"] == (model.n_out + 63) // 64
+    ref_out, ref_var = po.cloud_port(S, 1, 1024, np.arange(len(cts), dtype=np.uint32), cts, var, model.row_ptr, col, coef)
+    out, idx, ovar = api.cloud_compute_score(gpu_ctx, m, cts, in_var=var)
+    assert gpu_ctx.last_kernel() == _lib.KERNEL_TENSOR_RING
+    assert np.array_equal(out, ref_out) and np.array_equal(ovar, ref_var) and np.array_equal(idx, model.out_bidx)
+    slot_of_row = np.random.default_rng(1).permutation(model.n_out).astype(np.uint32)
+    out2, _, ovar2 = api.cloud_compute_score(gpu_ctx, m, cts, in_var=var, slot_of_row=slot_of_row)
+    assert np.array_equal(out2[slot_of_row], ref_out) and np.array_equal(ovar2[slot_of_row], ref_var)
+    x = torch.from_numpy(cts.view(np.int32)).cuda()
+    outs = [torch.zeros((model.n_out, 2048), dtype=torch.int32, device="cuda") for _ in range(2)]
+    api.cloud_compute_score_device_batched(gpu_ctx, m, [x, x], outs)
+    torch.cuda.synchronize()
+    gpu_ctx.check_device_status()
+    assert np.array_equal(outs[1].cpu().numpy().view(np.uint32), ref_out) and torch.equal(outs[0], outs[1])
+    # forcing the IMAD kernel for the whole model builds the full group layout on demand
+    gpu_ctx.set_kernel(_lib.KERNEL_IMAD)
+    out3, _, _ = api.cloud_compute_score(gpu_ctx, m, cts, in_var=var)
+    assert gpu_ctx.last_kernel() == _lib.KERNEL_IMAD and np.array_equal(out3, ref_out)
+    gpu_ctx.set_kernel(_lib.KERNEL_AUTO)
+    m.free()
+
+
 def test_cloud_auto_picks_tensor_kernel_for_idash_models(gpu_ctx):
     geo, model, cts, var = make_case(1004, T=60, G=101, n=5, seed=2)
     m = api.Model(gpu_ctx, 1004, 1, 1024, model.out_bidx, model.row_ptr, model.col, model.coef)

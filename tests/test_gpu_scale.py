@@ -96,6 +96,43 @@ def test_cloud_full_size_every_word_equals_the_reference(gpu_ctx, S, n):
     m.free()
 
 
+def test_cloud_eight_batches_wide_band_one_launch_full_size(gpu_ctx):
+    """Eight sample batches of the full neighbors = 50 model in one call (3 792 x 8 virtual tiles: a 13.5 KB per-CTA header table
+    beside 28 KB coefficient images -- the shape whose shared-memory budget used to end in an internal error): the ring plan
+    trades input-ring slots for room, the call succeeds, equals single launches, and a sample of rows equals the oracle."""
+    import torch
+    S, n = 1004, 50
+    tag, tgt = synth.make_positions(T_FULL, G_FULL, SEED)
+    model = synth.make_model(tag, tgt, n, SEED)
+    n_in = synth.Geometry(S, T_FULL, G_FULL).n_in_ct_used
+    gpu_ctx.set_kernel(_lib.KERNEL_AUTO)
+    m = api.Model(gpu_ctx, S, 1, 1024, model.out_bidx, model.row_ptr, model.col, model.coef)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    ins = [torch.randint(-2 ** 31, 2 ** 31, (n_in, 2048), dtype=torch.int32, device="cuda", generator=g) for _ in range(8)]
+    outs = [torch.zeros((model.n_out, 2048), dtype=torch.int32, device="cuda") for _ in range(8)]
+    api.cloud_compute_score_device_batched(gpu_ctx, m, ins, outs)
+    torch.cuda.synchronize()
+    gpu_ctx.check_device_status()
+    assert gpu_ctx.last_kernel() == _lib.KERNEL_TENSOR_RING
+    single = torch.zeros_like(outs[0])
+    for b in (0, 7):
+        api.cloud_compute_score_device(gpu_ctx, m, ins[b], single)
+        torch.cuda.synchronize()
+        assert torch.equal(single, outs[b]), b
+    rows = np.sort(np.random.default_rng(0).choice(model.n_out, 96, replace=False))
+    rp, col, coef = [0], [], []
+    for r in rows:
+        a, b = int(model.row_ptr[r]), int(model.row_ptr[r + 1])
+        col.extend(model.col[a:b]); coef.extend(model.coef[a:b]); rp.append(len(col))
+    xin = ins[3].cpu().numpy().view(np.uint32)
+    ref_out, _ = po.cloud_port(S, 1, 1024, np.arange(n_in, dtype=np.uint32), xin, np.full(n_in, ALPHA2),
+                               np.array(rp, np.uint64), np.array(col, np.uint32), np.array(coef, np.int32))
+    assert np.array_equal(outs[3][torch.from_numpy(rows).cuda()].cpu().numpy().view(np.uint32), ref_out)
+    m.free()
+    del ins, outs, single
+    torch.cuda.empty_cache()
+
+
 def _fmt_rows(path):
     rows = Path(path).read_text().splitlines()
     assert rows[0] == "Subject ID,target SNP,0,1,2"

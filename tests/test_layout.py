@@ -66,22 +66,105 @@ def test_tile_interpreter_matches_oracle(built_lib, S, n, cr):
         assert T["K"] % 32 == 0 and 32 <= T["K"] <= _lib.TILE_KMAX and T["b_off"] % 16 == 0
 
 
-def test_tiles_absent_when_model_not_eligible(built_lib):
+def _with_outliers(model, wide_row, big_row, wide_span=400):
+    """The CSR of `model` with row `wide_row` stretched to a window of `wide_span` features and one coefficient of row `big_row`
+    outside the limb range of the tensor-core kernels."""
+    rp, col, coef = model.row_ptr.astype(np.int64), model.col.copy(), model.coef.copy()
+    a, b = int(rp[wide_row]), int(rp[wide_row + 1])
+    real = np.nonzero(col[a:b] != 0xFFFFFFFF)[0]
+    col[a + real[-1]] = col[a + real[0]] + wide_span - 1          # entries stay distinct: the last one moves far to the right
+    coef[a + real[-1]] = 77
+    a, b = int(rp[big_row]), int(rp[big_row + 1])
+    real = np.nonzero(col[a:b] != 0xFFFFFFFF)[0]
+    coef[a + real[1]] = 40000
+    return col, coef
+
+
+def test_outlier_rows_are_evicted_and_the_rest_keeps_its_tiles(built_lib):
+    """Per-tile eligibility: one window of 400 features (a tile band holds at most 224) and one coefficient outside int16 send TWO
+    rows to the overflow groups (IMAD kernel); every other row stays on its band tile and the model stays eligible for the
+    persistent ring kernel. Tiles + overflow groups, interpreted, cover every row exactly once and equal the oracle."""
+    S = 1004
+    geo, model, cts, var = make_case(S, T=300, G=400, n=5, seed=19)
+    col, coef = _with_outliers(model, wide_row=301, big_row=700)
+    cts = synth.random_ciphertexts(int(col[col != 0xFFFFFFFF].max()) + 1, 19)
+    var = np.full(len(cts), ALPHA2)
+    lay = api.compile_layout(S, 1, 1024, model.out_bidx, model.row_ptr, col, coef, flags=_lib.COMPILE_DEFAULT)
+    info = lay.info
+    assert info["n_overflow_rows"] == 2 and info["ring_ok"] == 1 and info["n_tiles"] == (model.n_out + 63) // 64
+    assert info["tile_kmax"] <= _lib.RING_KMAX and info["groups_all"] == 0 and len(lay.groups) == 0
+    assert sorted(int(r) for G in lay.overflow_groups for r in G["row"] if r != _lib.NO_ROW) == [301, 700]
+    ref_out, ref_var = po.cloud_port(S, 1, 1024, np.arange(len(cts), dtype=np.uint32), cts, var, model.row_ptr, col, coef)
+    t_out, t_seen = interpret_tiles(lay, S, 1, 1024, cts, partial=True)
+    o_out, o_seen = interpret_layout(lay, S, 1024, cts, var, overflow=True)
+    assert not (t_seen & o_seen).any() and (t_seen | o_seen).all() and o_seen.sum() == 2
+    assert np.array_equal(np.where(t_seen[:, None], t_out, o_out), ref_out)
+    # tiles with a hole are not "fast" (consecutive caller rows)
+    holes = {301 // 64, 700 // 64}
+    for t, T in enumerate(lay.tiles):
+        assert (int(T["flags"]) & 1) == (0 if t in holes or t == len(lay.tiles) - 1 and model.n_out % 64 else 1)
+    # the full IMAD layout on request still covers everything
+    full = api.compile_layout(S, 1, 1024, model.out_bidx, model.row_ptr, col, coef)
+    out, ovar = interpret_layout(full, S, 1024, cts, var)
+    assert np.array_equal(out, ref_out) and np.array_equal(ovar, ref_var) and full.info["groups_all"] == 1
+
+
+def test_tiles_absent_only_when_no_row_is_eligible(built_lib):
     geo, model, cts, var = make_case(1004, T=20, G=30, n=5, seed=3)
     coef = model.coef.copy()
-    coef[5] = 40000                                                   # outside int16
+    coef[5] = 40000                                                   # outside int16: that row only
     lay = api.compile_layout(1004, 1, 1024, model.out_bidx, model.row_ptr, model.col, coef)
-    assert lay.info["n_tiles"] == 0 and len(lay.tiles) == 0 and lay.info["n_groups"] > 0
-    lay = api.compile_layout(1004, 1, 1024, model.out_bidx, model.row_ptr, model.col, model.coef)
-    assert lay.info["n_tiles"] > 0
-    # a band wider than TILE_KMAX features
+    assert lay.info["n_tiles"] == 2 and lay.info["n_overflow_rows"] == 1
+    big = np.where(model.col == 0xFFFFFFFF, model.coef, 40000).astype(np.int32)          # every row
+    lay = api.compile_layout(1004, 1, 1024, model.out_bidx, model.row_ptr, model.col, big)
+    assert lay.info["n_tiles"] == 0 and len(lay.tiles) == 0 and lay.info["n_groups"] > 0 and lay.info["n_overflow_rows"] == model.n_out
+    # a window wider than a tile band
     ob = np.array([0], np.uint32)
     lay = api.compile_layout(1004, 1, 1024, ob, np.array([0, 2], np.uint64), np.array([0, 300], np.uint32),
                              np.array([1, 1], np.int32))
-    assert lay.info["n_tiles"] == 0
-    lay = api.compile_layout(1004, 1, 1024, ob, np.array([0, 2], np.uint64), np.array([0, 255], np.uint32),
+    assert lay.info["n_tiles"] == 0 and lay.info["n_overflow_rows"] == 1
+    lay = api.compile_layout(1004, 1, 1024, ob, np.array([0, 2], np.uint64), np.array([0, 223], np.uint32),
                              np.array([1, -1], np.int32))
-    assert lay.info["n_tiles"] == 1 and lay.info["tile_kmax"] == 256
+    assert lay.info["n_tiles"] == 1 and lay.info["tile_kmax"] == 224 and lay.info["n_overflow_rows"] == 0
+
+
+def test_layout_cache_roundtrip_and_thread_count_independence(built_lib, tmp_path, monkeypatch):
+    """models.bin: save + load reproduces every array; a wrong key, a truncated file or a missing file is refused. The compiler's
+    parallel passes give the same layout whatever the thread count."""
+    S = 335
+    geo, model, cts, var = make_case(S, T=200, G=700, n=20, seed=5, coef_range=8191)
+    f = tmp_path / "models.bin"
+    monkeypatch.setenv("IDASH_B200_THREADS", "1")
+    a = api.compile_layout(S, geo.NR, geo.RS, model.out_bidx, model.row_ptr, model.col, model.coef, save_to=f, key=0xABCDEF)
+    monkeypatch.setenv("IDASH_B200_THREADS", "7")
+    b = api.compile_layout(S, geo.NR, geo.RS, model.out_bidx, model.row_ptr, model.col, model.coef)
+    c = api.load_layout(f, 0xABCDEF)
+    for other in (b, c):
+        assert other.info == a.info
+        for name in ("groups", "entries", "var_ptr", "var_ct", "var_w", "out_bidx", "tiles", "tile_rows", "tile_bias", "tile_coef",
+                     "tile_used", "overflow_groups", "overflow_entries", "feat_ptr", "feat_bidx", "feat_coef", "bias"):
+            x, y = getattr(a, name), getattr(other, name)
+            assert x.dtype == y.dtype and x.tobytes() == y.tobytes(), name
+    with pytest.raises(api.IdashB200Error):
+        api.load_layout(f, 0xABCDEE)
+    with pytest.raises(api.IdashB200Error):
+        api.load_layout(tmp_path / "nope.bin", 0xABCDEF)
+    raw = f.read_bytes()
+    (tmp_path / "short.bin").write_bytes(raw[:-100])
+    with pytest.raises(api.IdashB200Error):
+        api.load_layout(tmp_path / "short.bin", 0xABCDEF)
+
+
+def test_variance_terms_keep_the_callers_entry_order(built_lib):
+    """tLweAddMulTo adds coef^2 * var_in in the order the row's map is walked (eval/idash.cpp:800-817): the variance CSR keeps the
+    caller's order, so non-uniform input variances give the same double as that walk."""
+    ob = np.array([0], np.uint32)
+    rp = np.array([0, 4], np.uint64)
+    col = np.array([9, 0xFFFFFFFF, 3, 6], np.uint32)
+    coef = np.array([3, 5, -7, 2], np.int32)
+    lay = api.compile_layout(1004, 1, 1024, ob, rp, col, coef)
+    assert lay.var_ct.tolist() == [9, 3, 6] and lay.var_w.tolist() == [9.0, 49.0, 4.0]
+    assert lay.feat_bidx.tolist() == [3, 6, 9] and lay.feat_coef.tolist() == [-7, 2, 3] and lay.bias.tolist() == [5]
 
 
 def test_layout_band_is_compact_at_idash_shape(built_lib):
