@@ -4,12 +4,16 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1]): iDASH-scale synthetic, 1004 samples x 16184 tag SNPs x 80882 target
+Workload at N = 1 (BASELINE.json configs[1]): iDASH-scale synthetic, 1004 samples x 16184 tag SNPs x 80882 target
 SNPs, neighbors = 5: 48 552 input TRLWE ciphertexts -> 242 646 output ciphertexts per batch of 1004
-samples. One step = one pass of cloud_compute_score over the batch(es). With N GPUs the job is N batches
-(N x 1004 samples, BASELINE configs[4] shape) sharded by contiguous target-SNP range: rank r evaluates
-targets [G r/N, G (r+1)/N) of every batch from the tag-ciphertext slab its band touches; no collective is
-on the data path (weak scaling: per-GPU work is constant).
+samples. One step = one pass of cloud_compute_score over the batch(es). With N > 1 GPUs the job is BASELINE
+configs[4] as written: N batches of 1004 samples (8032 samples at N = 8), neighbors = 20, sharded by contiguous
+target-SNP range: rank r evaluates targets [G r/N, G (r+1)/N) of every batch from the tag-ciphertext slab its
+band touches; no collective is on the data path (weak scaling: per-GPU work is constant).
+
+PARITY GATE: before a value is printed, the reference's own cloud_compute_score (oracle/_ref)
+is run on the SAME ciphertext words the GPU was given and every output word and variance is compared; the line
+carries "parity": {"checked_words": N, "equal": true} and the run fails without printing a value otherwise.
 
 metric = samples x targets x 3 per second (packed imputed slots/s); `out_ct_per_s` is the same in output
 ciphertexts. `value` is timed with the inputs resident in HBM; `e2e` goes through the host-buffer C-ABI
@@ -47,19 +51,24 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--neighbors", type=int, default=NEIGHBORS)
+    ap.add_argument("--neighbors", type=int, default=0, help="default: 5 at --gpus 1 (configs[1]), 20 at --gpus > 1 (configs[4])")
     ap.add_argument("--targets", type=int, default=G, help="(debug) fewer target SNPs")
     ap.add_argument("--tags", type=int, default=T)
     ap.add_argument("--samples", type=int, default=S)
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the extra timing runs of the CPU baseline (the parity run still happens)")
+    ap.add_argument("--no-parity", action="store_true", help="(debug / profiler runs) skip the parity gate; the line says so")
+    ap.add_argument("--sustain", type=float, default=2.0, help="seconds of back-to-back steps for the `sustained` record (0 = skip)")
     ap.add_argument("--no-decrypt", action="store_true", help="skip the secondary decrypt-kernel timing")
     ap.add_argument("--batches", type=int, default=0, help="(debug) batches per step; default = number of GPUs")
     ap.add_argument("--no-batched", action="store_true", help="N > 1: one launch per batch instead of one batched launch per step")
     ap.add_argument("--kernel", default="auto", choices=["auto", "imad", "tensor", "tile", "ring"],
                     help="cloud kernel: auto (tensor-core when the model is eligible), imad, tensor (ring if eligible, "
                          "else tile), tile (one CTA per tile), ring (persistent)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.neighbors <= 0:
+        a.neighbors = NEIGHBORS if a.gpus == 1 else 20
+    return a
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -152,6 +161,57 @@ def ncu_traffic(kernel: str, args, world: int):
         return None
 
 
+def workload_name(args, world=1, n_batches=1):
+    base = f"iDASH-scale synthetic {args.samples} samples x {args.tags} tag x {args.targets} target SNPs, neighbors={args.neighbors}"
+    if world > 1:
+        return (f"{base} x {n_batches} sample batches = {n_batches * args.samples} samples (BASELINE configs[4]), sharded by "
+                f"target range over {world} GPUs")
+    return base + " (BASELINE configs[1])"
+
+
+def reference_full(args, sub, cts, var, NR, RS, threads, want_output):
+    """The reference's cloud_compute_score (oracle/_ref; the C restatement where it is absent) on a whole (sub-)model.
+    -> (out_ct, out_var, seconds, kind)"""
+    from oracle import pyoracle as po
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    idx = np.arange(len(cts), dtype=np.uint32)
+    if po.have_ref():
+        o, v, t = po.cloud_ref(args.samples, NR, RS, idx, cts, var, sub.out_bidx, sub.row_ptr, sub.col, sub.coef, want_output=want_output)
+        return o, v, t, "reference"
+    t0 = time.perf_counter()
+    o, v = po.cloud_port(args.samples, NR, RS, idx, cts, var, sub.row_ptr, sub.col, sub.coef, threads=threads)
+    return o, v, time.perf_counter() - t0, "port"
+
+
+def parity_gate(args, api, ctx, m, sub, x0, NR, RS, world):
+    """Every output word + variance + index of one evaluation on this rank's inputs x0 (torch CUDA tensor) against the reference on
+    the same words. -> (parity dict, reference seconds, kind, cores)"""
+    import torch
+    from oracle import pyoracle as po
+    n_rows, slab = sub.n_out, x0.shape[0]
+    out = torch.zeros((n_rows, 2048), dtype=torch.int32, device="cuda")
+    ovar = torch.zeros(n_rows, dtype=torch.float64, device="cuda")
+    oidx = torch.zeros(n_rows, dtype=torch.int32, device="cuda")
+    xv = torch.full((slab,), 2.0 ** -50, dtype=torch.float64, device="cuda")
+    api.cloud_compute_score_device(ctx, m, x0, out, in_var=xv, out_index=oidx, out_var=ovar)
+    torch.cuda.synchronize()
+    ctx.check_device_status()
+    cts = x0.cpu().numpy().view(np.uint32)
+    threads = max(1, po.host_threads() // world)
+    ref_out, ref_var, secs, kind = reference_full(args, sub, cts, np.full(slab, 2.0 ** -50), NR, RS, threads, True)
+    bad = 0
+    for lo in range(0, n_rows, 16384):
+        r = torch.from_numpy(ref_out[lo:lo + 16384].view(np.int32)).cuda()
+        bad += int((out[lo:lo + 16384] != r).any(dim=1).sum())
+    var_ok = bool(np.array_equal(ovar.cpu().numpy(), ref_var))
+    idx_ok = bool(np.array_equal(oidx.cpu().numpy().view(np.uint32), sub.out_bidx))
+    par = {"checked_words": int(n_rows) * 2048, "checked_variances": int(n_rows), "differing_ciphertexts": bad,
+           "equal": bool(bad == 0 and var_ok and idx_ok), "against": kind,
+           "how": "reference cloud_compute_score on the same input ciphertext words, all output words + variances + indices compared"}
+    del out, ref_out
+    return par, secs, kind, threads
+
+
 def build_workload(args):
     from idash2019_2_b200 import synth
     tag, tgt = synth.make_positions(args.tags, args.targets, SEED)
@@ -216,12 +276,10 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "out_ct_per_s": 3 * sample * args.steps / total,
-        "config": {"workload": f"iDASH-scale synthetic {args.samples} samples x {args.tags} tag x {args.targets} target SNPs, "
-                               f"neighbors={args.neighbors} (BASELINE configs[1])", "neighbors": args.neighbors,
-                   "l2": "n/a (CPU)"},
+        "config": {"workload": workload_name(args, args.gpus, args.batches or args.gpus), "neighbors": args.neighbors, "l2": "n/a (CPU)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                         "sample": f"first {sample} of {args.targets} target SNPs ({3 * sample} output ciphertexts) per step, "
-                                   f"reference cloud_compute_score 'fhe wall time' with {cores} OpenMP threads"},
+                         "sample": f"first {sample} of {args.targets} target SNPs ({3 * sample} output ciphertexts) of one 1004-sample batch "
+                                   f"per step, reference cloud_compute_score 'fhe wall time' with {cores} OpenMP threads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -229,6 +287,59 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------
+def bench_decrypt(args, api, ctx, out_ct, n_rows, peak):
+    """The decrypt stage (decrypt_predictions, eval/idash.cpp:681-761) on the step's own output ciphertexts: kernel roofline,
+    end to end through the host-buffer entry point, and the reference's decrypt_predictions on a bounded sample."""
+    import torch
+    key = np.random.default_rng(5).integers(0, 2, 1024).astype(np.int32)
+    scores = torch.empty((n_rows, args.samples), dtype=torch.float32, device="cuda")
+    for _ in range(2):
+        api.decrypt_predictions_device(ctx, key, args.samples, out_ct, scores)
+    torch.cuda.synchronize()
+    ctx.timing_enable(10)
+    for _ in range(10):
+        api.decrypt_predictions_device(ctx, key, args.samples, out_ct, scores)
+    torch.cuda.synchronize()
+    d_ms = statistics.mean(ctx.timing_read(10))
+    ctx.timing_enable(0)
+    d_bytes = n_rows * (CT_BYTES + 4 * args.samples)
+    kname = "decrypt_tc_kernel" if ctx.last_decrypt_kernel() == api.DECRYPT_TENSOR else "decrypt_kernel"
+    rec = {"metric": "decrypted output ciphertexts/sec", "value": n_rows / (d_ms * 1e-3), "unit": "ct/s", "ciphertexts": n_rows,
+           "roofline": {"bound": "hbm", "achieved": d_bytes / (d_ms * 1e-3) * 1e-9, "peak": peak, "unit": "GB/s",
+                        "frac": d_bytes / (d_ms * 1e-3) * 1e-9 / peak, "traffic": None, "kernel": kname, "kernel_ms": d_ms,
+                        "algorithmic_bytes": d_bytes, "int8_mac_per_s": n_rows * 4 * 1024 * 1024 / (d_ms * 1e-3)}}
+    # end to end: pinned host ciphertexts in, pinned host scores out
+    try:
+        h_ct = torch.empty((n_rows, 2048), dtype=torch.int32, pin_memory=True)
+        h_ct.copy_(out_ct)
+        h_sc = torch.empty((n_rows, args.samples), dtype=torch.float32, pin_memory=True)
+        np_ct, np_sc = h_ct.numpy().view(np.uint32), h_sc.numpy()
+        api.decrypt_predictions(ctx, key, args.samples, np_ct, out_scores=np_sc)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            api.decrypt_predictions(ctx, key, args.samples, np_ct, out_scores=np_sc)
+        t = (time.perf_counter() - t0) / 2
+        rec["e2e"] = {"value": n_rows / t, "unit": "ct/s", "ms_per_step": t * 1e3, "h2d_bytes_per_step": n_rows * CT_BYTES,
+                      "d2h_bytes_per_step": n_rows * 4 * args.samples,
+                      "matches_device_path": bool(torch.equal(h_sc.cuda(), scores))}
+        # CPU baseline + parity on a bounded sample: the reference's decrypt_predictions (FFT path: +-1 LSB of the phase) and the
+        # exact integer phase of the oracle (bit-exact)
+        from oracle import pyoracle as po
+        n_s = min(n_rows, 3 * 8000)
+        sample = np.ascontiguousarray(np_ct[:n_s])
+        exact = po.decode_port(args.samples, po.phase_exact_port(key, sample))
+        rec["parity"] = {"checked_scores": int(n_s) * args.samples, "equal": bool(np.array_equal(np_sc[:n_s], exact)),
+                         "against": "oracle exact integer phase (TFHE's exact product), decoded as eval/idash.cpp:717-719"}
+        if po.have_ref():
+            ref_sc, secs = po.decrypt_ref(args.samples, key, sample)
+            rec["cpu_baseline"] = {"value": n_s / secs, "unit": "ct/s", "cores": po.host_threads(), "kind": "reference",
+                                   "sample": f"first {n_s} of {n_rows} output ciphertexts, reference decrypt_predictions ('decrypt wall time')",
+                                   "max_abs_score_diff_vs_reference_fft": float(np.abs(ref_sc.astype(np.float64) - np_sc[:n_s]).max())}
+    except Exception as e:  # secondary record: say why a part is missing
+        rec["e2e_error"] = repr(e)
+    return rec
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -267,7 +378,12 @@ def run_b200(args):
     ctx = api.Context(local_rank)
     ctx.set_kernel({"auto": api.KERNEL_AUTO, "imad": api.KERNEL_IMAD, "tensor": api.KERNEL_TENSOR,
                     "tile": api.KERNEL_TENSOR_TILE, "ring": api.KERNEL_TENSOR_RING}[args.kernel])
+    t0 = time.perf_counter()
     m = api.Model(ctx, args.samples, NR, RS, sub.out_bidx, sub.row_ptr, sub.col, sub.coef)
+    m.free()
+    t0 = time.perf_counter()
+    m = api.Model(ctx, args.samples, NR, RS, sub.out_bidx, sub.row_ptr, sub.col, sub.coef)     # warm: allocator and page cache primed
+    model_upload_s = time.perf_counter() - t0
     gen = torch.Generator(device="cuda").manual_seed(SEED + rank)
     ins = [torch.randint(-2 ** 31, 2 ** 31, (slab, 2048), dtype=torch.int32, device="cuda", generator=gen)
            for _ in range(n_batches)]
@@ -328,6 +444,24 @@ def run_b200(args):
     launches = ctx.kernel_launches() - launches0
     kernel_used = ctx.last_kernel()
 
+    # ---- sustained: seconds of back-to-back steps with their own clock samples (does the burst figure survive thermally?)
+    sustained = None
+    if args.sustain > 0:
+        n_sus = max(args.steps, int(args.sustain * 1e3 / max(ms_total / args.steps, 1e-3)))
+        sampler2 = ClockSampler(local_rank) if rank == 0 else None
+        es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        if sampler2:
+            sampler2.start()
+        es0.record()
+        for _ in range(n_sus):
+            step()
+        es1.record()
+        barrier()
+        sus_ms = es0.elapsed_time(es1)
+        sustained = {"steps": n_sus, "seconds": sus_ms * 1e-3, "ms_per_step": sus_ms / n_sus,
+                     "clocks": sampler2.stop() if sampler2 else None}
+
     # ---- end to end through the host-buffer entry point (pinned host memory, H2D + D2H per step)
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
     h_in = torch.empty((slab, 2048), dtype=torch.int32, pin_memory=True)
@@ -347,35 +481,44 @@ def run_b200(args):
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     barrier()
+    # what the host link alone allows: the same device->host bytes as a bare pinned copy, all ranks at the same time
+    eb0, eb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eb0.record()
+    for _b in range(n_batches):
+        h_out.copy_(outs[0], non_blocking=True)
+    eb1.record()
+    torch.cuda.synchronize()
+    bare_d2h_ms = eb0.elapsed_time(eb1)
+    barrier()
     clocks = sampler.stop() if sampler else None
-    same = torch.equal(h_out.cuda(), outs[0])   # host path and device path agree on the same input
+    h_out_host_path = None
+    if True:
+        api.cloud_compute_score(ctx, m, np_in, out_ct=np_out)
+        h_out_host_path = torch.equal(h_out.cuda(), outs[0])   # host path and device path agree on the same input
 
-    # ---- the decrypt stage on the step's own output ciphertexts (secondary: reported beside the headline, not part of it)
+    # ---- parity gate: the reference on the same input words (every rank checks its own shard, batch 0)
+    parity, ref_secs, ref_kind, ref_cores = None, None, None, None
+    if not args.no_parity:
+        parity, ref_secs, ref_kind, ref_cores = parity_gate(args, api, ctx, m, sub, ins[0], NR, RS, world)
+
+    # ---- the decrypt stage on the step's own output ciphertexts (secondary record beside the headline)
     decrypt = None
     if rank == 0 and not args.no_decrypt:
-        key = np.random.default_rng(5).integers(0, 2, 1024).astype(np.int32)
-        scores = torch.empty((n_rows, args.samples), dtype=torch.float32, device="cuda")
-        for _ in range(2):
-            api.decrypt_predictions_device(ctx, key, args.samples, outs[0], scores)
-        torch.cuda.synchronize()
-        ctx.timing_enable(5)
-        for _ in range(5):
-            api.decrypt_predictions_device(ctx, key, args.samples, outs[0], scores)
-        torch.cuda.synchronize()
-        d_ms = statistics.mean(ctx.timing_read(5))
-        ctx.timing_enable(0)
-        d_bytes = n_rows * (CT_BYTES + 4 * args.samples)
-        pk, _ = measured_peak_gbs()
-        decrypt = {"kernel": "decrypt_tc_kernel" if ctx.last_decrypt_kernel() == api.DECRYPT_TENSOR else "decrypt_kernel",
-                   "ciphertexts": n_rows, "kernel_ms": d_ms, "ct_per_s": n_rows / (d_ms * 1e-3), "algorithmic_bytes": d_bytes,
-                   "achieved": d_bytes / (d_ms * 1e-3) * 1e-9, "unit": "GB/s", "frac": d_bytes / (d_ms * 1e-3) * 1e-9 / pk,
-                   "int8_mac_per_s": n_rows * 4 * 1024 * 1024 / (d_ms * 1e-3)}
+        decrypt = bench_decrypt(args, api, ctx, outs[0], n_rows, measured_peak_gbs()[0])
 
-    t = torch.tensor([ms_total, t_e2e * 1e3], dtype=torch.float64, device="cuda")
+    par_ok = 1.0 if (parity is None or parity["equal"]) else 0.0
+    par_words = float(parity["checked_words"]) if parity else 0.0
+    t = torch.tensor([ms_total, t_e2e * 1e3, bare_d2h_ms, sustained["ms_per_step"] if sustained else 0.0], dtype=torch.float64, device="cuda")
+    pt = torch.tensor([par_ok, 1.0 if h_out_host_path else 0.0], dtype=torch.float64, device="cuda")
+    ps = torch.tensor([par_words], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = float(t[0]), float(t[1])
+        dist.all_reduce(pt, op=dist.ReduceOp.MIN)
+        dist.all_reduce(ps, op=dist.ReduceOp.SUM)
+    ms_total, ms_e2e, bare_d2h_ms, sus_ms_step = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+    all_equal, host_same = bool(pt[0] > 0.5), bool(pt[1] > 0.5)
 
+    rc = 0
     if rank == 0:
         slots_per_step = args.samples * args.targets * 3 * n_batches
         ct_per_step = args.targets * 3 * n_batches
@@ -394,49 +537,77 @@ def run_b200(args):
         d2h = n_batches * (n_rows * (CT_BYTES + 4 + 8))
         kernel_name = {api.KERNEL_IMAD: "cloud_eval_kernel", api.KERNEL_TENSOR_TILE: "cloud_tc_kernel",
                        api.KERNEL_TENSOR_RING: "cloud_ring_kernel"}.get(kernel_used, "?")
+        e2e_value = slots_per_step * e2e_steps / (ms_e2e * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "out_ct_per_s": ct_per_step * args.steps / (ms_total * 1e-3),
-            "config": {"workload": f"iDASH-scale synthetic {args.samples} samples x {args.tags} tag x {args.targets} target SNPs, "
-                                   f"neighbors={args.neighbors} (BASELINE configs[1])" +
-                                   (f"; {n_batches} batches sharded by target range over {world} GPUs" if world > 1 else ""),
+            "config": {"workload": workload_name(args, world, n_batches),
                        "neighbors": args.neighbors, "batches": n_batches, "targets_per_gpu": t_hi - t_lo,
                        "in_ct_per_gpu_batch": slab, "out_ct_per_gpu_batch": n_rows,
                        "l2": "inputs+outputs per step (2.4 GB) exceed the 126 MB L2; no explicit flush",
                        "streams": ("batches of a step round-robin on 2 side streams" if side else
                                    f"single stream, one batched launch of {n_batches} batches per step" if batched else "single stream"),
                        "numa_local_cores": numa},
+            "parity": (dict(parity, checked_words=int(ps[0]), equal=all_equal, ranks=world) if parity else
+                       {"skipped": "--no-parity (debug / profiler run): this line is not a benchmark result"}),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(kernel_name, args, world),
                          "kernel": kernel_name, "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes,
                          "peak_source": peak_src, "kernel_share_of_step": k_ms * launches_per_step / (ms_total / args.steps), "how": how},
-            "e2e": {"value": slots_per_step * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
-                    "matches_device_path": bool(same)},
+                    "matches_device_path": host_same,
+                    "excludes": "one-time costs outside the per-step call: model compile + upload (model_upload_ms below, once per model), "
+                                "CUDA context creation, page-locking of the host buffers",
+                    "model_upload_ms": model_upload_s * 1e3,
+                    "value_with_model_upload": slots_per_step / (ms_e2e / e2e_steps * 1e-3 + model_upload_s),
+                    "d2h_gbs_per_gpu": d2h / (ms_e2e / e2e_steps * 1e-3) * 1e-9,
+                    "bare_d2h_ms_per_step": bare_d2h_ms,
+                    "bare_d2h_gbs_per_gpu": d2h / (bare_d2h_ms * 1e-3) * 1e-9,
+                    "limiter": "device->host copy of the output ciphertexts over the GPU's host link: a bare pinned copy of the same bytes "
+                               "(all ranks at once) takes bare_d2h_ms_per_step"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if sustained:
+            sustained["ms_per_step"] = sus_ms_step
+            sustained["value"] = slots_per_step / (sus_ms_step * 1e-3)
+            sustained["frac"] = (CT_BYTES * (slab + n_rows) * n_batches / (sus_ms_step * 1e-3) * 1e-9) / peak
+            sustained["vs_burst"] = (ms_total / args.steps) / sus_ms_step
+            line["sustained"] = sustained
         if decrypt:
             line["decrypt"] = decrypt
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and parity is not None:
             try:
-                run, kind, cores = reference_sample_runner(args, model)
-                sample = pick_sample(run, args.targets, budget_s=3.0)
-                tt = min(run(sample) for _ in range(2))
-                line["cpu_baseline"] = {"value": args.samples * sample * 3 / tt, "unit": UNIT, "cores": cores, "kind": kind,
-                                        "sample": f"first {sample} of {args.targets} target SNPs ({3 * sample} output "
-                                                  f"ciphertexts), best of 2, cloud_compute_score only ('fhe wall time')",
-                                        "seconds": tt}
+                best = ref_secs
+                if not args.no_cpu_baseline:
+                    cts0 = ins[0].cpu().numpy().view(np.uint32)
+                    v0 = np.full(slab, 2.0 ** -50)
+                    for _ in range(2):
+                        best = min(best, reference_full(args, sub, cts0, v0, NR, RS, ref_cores, False)[2])
+                line["cpu_baseline"] = {"value": args.samples * args.targets * 3 / best, "unit": UNIT, "cores": ref_cores, "kind": ref_kind,
+                                        "sample": f"the whole workload: all {args.targets} target SNPs ({n_rows} output ciphertexts) of one "
+                                                  f"{args.samples}-sample batch, best of {1 if args.no_cpu_baseline else 3} runs, cloud_compute_score "
+                                                  f"only ('fhe wall time'); the first run is the parity gate's",
+                                        "seconds": best}
             except Exception as e:  # the checker is optional for the bench line; say why it is missing
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
+        if parity is not None and not all_equal:
+            # parity is a gate -- no value without it
+            line["value"] = None
+            line["e2e"]["value"] = None
+            line["error"] = "parity gate failed: the CUDA path's output differs from the reference's on the same inputs"
+            rc = 1
         print(json.dumps(line), flush=True)
     m.free()
     ctx.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if rc:
+        raise SystemExit(rc)
 
 
 if __name__ == "__main__":

@@ -82,13 +82,17 @@ EXPORTS = {
     "idash_b200_timing_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "idash_b200_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "idash_b200_host_free": (C.c_int, [C.c_void_p]),
+    "idash_b200_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "idash_b200_host_unregister": (C.c_int, [C.c_void_p]),
     "idash_b200_model_upload": (C.c_int, [C.c_void_p, C.POINTER(ModelDesc), C.POINTER(C.c_void_p)]),
     "idash_b200_model_upload_layout": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "idash_b200_model_clone": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "idash_b200_model_free": (C.c_int, [C.c_void_p]),
     "idash_b200_model_get_info": (C.c_int, [C.c_void_p, C.POINTER(ModelInfo)]),
     "idash_b200_cloud_eval_host": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Cts), C.POINTER(Cts), C.c_void_p]),
     "idash_b200_cloud_eval_device": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Cts), C.POINTER(Cts), C.c_void_p,
                                                C.c_void_p]),
+    "idash_b200_cloud_eval_host_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Cts), C.POINTER(Cts), C.c_uint64, C.c_uint64]),
     "idash_b200_cloud_eval_device_batched": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(Cts), C.POINTER(Cts), C.c_void_p]),
     "idash_b200_check_device_status": (C.c_int, [C.c_void_p]),
     "idash_b200_decrypt_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(Cts), C.c_void_p, C.c_void_p]),

@@ -214,12 +214,18 @@ def cloud_compute_score_device_batched(ctx: Context, model: Model, in_cts, out_c
     L.check(L.lib().idash_b200_cloud_eval_device_batched(ctx.handle, model.handle, n, cin, cout, C.c_void_p(stream)))
 
 
-def decrypt_predictions(ctx: Context, key, S: int, ct: np.ndarray, want_phase: bool = False):
-    """PACKED host path. key [1024] in {0,1}; ct [n, 2048]. Returns scores [n, S] float32 (and phase [n, 1024])."""
+def decrypt_predictions(ctx: Context, key, S: int, ct: np.ndarray, want_phase: bool = False, out_scores: np.ndarray | None = None):
+    """PACKED host path. key [1024] in {0,1}; ct [n, 2048]. Returns scores [n, S] float32 (and phase [n, 1024]). out_scores: a
+    caller-owned (e.g. pinned) C-contiguous float32 [n, S] array to receive the scores."""
     key = np.ascontiguousarray(key, np.int32)
     ct = np.ascontiguousarray(ct, np.uint32).reshape(-1, CT_WORDS)
     n = len(ct)
-    scores = np.empty((n, S), np.float32)
+    if out_scores is not None:
+        if out_scores.dtype != np.float32 or not out_scores.flags.c_contiguous or out_scores.shape != (n, S):
+            raise ValueError("out_scores must be a C-contiguous float32 [n, S] array")
+        scores = out_scores
+    else:
+        scores = np.empty((n, S), np.float32)
     phase = np.empty((n, N), np.uint32) if want_phase else None
     cin = L.Cts(LAYOUT_PACKED, _ptr(ct) if n else None, n, None, None)
     L.check(L.lib().idash_b200_decrypt_host(ctx.handle, _ptr(key), S, C.byref(cin), _ptr(scores), _ptr(phase)))

@@ -41,7 +41,11 @@
 #define RG_MAX_BATCHES 8u
 #define RG_BATCH_SHIFT 14u                       // input blocks per batch < 2^14 (features < 524 288) in a batched launch
 #define RG_SMEM_MAX (226u * 1024u)               // dynamic shared memory budget of the one resident CTA
-#define RG_TUNE_DEFAULT 8u                       // RingParams::tune of the production library
+// Production schedule (measured on B200, profiles/r02_ring_schedule_sweep.txt): warp-converged MMA issue + TMEM stage handed back
+// after the epilogue's last tcgen05.ld (tune 8 | 64) + x16 TMEM loads (EPI 1): 0.470 / 0.507 / 0.602 / 0.537 ms at neighbors 5 / 20 /
+// 50 / NUM_REGIONS = 3, against 0.480 / 0.514 / 0.634 / 0.552 ms without the last two.
+#define RG_TUNE_DEFAULT (8u | 64u)               // RingParams::tune of the production library
+#define RG_EPI_DEFAULT 1                         // ... and its epilogue schedule (template parameter EPI of the kernel)
 
 struct RingParams {
     const idash_b200_tile *tiles;
@@ -77,9 +81,10 @@ struct RingParams {
     uint32_t tune;                 // schedule switches: 1 epilogue waits with try_wait, 2 publisher waits with try_wait, 4 MMA warp polls
                                    // without nanosleep, 8 warp-converged MMA issue (uniform operands), 32 the two MMA warps issue their
                                    // tiles strictly in tile order, 64 the epilogue frees its TMEM stage after its last tcgen05.ld, 128 weight-stationary MMAs (the
-                                   // coefficient chunk of a K step is read from shared memory once, tcgen05.mma.ws + collector buffer)
+                                   // coefficient chunk of a K step is read from shared memory once, tcgen05.mma.ws + collector buffer); host side: 256 / 512 pick
+                                   // the kernel's EPI template parameter (x16 loads / burst epilogue)
     uint32_t knockout;             // profiling aid (IDASH_B200_KNOCKOUT, results are wrong when non-zero):
-                                   // 1 no MMAs, 2 no output stores, 4 no epilogue TMEM loads, 8 no input loads
+                                   // 1 no MMAs, 2 no output stores, 4 no epilogue TMEM loads, 8 no input loads, 16 no zero fill
 };
 
 __host__ __device__ constexpr uint32_t ring_smem_bytes(uint32_t n_slots, uint32_t n_bchunks, uint32_t max_chunk_tiles) {
@@ -243,9 +248,88 @@ __device__ __forceinline__ void ring_ld_chunk(uint32_t taddr, uint32_t (&v0)[8],
 // release_bar: the TMEM stage's t_empty barrier when the stage is to be handed back as soon as the last tcgen05.ld of this warp
 // has completed (the accumulators are in registers then; the recombine + stores of the last group no longer need TMEM), or
 // nullptr when the caller arrives after the whole epilogue. Returns true if it has arrived.
-template <bool FAST, uint32_t STRIDE, bool BIAS, bool MASK = false>
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+
+// One recombined output word -> its row (shared by the two load widths below)
+template <bool FAST, uint32_t STRIDE, bool BIAS, bool MASK>
+__device__ __forceinline__ void ring_emit(uint32_t n, uint32_t x, uint8_t *base_lane, uint64_t ptr_own, uint32_t bias_own, uint32_t bias_flag,
+                                          uint32_t lane_off, uint32_t knockout, uint32_t keep_mask) {
+    if (BIAS) x += __shfl_sync(0xFFFFFFFFu, bias_own, n) * bias_flag;
+    if (MASK) x &= keep_mask;                                                  // b[RS..N) = 0 (idash.cpp:839-841)
+    if (knockout & 2u) { if (x == 0x9E3779B9u && bias_flag == 77u) stg32_stream(base_lane, x); return; }
+    if (FAST) {
+        stg32_stream(base_lane + (uint64_t) n * STRIDE, x);
+    } else {
+        const uint64_t ptr = __shfl_sync(0xFFFFFFFFu, ptr_own, n);
+        if (ptr) stg32_stream(reinterpret_cast<uint8_t *>(ptr) + lane_off, x);
+    }
+}
+
+// Wide-load variant (tune & 256): two groups of 16 rows, each accumulator read with ONE 32x32b.x16 load -- 8 tcgen05.ld per
+// warp and tile instead of 16. TMEM is shared by the epilogue's loads and the accumulator read-modify-writes of the running
+// MMAs (knock-outs: MMAs alone 0.42 ms, TMEM loads + recombine alone 0.41-0.51 ms, together 0.63 ms at neighbors = 50).
+template <bool FAST, uint32_t STRIDE, bool BIAS, bool MASK>
+__device__ __forceinline__ bool ring_epilogue_w16(uint32_t taddr, uint8_t *base_lane, uint64_t ptr_own, uint32_t bias_own, uint32_t bias_flag,
+                                                  uint32_t lane_off, uint32_t knockout, uint32_t keep_mask, uint64_t *release_bar) {
+    if (knockout & 4u) return false;
+    uint32_t v[4][16];
+#pragma unroll
+    for (uint32_t g = 0; g < 2; ++g) {
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) tc_ld16(taddr + g * 16u + j * TC_TN, v[j]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (g == 1 && release_bar) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if ((threadIdx.x & 31u) == 0) mbar_arrive(release_bar);
+        }
+#pragma unroll
+        for (uint32_t c = 0; c < 16; ++c) {
+            const uint32_t x = ((v[3][c] * 256u + v[2][c]) * 256u + v[1][c]) * 256u + v[0][c];
+            ring_emit<FAST, STRIDE, BIAS, MASK>(g * 16u + c, x, base_lane, ptr_own, bias_own, bias_flag, lane_off, knockout, keep_mask);
+        }
+    }
+    return release_bar != nullptr;
+}
+
+// Burst variant (EPI = 2): ALL accumulators of the warp's 32 rows are pulled out of TMEM and recombined first (four rounds of
+// four x8 loads, 32 result registers), the stage is handed back, and only then are the 32 rows stored. The TMEM stage is held for
+// the loads only, not for the stores (~1300-1600 cycles under HBM back-pressure), and the loads -- which slow down concurrently
+// running MMAs by ~1.5x (tools/tmem_ld_rate.cu) -- are over quickly. 32 + 32 data registers.
+template <bool FAST, uint32_t STRIDE, bool BIAS, bool MASK>
+__device__ __forceinline__ bool ring_epilogue_burst(uint32_t taddr, uint8_t *base_lane, uint64_t ptr_own, uint32_t bias_own, uint32_t bias_flag,
+                                                    uint32_t lane_off, uint32_t knockout, uint32_t keep_mask, uint64_t *release_bar) {
+    if (knockout & 4u) return false;
+    uint32_t out[32];
+#pragma unroll
+    for (uint32_t g = 0; g < 4; ++g) {
+        uint32_t v[4][8];
+        ring_ld_chunk(taddr + g * 8u, v[0], v[1], v[2], v[3]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (uint32_t c = 0; c < 8; ++c) out[g * 8u + c] = ((v[3][c] * 256u + v[2][c]) * 256u + v[1][c]) * 256u + v[0][c];
+    }
+    if (release_bar) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if ((threadIdx.x & 31u) == 0) mbar_arrive(release_bar);
+    }
+#pragma unroll
+    for (uint32_t n = 0; n < 32; ++n)
+        ring_emit<FAST, STRIDE, BIAS, MASK>(n, out[n], base_lane, ptr_own, bias_own, bias_flag, lane_off, knockout, keep_mask);
+    return release_bar != nullptr;
+}
+
+template <int EPI, bool FAST, uint32_t STRIDE, bool BIAS, bool MASK = false>
 __device__ __forceinline__ bool ring_epilogue(uint32_t taddr, uint8_t *base_lane, uint64_t ptr_own, uint32_t bias_own, uint32_t bias_flag,
                                               uint32_t lane_off, uint32_t knockout, uint32_t keep_mask, uint64_t *release_bar) {
+    if (EPI == 2) return ring_epilogue_burst<FAST, STRIDE, BIAS, MASK>(taddr, base_lane, ptr_own, bias_own, bias_flag, lane_off, knockout, keep_mask, release_bar);
+    if (EPI == 1) return ring_epilogue_w16<FAST, STRIDE, BIAS, MASK>(taddr, base_lane, ptr_own, bias_own, bias_flag, lane_off, knockout, keep_mask, release_bar);
     if (knockout & 4u) return false;
     uint32_t v[2][4][8];
     ring_ld_chunk(taddr, v[0][0], v[0][1], v[0][2], v[0][3]);
@@ -260,17 +344,8 @@ __device__ __forceinline__ bool ring_epilogue(uint32_t taddr, uint8_t *base_lane
         }
 #pragma unroll
         for (uint32_t c = 0; c < 8; ++c) {
-            const uint32_t n = g * 8u + c;
-            uint32_t x = ((v[g & 1][3][c] * 256u + v[g & 1][2][c]) * 256u + v[g & 1][1][c]) * 256u + v[g & 1][0][c];
-            if (BIAS) x += __shfl_sync(0xFFFFFFFFu, bias_own, n) * bias_flag;
-            if (MASK) x &= keep_mask;                                                  // b[RS..N) = 0 (idash.cpp:839-841)
-            if (knockout & 2u) { if (x == 0x9E3779B9u && bias_flag == 77u) stg32_stream(base_lane, x); continue; }
-            if (FAST) {
-                stg32_stream(base_lane + (uint64_t) n * STRIDE, x);
-            } else {
-                const uint64_t ptr = __shfl_sync(0xFFFFFFFFu, ptr_own, n);
-                if (ptr) stg32_stream(reinterpret_cast<uint8_t *>(ptr) + lane_off, x);
-            }
+            const uint32_t x = ((v[g & 1][3][c] * 256u + v[g & 1][2][c]) * 256u + v[g & 1][1][c]) * 256u + v[g & 1][0][c];
+            ring_emit<FAST, STRIDE, BIAS, MASK>(g * 8u + c, x, base_lane, ptr_own, bias_own, bias_flag, lane_off, knockout, keep_mask);
         }
     }
     return release_bar != nullptr;
@@ -282,7 +357,8 @@ __device__ __forceinline__ void stg128_zero_stream(void *p) {
 
 // ROT = NUM_REGIONS > 1 (rotated loads, masked b tail), BATCHED = several input / output sets in one launch: the plain
 // instantiation carries none of that code (a run-time `batched` flag alone cost the single-set launch 5 %)
-template <bool ROT, bool BATCHED>
+// EPI: epilogue schedule (0 x8 loads double-buffered against the stores, 1 x16 loads, 2 burst: all loads, release the stage, stores)
+template <bool ROT, bool BATCHED, int EPI>
 __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t a_full[RG_MAX_SLOTS], b_full[RG_BBARS], t_full[2], t_empty[2];
@@ -391,21 +467,21 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                 bool arrived;
                 if (fast) {
                     if (records) {
-                        if (is_b) arrived = ring_epilogue<true, IDASH_B200_RECORD_BYTES, true, ROT>(taddr, base_lane, 0, bias_own, bias_flag, lane_off, p.knockout, keep_mask, rel);
-                        else arrived = ring_epilogue<true, IDASH_B200_RECORD_BYTES, false>(taddr, base_lane, 0, 0, 0, lane_off, p.knockout, 0xFFFFFFFFu, rel);
+                        if (is_b) arrived = ring_epilogue<EPI, true, IDASH_B200_RECORD_BYTES, true, ROT>(taddr, base_lane, 0, bias_own, bias_flag, lane_off, p.knockout, keep_mask, rel);
+                        else arrived = ring_epilogue<EPI, true, IDASH_B200_RECORD_BYTES, false>(taddr, base_lane, 0, 0, 0, lane_off, p.knockout, 0xFFFFFFFFu, rel);
                     } else {
-                        if (is_b) arrived = ring_epilogue<true, IDASH_B200_CT_BYTES, true, ROT>(taddr, base_lane, 0, bias_own, bias_flag, lane_off, p.knockout, keep_mask, rel);
-                        else arrived = ring_epilogue<true, IDASH_B200_CT_BYTES, false>(taddr, base_lane, 0, 0, 0, lane_off, p.knockout, 0xFFFFFFFFu, rel);
+                        if (is_b) arrived = ring_epilogue<EPI, true, IDASH_B200_CT_BYTES, true, ROT>(taddr, base_lane, 0, bias_own, bias_flag, lane_off, p.knockout, keep_mask, rel);
+                        else arrived = ring_epilogue<EPI, true, IDASH_B200_CT_BYTES, false>(taddr, base_lane, 0, 0, 0, lane_off, p.knockout, 0xFFFFFFFFu, rel);
                     }
                 } else {
-                    arrived = ring_epilogue<false, 0, true, ROT>(taddr, nullptr, ptr_own, bias_own, bias_flag, lane_off, p.knockout, keep_mask, rel);
+                    arrived = ring_epilogue<EPI, false, 0, true, ROT>(taddr, nullptr, ptr_own, bias_own, bias_flag, lane_off, p.knockout, keep_mask, rel);
                 }
                 if (!arrived) {
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&t_empty[st]);      // one arrival per epilogue warp
                 }
-                if (ROT && zero_units && !(p.knockout & 2u)) {
+                if (ROT && zero_units && !(p.knockout & (2u | 16u))) {
                     // zero fill of b[128 n_slices - 1024 .. 1024) of this tile's rows: unit u = (tile row u / n_zero_seg, segment u % n_zero_seg)
                     const uint32_t row_lane0 = __shfl_sync(0xFFFFFFFFu, row, 0);       // caller row of tile row col_base
                     const uint32_t tt = real_tile(t);
@@ -510,6 +586,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                 uint32_t aslot = __shfl_sync(0xFFFFFFFFu, first_slot, 0);
                 const uint32_t d0 = tmem_u + st * 4u * TC_TN;
                 uint32_t bchunk = __shfl_sync(0xFFFFFFFFu, bpos, 0);
+                if (lane == 0) RG_TRACE(7, it);
                 if (!(p.knockout & 1u)) {
                     if (p.tune & 128u) {
                         for (uint32_t ks = 0; ks < nb_u; ++ks) {
@@ -527,6 +604,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                         if (++bchunk == n_bchunks) bchunk = 0;
                     }
                 }
+                if (lane == 0) RG_TRACE(11, it);
                 if (leader) {
                     if (fifo) progress_publish(&mma_issued_s, it + 1u);
                     tc_commit(&t_full[st]);

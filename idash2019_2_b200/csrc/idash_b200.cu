@@ -190,6 +190,28 @@ __global__ void __launch_bounds__(128) cloud_eval_kernel(const CloudParams p) {
 #include "cloud_tc.cuh"
 #include "cloud_ring.cuh"
 
+// The production library carries one epilogue schedule; the profiling build all of them (IDASH_B200_TUNE bits 256 / 512).
+#ifdef IDASH_B200_PROFILE
+#define RG_EPI_VARIANTS 2
+#else
+#define RG_EPI_VARIANTS 1
+#endif
+typedef void (*ring_kernel_t)(const RingParams);
+template <int EPI>
+static ring_kernel_t ring_kernel_pick(bool rot, bool batched) {
+    return rot ? (batched ? cloud_ring_kernel<true, true, EPI> : cloud_ring_kernel<true, false, EPI>)
+               : (batched ? cloud_ring_kernel<false, true, EPI> : cloud_ring_kernel<false, false, EPI>);
+}
+static ring_kernel_t ring_kernel_fn(bool rot, bool batched, int epi) {
+#ifdef IDASH_B200_PROFILE
+    if (epi == 1) return ring_kernel_pick<1>(rot, batched);
+    return ring_kernel_pick<0>(rot, batched);
+#else
+    (void) epi;
+    return ring_kernel_pick<RG_EPI_DEFAULT>(rot, batched);
+#endif
+}
+
 // Per caller row: output variance, record header / index array.
 struct FinalizeParams {
     uint64_t row_lo;     // rows [row_lo, n_rows) of the model
@@ -429,10 +451,10 @@ extern "C" int idash_b200_init(idash_b200_ctx **out, int device) {
     CUDA_TRY(cudaFuncSetAttribute(decrypt_tc_kernel<IDASH_B200_CT_BYTES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dec_tc_smem_bytes(DT_MAX_SLOTS)));
     CUDA_TRY(cudaFuncSetAttribute(decrypt_tc_kernel<IDASH_B200_RECORD_BYTES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dec_tc_smem_bytes(DT_MAX_SLOTS)));
     CUDA_TRY(cudaFuncSetAttribute(decrypt_tc_kernel<IDASH_B200_RECORD_BYTES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dec_tc_smem_bytes(DT_MAX_SLOTS)));
-    CUDA_TRY(cudaFuncSetAttribute(cloud_ring_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) RG_SMEM_MAX));
-    CUDA_TRY(cudaFuncSetAttribute(cloud_ring_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) RG_SMEM_MAX));
-    CUDA_TRY(cudaFuncSetAttribute(cloud_ring_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) RG_SMEM_MAX));
-    CUDA_TRY(cudaFuncSetAttribute(cloud_ring_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) RG_SMEM_MAX));
+    for (int rot = 0; rot < 2; ++rot)
+        for (int bat = 0; bat < 2; ++bat)
+            for (int epi = 0; epi < RG_EPI_VARIANTS; ++epi)
+                CUDA_TRY(cudaFuncSetAttribute(ring_kernel_fn(rot != 0, bat != 0, epi), cudaFuncAttributeMaxDynamicSharedMemorySize, (int) RG_SMEM_MAX));
     *out = c;
     return IDASH_B200_OK;
 }
@@ -514,6 +536,17 @@ extern "C" int idash_b200_host_alloc(void **ptr, size_t bytes) {
     CUDA_TRY(cudaMallocHost(ptr, bytes ? bytes : 1));
     return IDASH_B200_OK;
 }
+extern "C" int idash_b200_host_register(void *ptr, size_t bytes) {
+    clear_error();
+    if (!ptr || !bytes) return set_error(IDASH_B200_ERR_INVALID, "host_register: null argument");
+    CUDA_TRY(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return IDASH_B200_OK;
+}
+extern "C" int idash_b200_host_unregister(void *ptr) {
+    clear_error();
+    if (ptr) CUDA_TRY(cudaHostUnregister(ptr));
+    return IDASH_B200_OK;
+}
 extern "C" int idash_b200_host_free(void *ptr) {
     clear_error();
     if (ptr) CUDA_TRY(cudaFreeHost(ptr));
@@ -572,6 +605,13 @@ extern "C" int idash_b200_model_upload_layout(idash_b200_ctx *c, idash_b200_layo
     }
     *out = m;
     return IDASH_B200_OK;
+}
+
+extern "C" int idash_b200_model_clone(idash_b200_ctx *c, const idash_b200_model *src, idash_b200_model **out) {
+    clear_error();
+    if (!c || !src || !out) return set_error(IDASH_B200_ERR_INVALID, "model_clone: null argument");
+    src->layout->refs.fetch_add(1);
+    return idash_b200_model_upload_layout(c, src->layout, out);
 }
 
 extern "C" int idash_b200_model_upload(idash_b200_ctx *c, const idash_b200_model_desc *desc, idash_b200_model **out) {
@@ -796,13 +836,11 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
         if (const char *tr = debug_env("IDASH_B200_TRACE")) p.trace_cta = (uint32_t) atoi(tr) + 1u;
         const size_t ring_smem = ring_smem_bytes(p.n_slots, p.n_bchunks, p.max_chunk_tiles);
         const dim3 grid(p.n_slices * p.n_chunks);
-        if (n_batches > 1) {
-            if (L->NR == 1) cloud_ring_kernel<false, true><<<grid, RG_THREADS, ring_smem, st>>>(p);
-            else cloud_ring_kernel<true, true><<<grid, RG_THREADS, ring_smem, st>>>(p);
-        } else {
-            if (L->NR == 1) cloud_ring_kernel<false, false><<<grid, RG_THREADS, ring_smem, st>>>(p);
-            else cloud_ring_kernel<true, false><<<grid, RG_THREADS, ring_smem, st>>>(p);
-        }
+        int epi = RG_EPI_DEFAULT;
+#ifdef IDASH_B200_PROFILE
+        if (debug_env("IDASH_B200_TUNE")) epi = (p.tune & 256u) ? 1 : 0;
+#endif
+        ring_kernel_fn(L->NR != 1, n_batches > 1, epi)<<<grid, RG_THREADS, ring_smem, st>>>(p);
         if (p.trace_cta) {   // debugging only: dump the timeline of the traced CTA to the file named by IDASH_B200_TRACE_FILE
             static unsigned long long h[RG_TRACE_TILES * RG_TRACE_EVENTS];
             CUDA_TRY(cudaStreamSynchronize(st));
@@ -856,6 +894,7 @@ static bool ring_plan(const idash_b200_ctx *c, const idash_b200_layout *L, uint6
     // ceil(RS / 128) slices of b that hold kept words are computed; the CTAs zero-fill the rest. Fewer slices = more chunks = fewer
     // tiles per CTA (NUM_REGIONS = 3: 11 x 13 CTAs instead of 16 x 9).
     rp->n_slices = L->NR == 1 ? 16u : 8u + (L->RS + 127u) / 128u;
+    if (const char *ns = debug_env("IDASH_B200_RING_SLICES")) rp->n_slices = std::max(rp->n_slices, std::min(16u, (uint32_t) atoi(ns)));   // experiments
     if ((uint32_t) c->sm_count < rp->n_slices || n_tiles == 0 || L->tile_kmax == 0) return false;
     rp->n_chunks = (uint32_t) c->sm_count / rp->n_slices;
     const uint64_t chunk_tiles = (n_tiles * n_batches + rp->n_chunks - 1u) / rp->n_chunks + 1u;
@@ -1010,9 +1049,14 @@ static bool rows_identity(const idash_b200_model *m) {
 // range is cut into pieces and the three engines run concurrently -- host->device copy of the input ciphertexts piece k+1
 // needs (copy-in stream), kernels of piece k (compute stream), device->host copy of the outputs of piece k-1 (copy-out
 // stream). PCIe is full duplex, so the input upload disappears behind the (5x larger) output download.
-static int cloud_eval_host_pipelined(idash_b200_ctx *c, const idash_b200_model *m, const idash_b200_cts *in, const idash_b200_cts *out) {
+// [tile_lo, tile_hi): the tiles to evaluate (the whole model, or one GPU's contiguous target range of a multi-GPU evaluation);
+// only their rows of `out` are written, only the input ciphertexts their bands touch are uploaded (PACKED identity inputs), and
+// the device staging buffers are sized for that range.
+static int cloud_eval_host_pipelined(idash_b200_ctx *c, const idash_b200_model *m, const idash_b200_cts *in, const idash_b200_cts *out,
+                                     uint32_t tile_lo, uint32_t tile_hi) {
     const idash_b200_layout *L = m->layout;
-    const uint32_t n_tiles = (uint32_t) L->tiles.size();
+    const uint32_t n_tiles = tile_hi - tile_lo;
+    if (n_tiles == 0) return IDASH_B200_OK;
     const uint32_t P = std::max<uint32_t>(1u, std::min<uint32_t>(8u, n_tiles / 64u));
     if (!c->s_in) { CUDA_TRY(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking)); CUDA_TRY(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking)); }
     while (c->ev_in.size() < P) {
@@ -1023,15 +1067,26 @@ static int cloud_eval_host_pipelined(idash_b200_ctx *c, const idash_b200_model *
     }
     int rc;
     CtView vin, vout;
+    const uint64_t row_lo_all = (uint64_t) tile_lo * IDASH_B200_TILE_ROWS;
+    const uint64_t row_hi_all = std::min<uint64_t>(L->n_rows, (uint64_t) tile_hi * IDASH_B200_TILE_ROWS);
     const bool chunked_in = in->layout == IDASH_B200_LAYOUT_PACKED && !in->index;     // slot i holds ciphertext i
+    uint64_t ct_lo = 0;
     if (!chunked_in) {
         if ((rc = stage_in(c, in, c->in_buf, c->aux_in_idx, c->aux_in_var, &vin, "cloud_eval_host(in)"))) return rc;
     } else {
         if (in->count && !in->data) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_host(in): null data pointer");
+        // ciphertexts the band of [tile_lo, tile_hi) touches: [ct_lo, ct_hi)
+        uint64_t f_lo = UINT64_MAX, f_hi = 0;
+        for (uint32_t t = tile_lo; t < tile_hi; ++t) {
+            f_lo = std::min<uint64_t>(f_lo, L->tiles[t].f_base);
+            f_hi = std::max<uint64_t>(f_hi, (uint64_t) L->tiles[t].f_base + L->tiles[t].K);
+        }
+        ct_lo = std::min<uint64_t>(f_lo / L->NR, in->count);
+        const uint64_t ct_hi = std::min<uint64_t>((f_hi + L->NR - 1) / L->NR, in->count);
         memset(&vin, 0, sizeof(vin));
         vin.count = in->count;
-        if ((rc = c->in_buf.ensure((size_t) in->count * IDASH_B200_CT_BYTES + 16))) return rc;
-        vin.words = (uint8_t *) c->in_buf.p;
+        if ((rc = c->in_buf.ensure((size_t) (ct_hi - ct_lo) * IDASH_B200_CT_BYTES + 16))) return rc;
+        vin.words = (uint8_t *) c->in_buf.p - ct_lo * IDASH_B200_CT_BYTES;      // virtual base: slot ct_lo is the first one resident
         vin.stride = IDASH_B200_CT_BYTES;
         if (in->variance) {
             if ((rc = c->aux_in_var.ensure((size_t) in->count * 8 + 8))) return rc;
@@ -1043,21 +1098,24 @@ static int cloud_eval_host_pipelined(idash_b200_ctx *c, const idash_b200_model *
     vout.count = out->count;
     const bool rec = out->layout == IDASH_B200_LAYOUT_RECORDS;
     const size_t ostride = rec ? IDASH_B200_RECORD_BYTES : IDASH_B200_CT_BYTES;
-    if ((rc = c->out_buf.ensure((size_t) out->count * ostride + 32))) return rc;
+    const uint64_t n_out_rows = row_hi_all - row_lo_all;
+    // device output buffer for the rows of this range only (virtual base like the input's)
+    if ((rc = c->out_buf.ensure((size_t) n_out_rows * ostride + 32))) return rc;
+    uint8_t *const obase = (uint8_t *) c->out_buf.p - row_lo_all * ostride;
     if (rec) {
         if (out->index || out->variance) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_host(out): index/variance must be NULL for the RECORDS layout");
-        vout.words = (uint8_t *) c->out_buf.p + 16; vout.stride = IDASH_B200_RECORD_BYTES; vout.records = 1;
+        vout.words = obase + 16; vout.stride = IDASH_B200_RECORD_BYTES; vout.records = 1;
     } else {
-        vout.words = (uint8_t *) c->out_buf.p; vout.stride = IDASH_B200_CT_BYTES;
-        if (out->index) { if ((rc = c->aux_out_idx.ensure((size_t) out->count * 4 + 4))) return rc; vout.index = (uint32_t *) c->aux_out_idx.p; }
-        if (out->variance) { if ((rc = c->aux_out_var.ensure((size_t) out->count * 8 + 8))) return rc; vout.variance = (double *) c->aux_out_var.p; }
+        vout.words = obase; vout.stride = IDASH_B200_CT_BYTES;
+        if (out->index) { if ((rc = c->aux_out_idx.ensure((size_t) n_out_rows * 4 + 4))) return rc; vout.index = (uint32_t *) c->aux_out_idx.p - row_lo_all; }
+        if (out->variance) { if ((rc = c->aux_out_var.ensure((size_t) n_out_rows * 8 + 8))) return rc; vout.variance = (double *) c->aux_out_var.p - row_lo_all; }
     }
-    uint64_t uploaded = 0, need = 0;
-    uint32_t t_scan = 0;
+    uint64_t uploaded = ct_lo, need = 0;
+    uint32_t t_scan = tile_lo;
     for (uint32_t k = 0; k < P; ++k) {
         Piece pc;
-        pc.tile_lo = (uint32_t) ((uint64_t) n_tiles * k / P);
-        pc.tile_hi = (uint32_t) ((uint64_t) n_tiles * (k + 1) / P);
+        pc.tile_lo = tile_lo + (uint32_t) ((uint64_t) n_tiles * k / P);
+        pc.tile_hi = tile_lo + (uint32_t) ((uint64_t) n_tiles * (k + 1) / P);
         pc.row_lo = (uint64_t) pc.tile_lo * IDASH_B200_TILE_ROWS;
         pc.row_hi = std::min<uint64_t>(L->n_rows, (uint64_t) pc.tile_hi * IDASH_B200_TILE_ROWS);
         pc.first = k == 0;
@@ -1065,7 +1123,7 @@ static int cloud_eval_host_pipelined(idash_b200_ctx *c, const idash_b200_model *
             for (; t_scan < pc.tile_hi; ++t_scan) need = std::max<uint64_t>(need, (uint64_t) L->tiles[t_scan].f_base + L->tiles[t_scan].K);   // features
             const uint64_t upto = std::min<uint64_t>((need + L->NR - 1) / L->NR, in->count);                                            // ciphertexts
             if (upto > uploaded) {
-                CUDA_TRY(cudaMemcpyAsync((uint8_t *) c->in_buf.p + uploaded * IDASH_B200_CT_BYTES, (const uint8_t *) in->data + uploaded * IDASH_B200_CT_BYTES,
+                CUDA_TRY(cudaMemcpyAsync(vin.words + uploaded * IDASH_B200_CT_BYTES, (const uint8_t *) in->data + uploaded * IDASH_B200_CT_BYTES,
                                          (upto - uploaded) * IDASH_B200_CT_BYTES, cudaMemcpyHostToDevice, c->s_in));
                 uploaded = upto;
             }
@@ -1078,17 +1136,17 @@ static int cloud_eval_host_pipelined(idash_b200_ctx *c, const idash_b200_model *
         const uint64_t nr = pc.row_hi - pc.row_lo;
         if (nr) {
             if (rec) {
-                CUDA_TRY(cudaMemcpyAsync((uint8_t *) out->data + pc.row_lo * ostride, (uint8_t *) c->out_buf.p + 8 + pc.row_lo * ostride, nr * ostride, cudaMemcpyDeviceToHost, c->s_out));
+                CUDA_TRY(cudaMemcpyAsync((uint8_t *) out->data + pc.row_lo * ostride, obase + 8 + pc.row_lo * ostride, nr * ostride, cudaMemcpyDeviceToHost, c->s_out));
             } else {
-                CUDA_TRY(cudaMemcpyAsync((uint8_t *) out->data + pc.row_lo * ostride, (uint8_t *) c->out_buf.p + pc.row_lo * ostride, nr * ostride, cudaMemcpyDeviceToHost, c->s_out));
+                CUDA_TRY(cudaMemcpyAsync((uint8_t *) out->data + pc.row_lo * ostride, obase + pc.row_lo * ostride, nr * ostride, cudaMemcpyDeviceToHost, c->s_out));
             }
         }
     }
     // the small per-row arrays go last, in one piece: callers often pass pageable memory for them, and a copy to pageable
     // memory blocks the host thread, which would stop the pieces above from being enqueued ahead of the GPU
-    if (!rec && out->count) {
-        if (out->index) CUDA_TRY(cudaMemcpyAsync(out->index, vout.index, (size_t) out->count * 4, cudaMemcpyDeviceToHost, c->s_out));
-        if (out->variance) CUDA_TRY(cudaMemcpyAsync(out->variance, vout.variance, (size_t) out->count * 8, cudaMemcpyDeviceToHost, c->s_out));
+    if (!rec && n_out_rows) {
+        if (out->index) CUDA_TRY(cudaMemcpyAsync(out->index + row_lo_all, vout.index + row_lo_all, (size_t) n_out_rows * 4, cudaMemcpyDeviceToHost, c->s_out));
+        if (out->variance) CUDA_TRY(cudaMemcpyAsync(out->variance + row_lo_all, vout.variance + row_lo_all, (size_t) n_out_rows * 8, cudaMemcpyDeviceToHost, c->s_out));
     }
     CUDA_TRY(cudaMemcpyAsync(c->h_status, c->d_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -1099,6 +1157,37 @@ static int cloud_eval_host_pipelined(idash_b200_ctx *c, const idash_b200_model *
         return set_error(IDASH_B200_ERR_MISSING_INPUT, "cloud_eval: the model references an input ciphertext that was not supplied");
     }
     return IDASH_B200_OK;
+}
+
+static bool host_pipeline_applies(const idash_b200_ctx *c, const idash_b200_model *m, const idash_b200_cts *in) {
+    const idash_b200_layout *L = m->layout;
+    return in->count < NO_SLOT && ring_selected(c, L) && L->n_overflow_rows == 0 && rows_identity(m);
+}
+
+// One GPU's share of an evaluation that is sharded by contiguous target ranges: rows [row_begin, row_end) of the
+// model, row_begin a multiple of 64 (a tile boundary). `out` describes the WHOLE output array (out->count = model rows); only
+// the rows of the range are written. Needs a model whose caller rows are sorted by output bigIndex and which the ring kernel takes.
+extern "C" int idash_b200_cloud_eval_host_rows(idash_b200_ctx *c, const idash_b200_model *m, const idash_b200_cts *in,
+                                               const idash_b200_cts *out, uint64_t row_begin, uint64_t row_end) {
+    clear_error();
+    if (!c || !m || !in || !out) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_host_rows: null argument");
+    if (m->device != c->device) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_host_rows: model lives on device %d, ctx on %d", m->device, c->device);
+    CUDA_TRY(cudaSetDevice(c->device));
+    const idash_b200_layout *L = m->layout;
+    if (out->count != L->n_rows) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_host_rows: out->count (%llu) != model rows (%llu)",
+                                                  (unsigned long long) out->count, (unsigned long long) L->n_rows);
+    if (row_begin > row_end || row_end > L->n_rows || row_begin % IDASH_B200_TILE_ROWS || (row_end % IDASH_B200_TILE_ROWS && row_end != L->n_rows))
+        return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_host_rows: rows [%llu, %llu) are not a tile-aligned range of the model",
+                         (unsigned long long) row_begin, (unsigned long long) row_end);
+    if (row_begin == row_end) return IDASH_B200_OK;
+    if (out->count && !out->data) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_host_rows: null output data pointer");
+    if (out->layout != IDASH_B200_LAYOUT_PACKED && out->layout != IDASH_B200_LAYOUT_RECORDS)
+        return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_host_rows(out): unknown layout %d", out->layout);
+    if (!host_pipeline_applies(c, m, in))
+        return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_host_rows: needs a model with rows sorted by output bigIndex that the persistent "
+                                                 "ring kernel evaluates whole (no overflow rows)");
+    return cloud_eval_host_pipelined(c, m, in, out, (uint32_t) (row_begin / IDASH_B200_TILE_ROWS),
+                                     (uint32_t) ((row_end + IDASH_B200_TILE_ROWS - 1) / IDASH_B200_TILE_ROWS));
 }
 
 extern "C" int idash_b200_cloud_eval_host(idash_b200_ctx *c, const idash_b200_model *m, const idash_b200_cts *in,
@@ -1113,8 +1202,8 @@ extern "C" int idash_b200_cloud_eval_host(idash_b200_ctx *c, const idash_b200_mo
     if (out->count && !out->data) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_host: null output data pointer");
     if (out->layout != IDASH_B200_LAYOUT_PACKED && out->layout != IDASH_B200_LAYOUT_RECORDS)
         return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_host(out): unknown layout %d", out->layout);
-    if (!slot_of_row && L->tiles.size() >= 128 && in->count < NO_SLOT && ring_selected(c, L) && rows_identity(m) && !getenv("IDASH_B200_NO_PIPELINE"))
-        return cloud_eval_host_pipelined(c, m, in, out);
+    if (!slot_of_row && L->tiles.size() >= 128 && host_pipeline_applies(c, m, in) && !getenv("IDASH_B200_NO_PIPELINE"))
+        return cloud_eval_host_pipelined(c, m, in, out, 0u, (uint32_t) L->tiles.size());
     int rc;
     CtView vin, vout;
     if ((rc = stage_in(c, in, c->in_buf, c->aux_in_idx, c->aux_in_var, &vin, "cloud_eval_host(in)"))) return rc;

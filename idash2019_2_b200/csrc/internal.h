@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <atomic>
 #include <memory>
 #include <utility>
 #include <vector>
@@ -46,6 +47,7 @@ struct default_init_allocator {
 template <class T> using raw_vector = std::vector<T, default_init_allocator<T>>;
 
 struct idash_b200_layout {
+    std::atomic<int> refs{1};         // models on several devices share one layout (idash_b200_model_clone)
     uint32_t S = 0, NR = 0, RS = 0;
     uint64_t n_rows = 0, nnz = 0;
     std::vector<uint32_t> out_bidx;   // per caller row

@@ -513,7 +513,7 @@ extern "C" int idash_b200_layout_ensure_groups_all(idash_b200_layout *L) {
 }
 
 extern "C" int idash_b200_layout_free(idash_b200_layout *layout) {
-    delete layout;
+    if (layout && layout->refs.fetch_sub(1) == 1) delete layout;
     return IDASH_B200_OK;
 }
 

@@ -87,8 +87,13 @@ struct IdashKey {
 };
 
 // model[output bigIndex][input bigIndex or constant_bigIndex()] = integer coefficient (eval/idash.h:129-134)
+struct CompiledModel;   // idash_host.cpp: the block-banded device layout read_model emits
 struct Model {
     std::unordered_map<FeatBigIndex, std::unordered_map<FeatBigIndex, int32_t>> model;
+    // B200: set by read_model -- the model compiled into the device layout (and uploaded), with the order in which the reference
+    // would walk `model`. When present it is what cloud_compute_score evaluates; `model` itself is left EMPTY when read_model took
+    // the layout from the model cache (models.bin) instead of parsing the .hr files. Hand-built / edited models: compiled.reset().
+    std::shared_ptr<CompiledModel> compiled;
 };
 
 // One host allocation holding `count` ciphertext records in file layout, preceded by the u64 count:
@@ -162,6 +167,14 @@ void decrypt_predictions(DecryptedPredictions &predictions, const EncryptedPredi
 
 // GPU used by this process: IDASH_B200_DEVICE, else LOCAL_RANK, else 0.
 int idash_host_device();
+// GPUs cloud_compute_score shards the target range over: IDASH_GPUS="0,1,2,3" (default: the one of idash_host_device()).
+std::vector<int> idash_host_devices();
+// The cached packed model: read_model stores / finds the compiled layout in this file ("" = off). The `cloud` binary
+// turns it on with "models.bin" in the working directory unless IDASH_MODEL_CACHE is set ("0" / "off" disables, else a path).
+void idash_host_set_model_cache(const std::string &path);
+// Blocks until the helper threads read_params / read_model / read_encrypted_data started (CUDA contexts, output slab, page-locking,
+// model upload) are done, so that a stage timer started afterwards measures the evaluation and not process start-up.
+void idash_host_wait_ready();
 // seconds spent inside the C-ABI call of the last cloud_compute_score / decrypt_predictions (for the BENCHMARK block)
 double idash_host_last_gpu_seconds();
 

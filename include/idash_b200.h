@@ -130,6 +130,9 @@ int idash_b200_last_kernel(const idash_b200_ctx *ctx);
 /* pinned host memory for the *_host entry points */
 int idash_b200_host_alloc(void **ptr, size_t bytes);
 int idash_b200_host_free(void *ptr);
+/* page-lock / unlock memory the caller allocated itself (e.g. the slab a ciphertext file was read into) */
+int idash_b200_host_register(void *ptr, size_t bytes);
+int idash_b200_host_unregister(void *ptr);
 
 /* ---- model: replaces the per-call deep copy of Model (eval/idash.cpp:772) by a one-time compile of
  *      the coefficient maps into a device-resident block-banded layout ---------------------------- */
@@ -138,6 +141,9 @@ int idash_b200_model_upload(idash_b200_ctx *ctx, const idash_b200_model_desc *de
  * beforehand; the model takes ownership of `layout` (also on failure). struct idash_b200_layout is declared in idash_b200_layout.h. */
 struct idash_b200_layout;
 int idash_b200_model_upload_layout(idash_b200_ctx *ctx, struct idash_b200_layout *layout, idash_b200_model **model);
+/* The same model on another device (ctx of that device): the compiled layout is shared, only the device arrays are uploaded again.
+ * What a process that shards one evaluation over several GPUs does once per GPU. */
+int idash_b200_model_clone(idash_b200_ctx *ctx, const idash_b200_model *model, idash_b200_model **clone);
 int idash_b200_model_free(idash_b200_model *model);
 int idash_b200_model_get_info(const idash_b200_model *model, idash_b200_model_info *info);
 
@@ -150,6 +156,13 @@ int idash_b200_cloud_eval_host(idash_b200_ctx *ctx, const idash_b200_model *mode
                                const idash_b200_cts *out, const uint32_t *slot_of_row);
 int idash_b200_cloud_eval_device(idash_b200_ctx *ctx, const idash_b200_model *model, const idash_b200_cts *in,
                                  const idash_b200_cts *out, const uint32_t *slot_of_row, void *cuda_stream);
+/* One GPU's share of an evaluation sharded by contiguous target ranges (the loop being cut is eval/idash.cpp:779-790):
+ * model rows [row_begin, row_end), row_begin a multiple of 64 (IDASH_B200_TILE_ROWS) and row_end a multiple of 64 or the model's row
+ * count. `out` describes the WHOLE output array (out->count = model rows, caller rows in output-bigIndex order); only the rows of
+ * the range are written, only the input ciphertexts their windows touch are copied to the device (PACKED inputs in identity
+ * order), and the device staging buffers are sized for the range. One host thread per GPU calls this on its own ctx / model copy. */
+int idash_b200_cloud_eval_host_rows(idash_b200_ctx *ctx, const idash_b200_model *model, const idash_b200_cts *in,
+                                    const idash_b200_cts *out, uint64_t row_begin, uint64_t row_end);
 /* The same model on n_batches input / output sets (in[b] -> out[b], b < n_batches) in one call: what a GPU that owns a target
  * range does for several sample batches (BASELINE configs[4]). When the ring kernel takes the model, all sets are PACKED
  * with inputs in identity order (index == NULL) and have the same sizes, they are evaluated by ONE launch (n_batches <= 8);

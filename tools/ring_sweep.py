@@ -6,7 +6,7 @@ _RING_BCHUNKS / _COEF_PREFETCH, read by the profiling build at each launch) is t
 and its output is compared word for word with the first setting's output (a schedule switch must not change a single bit).
 
 usage: ring_sweep.py [--workloads 1004:5,1004:20,1004:50,335:20] [--settings "8;40;72;104;104,slots=9"] [--steps 20] [--out FILE]
-  a setting is  TUNE[,slots=N][,bchunks=N][,prefetch=N]
+  a setting is  TUNE[,slots=N][,bchunks=N][,prefetch=N][,ko=MASK (knock-out: results are wrong, same_bits is False)][,slices=N]
 """
 import argparse
 import json
@@ -25,7 +25,8 @@ import torch  # noqa: E402
 from idash2019_2_b200 import api, synth  # noqa: E402
 
 T, G, SEED = 16184, 80882, 1234
-ENV = {"slots": "IDASH_B200_RING_SLOTS", "bchunks": "IDASH_B200_RING_BCHUNKS", "prefetch": "IDASH_B200_COEF_PREFETCH"}
+ENV = {"slots": "IDASH_B200_RING_SLOTS", "bchunks": "IDASH_B200_RING_BCHUNKS", "prefetch": "IDASH_B200_COEF_PREFETCH",
+       "ko": "IDASH_B200_KNOCKOUT", "slices": "IDASH_B200_RING_SLICES"}
 
 
 def apply(setting: str):
