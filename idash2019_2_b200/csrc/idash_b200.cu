@@ -1190,6 +1190,26 @@ extern "C" int idash_b200_cloud_eval_host_rows(idash_b200_ctx *c, const idash_b2
                                      (uint32_t) ((row_end + IDASH_B200_TILE_ROWS - 1) / IDASH_B200_TILE_ROWS));
 }
 
+extern "C" int idash_b200_model_input_range(const idash_b200_model *m, uint64_t row_begin, uint64_t row_end, uint32_t *ct_begin, uint32_t *ct_end) {
+    clear_error();
+    if (!m || !ct_begin || !ct_end) return set_error(IDASH_B200_ERR_INVALID, "model_input_range: null argument");
+    const idash_b200_layout *L = m->layout;
+    if (row_begin > row_end || row_end > L->n_rows || row_begin % IDASH_B200_TILE_ROWS || (row_end % IDASH_B200_TILE_ROWS && row_end != L->n_rows))
+        return set_error(IDASH_B200_ERR_INVALID, "model_input_range: rows [%llu, %llu) are not a tile-aligned range of the model",
+                         (unsigned long long) row_begin, (unsigned long long) row_end);
+    if (L->tiles.empty() || L->n_overflow_rows || !rows_identity(m))
+        return set_error(IDASH_B200_ERR_INVALID, "model_input_range: needs a model with rows sorted by output bigIndex and no overflow rows");
+    uint64_t f_lo = UINT64_MAX, f_hi = 0;
+    for (uint64_t t = row_begin / IDASH_B200_TILE_ROWS; t < (row_end + IDASH_B200_TILE_ROWS - 1) / IDASH_B200_TILE_ROWS; ++t) {
+        f_lo = std::min<uint64_t>(f_lo, L->tiles[t].f_base);
+        f_hi = std::max<uint64_t>(f_hi, (uint64_t) L->tiles[t].f_base + L->tiles[t].K);
+    }
+    if (f_lo > f_hi) { *ct_begin = *ct_end = 0; return IDASH_B200_OK; }
+    *ct_begin = (uint32_t) (f_lo / L->NR);
+    *ct_end = (uint32_t) ((f_hi + L->NR - 1) / L->NR);
+    return IDASH_B200_OK;
+}
+
 extern "C" int idash_b200_cloud_eval_host(idash_b200_ctx *c, const idash_b200_model *m, const idash_b200_cts *in,
                                           const idash_b200_cts *out, const uint32_t *slot_of_row) {
     clear_error();

@@ -23,9 +23,29 @@
 #include <sys/time.h>
 #include <time.h>
 
+#include <sys/stat.h>
+
 #include "idash_b200.h"
+#include "idash_b200_layout.h"
 
 using std::string;
+
+// The model as read_model emits it for the device (north-star: "parse_vw emits a device-resident block-banded layout"): rows sorted
+// by output bigIndex (so that a contiguous target range is a contiguous row range: multi-GPU sharding and pipelined copies), one
+// uploaded copy per GPU, and the order in which the reference would walk Model::model -- the record order of
+// encrypted_prediction.bin (eval/idash.cpp:772-777, 607).
+struct CompiledModel {
+    uint32_t S = 0, NR = 0, RS = 0;
+    uint64_t n_rows = 0;
+    std::vector<uint32_t> sorted_bidx;      // device row -> output bigIndex, ascending
+    std::vector<uint32_t> map_order;        // output bigIndices in the iteration order of the reference's Model::model
+    bool from_cache = false;
+    std::shared_future<std::vector<idash_b200_model *>> device_models;   // one per entry of idash_host_devices()
+    ~CompiledModel() {
+        if (device_models.valid())
+            for (idash_b200_model *m : device_models.get()) idash_b200_model_free(m);
+    }
+};
 
 // ---- constants (eval/idash.cpp:20-45) --------------------------------------------------------------------------
 const double IdashParams::alpha = 1.0 / 33554432.0;            // pow(2., -25)
@@ -93,18 +113,31 @@ void host_buf_free(const HostBuf &b) {
     else free(b.p);
 }
 
-// one context per process (one process per GPU)
-// (thread-safe: the cloud binary creates it on a helper thread while the model files are parsed; `die` = false is that
+// one context per GPU of idash_host_devices() (normally one: one process per GPU; IDASH_GPUS lists several)
+// (thread-safe: the cloud binary creates them on a helper thread while the model files are parsed; `die` = false is that
 // helper's probe -- a box without a GPU must still run the file-format half of this layer)
-idash_b200_ctx *gpu_ctx(bool die = true) {
-    static idash_b200_ctx *ctx = nullptr;
+const std::vector<idash_b200_ctx *> &gpu_ctxs(bool die = true) {
+    static std::vector<idash_b200_ctx *> ctxs;
     static string error;
     static std::once_flag once;
     std::call_once(once, []() {
-        if (idash_b200_init(&ctx, idash_host_device()) != IDASH_B200_OK) { ctx = nullptr; error = idash_b200_last_error(); }
+        const std::vector<int> devs = idash_host_devices();
+        std::vector<idash_b200_ctx *> made(devs.size(), nullptr);
+        std::vector<string> errs(devs.size());
+        std::vector<std::thread> th;
+        for (size_t i = 0; i < devs.size(); ++i)
+            th.emplace_back([&, i]() { if (idash_b200_init(&made[i], devs[i]) != IDASH_B200_OK) { made[i] = nullptr; errs[i] = idash_b200_last_error(); } });
+        for (auto &x : th) x.join();
+        for (size_t i = 0; i < devs.size(); ++i)
+            if (!made[i]) { error = errs[i]; for (idash_b200_ctx *c : made) if (c) idash_b200_destroy(c); return; }
+        ctxs = made;
     });
-    if (!ctx && die) DIE_DRAMATICALLY("idash_b200_init: " << error);
-    return ctx;
+    if (ctxs.empty() && die) DIE_DRAMATICALLY("idash_b200_init: " << error);
+    return ctxs;
+}
+idash_b200_ctx *gpu_ctx(bool die = true) {
+    const auto &c = gpu_ctxs(die);
+    return c.empty() ? nullptr : c[0];
 }
 
 // Whole-range pread / pwrite by a pool of threads: a 2 GB ciphertext file moves through the page cache at memory speed
@@ -189,14 +222,45 @@ void parallel_file_write(int fd, uint8_t *buf, size_t bytes, const char *what) {
     REQUIRE_DRAMATICALLY(::munmap(map, bytes) == 0, "error unmapping encrypted " << what << " file");
 }
 
-std::shared_ptr<CtSlab> read_ct_file(const string &filename, const char *what) {
+void warm_up_pin_input(const std::shared_ptr<CtSlab> &slab);
+
+// whole ciphertext file -> slab; checks the size and every record's TLWE type uid (tfhe_io.cpp:308 aborts on a bad one).
+// file_order (optional) receives, for the k-th record of the file, the slab slot it was put into.
+// sort_by_index: the records are placed in the slab sorted by ciphertext index instead of file (hash) order, so that the inputs of a
+// contiguous target range are one contiguous run of records -- what a GPU that owns a target range copies. Same single
+// pass over the bytes: the file is mapped and every record is copied to its slot by all threads.
+std::shared_ptr<CtSlab> read_ct_file(const string &filename, const char *what, bool sort_by_index, bool pin, std::vector<uint32_t> *file_order) {
     const int fd = ::open(filename.c_str(), O_RDONLY);
     REQUIRE_DRAMATICALLY(fd >= 0, "Cannot open encrypted " << what << " file for read");
     uint64_t count = 0;
     REQUIRE_DRAMATICALLY(::pread(fd, &count, 8, 0) == 8, "truncated encrypted " << what << " file");
     REQUIRE_DRAMATICALLY(count < ((uint64_t) 1 << 32), "encrypted " << what << " file: implausible record count");
+    struct stat st;
+    REQUIRE_DRAMATICALLY(::fstat(fd, &st) == 0, "cannot stat encrypted " << what << " file");
+    // before anything is allocated: a corrupt count must end in this message, not in a 30 TB mapping
+    REQUIRE_DRAMATICALLY(!S_ISREG(st.st_mode) || (uint64_t) st.st_size >= 8 + count * (uint64_t) REC, "truncated encrypted " << what << " file");
     auto slab = std::make_shared<CtSlab>(count);
-    parallel_file_io(fd, slab->records(), (size_t) count * REC, 8, false, what);
+    if (pin) warm_up_pin_input(slab);          // page-locking runs on a helper thread while the records are read
+    const size_t bytes = (size_t) count * REC;
+    void *map = MAP_FAILED;
+    if (sort_by_index && count > 1 && !getenv("IDASH_HOST_NO_MMAP")) map = ::mmap(nullptr, 8 + bytes, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (map != MAP_FAILED) {
+        const uint8_t *src = static_cast<const uint8_t *>(map) + 8;
+        std::vector<uint32_t> idx(count);
+        parallel_ranges(count, [&](size_t b, size_t e) { for (size_t i = b; i < e; ++i) memcpy(&idx[i], src + i * REC, 4); });
+        std::vector<uint32_t> by_index(count);
+        for (uint64_t i = 0; i < count; ++i) by_index[i] = (uint32_t) i;
+        std::stable_sort(by_index.begin(), by_index.end(), [&](uint32_t a, uint32_t b) { return idx[a] < idx[b]; });
+        std::vector<uint32_t> slot_of(count);
+        slab->sorted_index.resize(count);
+        for (uint64_t s = 0; s < count; ++s) { slot_of[by_index[s]] = (uint32_t) s; slab->sorted_index[s] = idx[by_index[s]]; }
+        parallel_ranges(count, [&](size_t b, size_t e) { for (size_t i = b; i < e; ++i) memcpy(slab->record(slot_of[i]), src + i * REC, REC); });
+        ::munmap(map, 8 + bytes);
+        if (file_order) *file_order = std::move(slot_of);
+    } else {
+        parallel_file_io(fd, slab->records(), bytes, 8, false, what);
+        if (file_order) { file_order->resize(count); for (uint64_t i = 0; i < count; ++i) (*file_order)[i] = (uint32_t) i; }
+    }
     ::close(fd);
     std::atomic<uint64_t> bad_rec(UINT64_MAX);
     parallel_ranges(count, [&](size_t b, size_t e) {
@@ -210,6 +274,9 @@ std::shared_ptr<CtSlab> read_ct_file(const string &filename, const char *what) {
     REQUIRE_DRAMATICALLY(bad_rec == UINT64_MAX, "encrypted " << what << " file: bad TLWE sample type in record " << bad_rec.load());
     return slab;
 }
+
+template <class Map>
+bool all_views_of(const Map &m, const std::shared_ptr<CtSlab> &slab);
 
 // map iteration order == slab slot order? then the slab image IS the file
 template <class Map>
@@ -231,6 +298,53 @@ void write_ct_file(const Map &m, const std::shared_ptr<CtSlab> &slab, const stri
         REQUIRE_DRAMATICALLY(fd >= 0, "Cannot open encrypted " << what << " file for write");
         REQUIRE_DRAMATICALLY(::ftruncate(fd, (off_t) slab->image_bytes()) == 0, "cannot size encrypted " << what << " file");
         parallel_file_write(fd, slab->image(), slab->image_bytes(), what);
+        REQUIRE_DRAMATICALLY(::close(fd) == 0, "error closing encrypted " << what << " file");
+        return;
+    }
+    if (all_views_of(m, slab)) {
+        // Samples are views into one slab but the map walks them in another order (cloud_compute_score keeps its output slab in
+        // target order and the reference's record order is hash order): every record is copied from its slab slot to its file
+        // slot, by all threads, straight into the mapped file -- the same single pass over the bytes as the bulk copy above.
+        const uint64_t count = m.size();
+        std::vector<std::pair<uint32_t, const TLweSample *>> order;
+        order.reserve(count);
+        for (const auto &it : m) order.push_back({it.first, it.second});
+        const size_t bytes = 8 + (size_t) count * REC;
+        const int fd = ::open(filename.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0644);
+        REQUIRE_DRAMATICALLY(fd >= 0, "Cannot open encrypted " << what << " file for write");
+        REQUIRE_DRAMATICALLY(::ftruncate(fd, (off_t) bytes) == 0, "cannot size encrypted " << what << " file");
+        void *map = getenv("IDASH_HOST_NO_MMAP") ? MAP_FAILED : ::mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        const int32_t uid = IDASH_B200_TLWE_SAMPLE_UID;
+        auto fill = [&](uint8_t *dst, uint64_t k) {
+            memcpy(dst, slab->record((uint64_t) slab->slot_of(order[k].second)), REC);
+            memcpy(dst, &order[k].first, 4);
+            memcpy(dst + 4, &uid, 4);
+            memcpy(dst + REC_VAR_OFF, &order[k].second->current_variance, 8);
+        };
+        std::atomic<bool> bad(false);
+        if (map != MAP_FAILED) {
+            memcpy(map, &count, 8);
+            parallel_ranges(count, [&](size_t b, size_t e) { for (size_t k = b; k < e; ++k) fill(static_cast<uint8_t *>(map) + 8 + k * REC, k); });
+            REQUIRE_DRAMATICALLY(::munmap(map, bytes) == 0, "error unmapping encrypted " << what << " file");
+        } else {
+            REQUIRE_DRAMATICALLY(::pwrite(fd, &count, 8, 0) == 8, "short write to encrypted " << what << " file");
+            parallel_ranges(count, [&](size_t b, size_t e) {
+                const size_t batch = 256;
+                std::vector<uint8_t> buf(batch * REC);
+                for (size_t k0 = b; k0 < e; k0 += batch) {
+                    const size_t n = std::min(batch, e - k0);
+                    for (size_t i = 0; i < n; ++i) fill(buf.data() + i * REC, k0 + i);
+                    size_t lo = 0;
+                    while (lo < n * REC) {
+                        const ssize_t r = ::pwrite(fd, buf.data() + lo, n * REC - lo, (off_t) (8 + k0 * REC + lo));
+                        if (r < 0 && errno == EINTR) continue;
+                        if (r <= 0) { bad = true; return; }
+                        lo += (size_t) r;
+                    }
+                }
+            });
+        }
+        REQUIRE_DRAMATICALLY(!bad, "short write to encrypted " << what << " file");
         REQUIRE_DRAMATICALLY(::close(fd) == 0, "error closing encrypted " << what << " file");
         return;
     }
@@ -287,11 +401,23 @@ std::unique_ptr<PackedCts> pack_map(const Map &m) {
     return pk;
 }
 
-// Helper-thread warm-up for the cloud stage (started by read_model, collected by cloud_compute_score): GPU context +
-// the slab the output ciphertexts will be copied into.
+// Helper-thread warm-up for the cloud stage (started by read_params / read_model / read_encrypted_data, collected by
+// idash_host_wait_ready and cloud_compute_score): GPU contexts, the page-locked slab the output ciphertexts are copied into,
+// page-locking of the input slab, upload of the compiled model.
 std::mutex g_warm_mutex;
 std::shared_future<void> g_warm_ctx;
-std::future<std::shared_ptr<CtSlab>> g_warm_slab;
+std::shared_future<std::shared_ptr<CtSlab>> g_warm_slab;
+std::vector<std::shared_future<void>> g_warm_misc;
+string g_model_cache_path;
+
+// page-lock a slab once the context exists (the C ABI copies to / from page-locked memory at the link's full rate and
+// asynchronously; measured on the 2 GB output slab: 0.036 s against 0.105 s pageable). Best effort.
+void pin_slab(const std::shared_ptr<CtSlab> &slab) {
+    if (!slab || slab->count == 0 || slab->mem_kind == HOST_MEM_PINNED || getenv("IDASH_HOST_NO_PIN")) return;
+    if (!gpu_ctx(false)) return;
+    if (idash_b200_host_register(slab->mem, slab->mem_bytes) == IDASH_B200_OK) slab->registered = true;
+}
+
 // read_params is the first call of both GPU stages: start creating the CUDA context (0.3-0.5 s) right away
 void warm_up_context() {
     if (getenv("IDASH_HOST_NO_WARMUP")) return;
@@ -308,21 +434,109 @@ void warm_up_cloud(uint64_t n_rows) {
     warm_up_context();
     std::lock_guard<std::mutex> lock(g_warm_mutex);
     if (g_warm_slab.valid()) return;
-    g_warm_slab = std::async(std::launch::async, [n_rows]() {
+    std::shared_future<void> ctx_ready = g_warm_ctx;
+    g_warm_slab = std::async(std::launch::async, [n_rows, ctx_ready]() {
         const double t0 = now_s();
         auto slab = std::make_shared<CtSlab>(n_rows);
-        if (getenv("IDASH_HOST_TIMING")) fprintf(stderr, "[idash_host] warm-up: output slab (%.2f GB) in %.3f s\n", slab->image_bytes() * 1e-9, now_s() - t0);
+        const double t1 = now_s();
+        if (ctx_ready.valid()) ctx_ready.wait();
+        pin_slab(slab);
+        if (getenv("IDASH_HOST_TIMING"))
+            fprintf(stderr, "[idash_host] warm-up: output slab (%.2f GB) allocated in %.3f s, page-locked %s after %.3f s\n", slab->image_bytes() * 1e-9,
+                    t1 - t0, slab->registered ? "yes" : "no", now_s() - t0);
         return slab;
-    });
+    }).share();
+}
+void warm_up_pin_input(const std::shared_ptr<CtSlab> &slab) {
+    if (getenv("IDASH_HOST_NO_WARMUP")) return;
+    std::lock_guard<std::mutex> lock(g_warm_mutex);
+    if (!g_warm_ctx.valid()) return;             // no GPU stage in sight (file-format use of this layer)
+    std::shared_future<void> ctx_ready = g_warm_ctx;
+    g_warm_misc.push_back(std::async(std::launch::async, [slab, ctx_ready]() { ctx_ready.wait(); pin_slab(slab); }).share());
 }
 std::shared_ptr<CtSlab> take_output_slab(uint64_t n_rows) {
     std::shared_ptr<CtSlab> slab;
     {
         std::lock_guard<std::mutex> lock(g_warm_mutex);
-        if (g_warm_slab.valid()) slab = g_warm_slab.get();
+        if (g_warm_slab.valid()) { slab = g_warm_slab.get(); g_warm_slab = std::shared_future<std::shared_ptr<CtSlab>>(); }
     }
-    if (!slab || slab->count != n_rows) slab = std::make_shared<CtSlab>(n_rows);
+    if (!slab || slab->count != n_rows) { slab = std::make_shared<CtSlab>(n_rows); pin_slab(slab); }
     return slab;
+}
+
+uint64_t fnv1a(uint64_t h, const void *p, size_t n) {
+    const uint8_t *b = static_cast<const uint8_t *>(p);
+    for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+// Uploads a compiled layout to every GPU of this process (helper thread; the layout is shared between the copies).
+std::shared_future<std::vector<idash_b200_model *>> upload_everywhere(idash_b200_layout *layout) {
+    std::shared_future<void> ctx_ready;
+    {
+        std::lock_guard<std::mutex> lock(g_warm_mutex);
+        ctx_ready = g_warm_ctx;
+    }
+    return std::async(std::launch::async, [layout, ctx_ready]() {
+        if (ctx_ready.valid()) ctx_ready.wait();
+        const double t0 = now_s();
+        const auto &ctxs = gpu_ctxs(false);
+        std::vector<idash_b200_model *> ms(ctxs.size(), nullptr);
+        if (ctxs.empty()) { idash_b200_layout_free(layout); return ms; }       // no GPU: file-format use of this layer; the cloud stage dies later
+        if (idash_b200_model_upload_layout(ctxs[0], layout, &ms[0]) != IDASH_B200_OK) DIE_DRAMATICALLY("idash_b200_model_upload_layout: " << idash_b200_last_error());
+        for (size_t g = 1; g < ctxs.size(); ++g)
+            if (idash_b200_model_clone(ctxs[g], ms[0], &ms[g]) != IDASH_B200_OK) DIE_DRAMATICALLY("idash_b200_model_clone: " << idash_b200_last_error());
+        if (getenv("IDASH_HOST_TIMING")) fprintf(stderr, "[idash_host] model uploaded to %zu GPU(s) in %.3f s\n", ctxs.size(), now_s() - t0);
+        return ms;
+    }).share();
+}
+void track_upload(const std::shared_future<std::vector<idash_b200_model *>> &f) {
+    std::lock_guard<std::mutex> lock(g_warm_mutex);
+    g_warm_misc.push_back(std::async(std::launch::deferred, [f]() { f.wait(); }).share());
+}
+
+// CSR (rows sorted by output bigIndex) -> compiled layout (+ cache file) -> CompiledModel with the upload in flight
+std::shared_ptr<CompiledModel> compile_model(const IdashParams &params, std::vector<uint32_t> &&sorted_bidx, const std::vector<uint64_t> &row_ptr,
+                                             const std::vector<uint32_t> &col, const std::vector<int32_t> &coef, std::vector<uint32_t> &&map_order,
+                                             const string &cache_path, uint64_t cache_key) {
+    auto cm = std::make_shared<CompiledModel>();
+    cm->S = params.NUM_SAMPLES; cm->NR = params.NUM_REGIONS; cm->RS = params.REGION_SIZE;
+    cm->n_rows = sorted_bidx.size();
+    idash_b200_model_desc desc;
+    desc.num_samples = cm->S; desc.num_regions = cm->NR; desc.region_size = cm->RS;
+    desc.n_rows = cm->n_rows; desc.out_bidx = sorted_bidx.data(); desc.row_ptr = row_ptr.data(); desc.col = col.data(); desc.coef = coef.data();
+    idash_b200_layout *layout = nullptr;
+    if (idash_b200_layout_compile_ex(&desc, IDASH_B200_COMPILE_DEFAULT, &layout) != IDASH_B200_OK) DIE_DRAMATICALLY("idash_b200_layout_compile: " << idash_b200_last_error());
+    if (!cache_path.empty() && idash_b200_layout_save(layout, cache_path.c_str(), cache_key) != IDASH_B200_OK && getenv("IDASH_HOST_TIMING"))
+        fprintf(stderr, "[idash_host] model cache not written: %s\n", idash_b200_last_error());
+    cm->sorted_bidx = std::move(sorted_bidx);
+    cm->map_order = std::move(map_order);
+    cm->device_models = upload_everywhere(layout);
+    track_upload(cm->device_models);
+    return cm;
+}
+
+// Model (map of maps) -> CSR with rows sorted by output bigIndex -> compiled model. Row pointers serially, entries by all threads.
+std::shared_ptr<CompiledModel> compile_from_map(const Model &model, const IdashParams &params, const string &cache_path, uint64_t cache_key) {
+    const uint64_t n_rows = model.model.size();
+    std::vector<uint32_t> map_order;
+    map_order.reserve(n_rows);
+    std::vector<std::pair<uint32_t, const std::unordered_map<FeatBigIndex, int32_t> *>> rows;
+    rows.reserve(n_rows);
+    for (const auto &row : model.model) { map_order.push_back(row.first); rows.push_back({row.first, &row.second}); }
+    std::sort(rows.begin(), rows.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+    std::vector<uint32_t> sorted_bidx(n_rows);
+    std::vector<uint64_t> row_ptr(n_rows + 1, 0);
+    for (uint64_t r = 0; r < n_rows; ++r) { sorted_bidx[r] = rows[r].first; row_ptr[r + 1] = row_ptr[r] + rows[r].second->size(); }
+    std::vector<uint32_t> col(row_ptr[n_rows]);
+    std::vector<int32_t> coef(row_ptr[n_rows]);
+    parallel_ranges(n_rows, [&](size_t b, size_t e) {
+        for (size_t r = b; r < e; ++r) {
+            uint64_t k = row_ptr[r];
+            for (const auto &c : *rows[r].second) { col[k] = c.first; coef[k] = c.second; ++k; }
+        }
+    });
+    return compile_model(params, std::move(sorted_bidx), row_ptr, col, coef, std::move(map_order), cache_path, cache_key);
 }
 
 template <class Map>
@@ -354,10 +568,17 @@ CtSlab::CtSlab(uint64_t n) : count(n), samples(n), polys(2 * n) {
         samples[i].k = (int32_t) IdashParams::k;
     }
 }
-CtSlab::~CtSlab() { host_buf_free(HostBuf{mem, mem_kind, mem_bytes}); }
+CtSlab::~CtSlab() {
+    if (registered) idash_b200_host_unregister(mem);
+    host_buf_free(HostBuf{mem, mem_kind, mem_bytes});
+}
 uint32_t CtSlab::index_of(uint64_t i) const { uint32_t v; memcpy(&v, record(i), 4); return v; }
-void CtSlab::pull_variances() { for (uint64_t i = 0; i < count; ++i) memcpy(&samples[i].current_variance, record(i) + REC_VAR_OFF, 8); }
-void CtSlab::push_variances() { for (uint64_t i = 0; i < count; ++i) memcpy(record(i) + REC_VAR_OFF, &samples[i].current_variance, 8); }
+void CtSlab::pull_variances() {
+    parallel_ranges(count, [&](size_t b, size_t e) { for (size_t i = b; i < e; ++i) memcpy(&samples[i].current_variance, record(i) + REC_VAR_OFF, 8); }, 4096);
+}
+void CtSlab::push_variances() {
+    parallel_ranges(count, [&](size_t b, size_t e) { for (size_t i = b; i < e; ++i) memcpy(record(i) + REC_VAR_OFF, &samples[i].current_variance, 8); }, 4096);
+}
 
 // ---- files -----------------------------------------------------------------------------------------------------
 // NOTE: none of the reference-visible hash maps is reserve()d anywhere in this file: their bucket counts, hence their
@@ -402,13 +623,16 @@ void read_key(IdashKey &key, const string &filename) {
     key.tlweKey = new TLweKey{tp, poly};
 }
 
+// eval/idash.cpp:510-533. The map is filled in FILE order (emplace: the first record of an index wins), as the reference does -- its
+// iteration order is what write_encrypted_data reproduces; the slab itself holds the records sorted by index (read_ct_file).
 void read_encrypted_data(EncryptedData &d, const IdashParams &, const string &filename) {
-    d.slab = read_ct_file(filename, "data");
-    for (uint64_t i = 0; i < d.slab->count; ++i) d.enc_data.emplace(d.slab->index_of(i), &d.slab->samples[i]);
+    std::vector<uint32_t> file_order;
+    d.slab = read_ct_file(filename, "data", true, true, &file_order);
+    for (uint64_t k = 0; k < d.slab->count; ++k) d.enc_data.emplace(d.slab->index_of(file_order[k]), &d.slab->samples[file_order[k]]);
 }
 
 void read_encrypted_predictions(EncryptedPredictions &p, const IdashParams &, const string &filename) {
-    p.slab = read_ct_file(filename, "predictions");
+    p.slab = read_ct_file(filename, "predictions", false, false, nullptr);
     for (uint64_t i = 0; i < p.slab->count; ++i) p.score.emplace(p.slab->index_of(i), &p.slab->samples[i]);
 }
 
@@ -420,16 +644,97 @@ void write_encrypted_predictions(const EncryptedPredictions &p, const IdashParam
     write_ct_file(p.score, p.slab, filename, "predictions");
 }
 
+// The order in which the reference walks Model::model (eval/idash.cpp:772-777): keys inserted in the iteration order of
+// out_features_index, variants 0..2 (eval/idash.cpp:75-88). The iteration order of a libstdc++ unordered_map depends on the key type,
+// the hasher, the insertion sequence and the rehash policy only -- not on the mapped type -- so a map of the same keys to a byte
+// reproduces it without the coefficient maps (what the model-cache path needs).
+static std::vector<uint32_t> reference_row_order(const IdashParams &params) {
+    std::unordered_map<FeatBigIndex, char> probe;
+    for (const auto &e : params.out_features_index)
+        for (int snp = 0; snp < 3; ++snp) probe[e.second[(size_t) snp]] = 0;
+    std::vector<uint32_t> order;
+    order.reserve(probe.size());
+    for (const auto &it : probe) order.push_back(it.first);
+    return order;
+}
+
+// Fingerprint of what a compiled model depends on: the parameters (sizes and both feature index tables) and the model directory
+// (name, size and mtime of every <pos>_<variant>.hr file, combined order-independently; stat'ed by all threads: 0.02-0.05 s for
+// 242 646 files against 0.25 s for parsing them). false = some file is missing (read_model then dies like the reference).
+static bool model_fingerprint(const IdashParams &params, const string &path, uint64_t *key) {
+    uint64_t h = 1469598103934665603ull;
+    const uint32_t head[7] = {params.NUM_SAMPLES, params.NUM_INPUT_POSITIONS, params.NUM_OUTPUT_POSITIONS, params.NUM_INPUT_FEATURES,
+                              params.NUM_OUTPUT_FEATURES, params.NUM_REGIONS, params.REGION_SIZE};
+    h = fnv1a(h, head, sizeof(head));
+    uint64_t tags = 0;                                         // order-independent: the map's iteration order is not part of the model
+    for (const auto &e : params.in_features_index) tags += fnv1a(fnv1a(1469598103934665603ull, &e.first, 8), e.second.data(), 12);
+    h = fnv1a(h, &tags, 8);
+    std::vector<std::pair<uint64_t, std::array<FeatBigIndex, 3>>> outs(params.out_features_index.begin(), params.out_features_index.end());
+    std::atomic<uint64_t> files(0);
+    std::atomic<bool> missing(false);
+    parallel_ranges(outs.size(), [&](size_t b, size_t e) {
+        uint64_t acc = 0;
+        string fn;
+        for (size_t i = b; i < e; ++i) {
+            for (int snp = 0; snp < 3; ++snp) {
+                fn = path; fn += '/'; fn += std::to_string(outs[i].first); fn += '_'; fn += (char) ('0' + snp); fn += ".hr";
+                struct stat st;
+                if (::stat(fn.c_str(), &st) != 0) { missing = true; return; }
+                const uint64_t rec[5] = {outs[i].first, (uint64_t) outs[i].second[(size_t) snp], (uint64_t) st.st_size, (uint64_t) st.st_mtim.tv_sec, (uint64_t) st.st_mtim.tv_nsec};
+                acc += fnv1a(1469598103934665603ull, rec, sizeof(rec));
+            }
+        }
+        files += acc;
+    });
+    if (missing) return false;
+    const uint64_t f = files.load();
+    h = fnv1a(h, &f, 8);
+    *key = h;
+    return true;
+}
+
 // eval/idash.cpp:66-90. The .hr files are parsed by a pool of threads (3 x NUM_OUTPUT_POSITIONS small files);
 // the model map is then filled in the reference's order (iteration order of out_features_index, variant 0..2),
-// which fixes the record order of encrypted_prediction.bin downstream.
+// which fixes the record order of encrypted_prediction.bin downstream. The model is compiled into the device layout right here
+// (north-star: "parse_vw emits a device-resident block-banded layout") and its upload starts on a helper thread; with a model cache
+// (idash_host_set_model_cache) a later run takes the compiled layout from one file and skips the text files altogether.
 void read_model(Model &model, const IdashParams &params, const string &path) {
     // Only the cloud stage loads a model: bring the GPU context up and allocate + fault in the output slab on helper
     // threads while the files are parsed (CUDA initialisation and 2 GB of fresh host memory are the two largest fixed
     // costs of cloud_compute_score at iDASH scale).
     warm_up_cloud(3 * (uint64_t) params.out_features_index.size());
-
+    const bool timing = getenv("IDASH_HOST_TIMING") != nullptr;
     const double t_begin = now_s();
+
+    string cache_path;
+    {
+        std::lock_guard<std::mutex> lock(g_warm_mutex);
+        cache_path = g_model_cache_path;
+    }
+    uint64_t cache_key = 0;
+    if (!cache_path.empty()) {
+        if (!model_fingerprint(params, path, &cache_key)) cache_path.clear();      // a missing file: parse, and die on it like the reference
+        idash_b200_layout *layout = nullptr;
+        if (!cache_path.empty() && idash_b200_layout_load(cache_path.c_str(), cache_key, &layout) == IDASH_B200_OK) {
+            idash_b200_model_info info;
+            idash_b200_layout_get_info(layout, &info);
+            auto cm = std::make_shared<CompiledModel>();
+            cm->S = params.NUM_SAMPLES; cm->NR = params.NUM_REGIONS; cm->RS = params.REGION_SIZE;
+            cm->n_rows = info.n_rows;
+            cm->sorted_bidx.assign(idash_b200_layout_out_bidx(layout), idash_b200_layout_out_bidx(layout) + info.n_rows);
+            cm->map_order = reference_row_order(params);
+            cm->from_cache = true;
+            if (cm->map_order.size() == cm->n_rows) {
+                cm->device_models = upload_everywhere(layout);
+                track_upload(cm->device_models);
+                model.compiled = cm;
+                if (timing) fprintf(stderr, "[idash_host] read_model: compiled model taken from %s in %.3f s\n", cache_path.c_str(), now_s() - t_begin);
+                return;
+            }
+            idash_b200_layout_free(layout);                    // not this model after all: parse
+        }
+    }
+
     struct Job { uint64_t pos; std::array<FeatBigIndex, 3> out; };
     std::vector<Job> jobs;
     jobs.reserve(params.out_features_index.size());
@@ -461,7 +766,11 @@ void read_model(Model &model, const IdashParams &params, const string &path) {
     // outer map: filled serially in the reference's order (its iteration order is the row order downstream)
     for (size_t i = 0; i < jobs.size(); ++i)
         for (int snp = 0; snp < 3; ++snp) model.model[jobs[i].out[snp]] = std::move(parsed[i][snp]);
-    if (getenv("IDASH_HOST_TIMING")) fprintf(stderr, "[idash_host] read_model: parse %.3f s, fill %.3f s\n", t_parsed - t_begin, now_s() - t_parsed);
+    const double t_filled = now_s();
+    model.compiled = compile_from_map(model, params, cache_path, cache_key);
+    if (timing)
+        fprintf(stderr, "[idash_host] read_model: parse %.3f s, fill %.3f s, compile%s %.3f s\n", t_parsed - t_begin, t_filled - t_parsed,
+                cache_path.empty() ? "" : " + cache write", now_s() - t_filled);
 }
 
 // eval/idash.cpp:436-469: header, then for every sample, for every target in file order, "<sample>,<target>,<p0>,<p1>,<p2>".
@@ -545,77 +854,71 @@ int idash_host_device() {
     if (const char *e = getenv("LOCAL_RANK")) return atoi(e);
     return 0;
 }
+std::vector<int> idash_host_devices() {
+    std::vector<int> devs;
+    if (const char *e = getenv("IDASH_GPUS")) {
+        for (const char *p = e; *p;) {
+            char *end = nullptr;
+            const long v = strtol(p, &end, 10);
+            if (end == p) break;
+            if (v >= 0 && std::find(devs.begin(), devs.end(), (int) v) == devs.end()) devs.push_back((int) v);
+            p = end;
+            while (*p == ',' || *p == ' ') ++p;
+        }
+    }
+    if (devs.empty()) devs.push_back(idash_host_device());
+    return devs;
+}
 double idash_host_last_gpu_seconds() { return g_last_gpu_seconds; }
 
+void idash_host_set_model_cache(const string &path) {
+    std::lock_guard<std::mutex> lock(g_warm_mutex);
+    g_model_cache_path = path;
+}
+
+void idash_host_wait_ready() {
+    std::shared_future<void> ctx;
+    std::shared_future<std::shared_ptr<CtSlab>> slab;
+    std::vector<std::shared_future<void>> misc;
+    {
+        std::lock_guard<std::mutex> lock(g_warm_mutex);
+        ctx = g_warm_ctx; slab = g_warm_slab; misc.swap(g_warm_misc);
+    }
+    if (ctx.valid()) ctx.wait();
+    if (slab.valid()) slab.wait();
+    for (auto &f : misc) f.wait();
+}
+
+// eval/idash.cpp:763-848. No arithmetic here: the compiled model (read_model) is evaluated by libidash_b200 on one GPU, or -- with
+// IDASH_GPUS -- on several, each taking a contiguous target range (rows sorted by output bigIndex, cut at tile boundaries) and only
+// the part of the input slab its windows touch (the loop being cut is eval/idash.cpp:779-790). The output slab is kept in
+// target order, which makes every GPU's share one contiguous device->host copy; the reference's record order is restored by
+// write_encrypted_predictions while the records go to the file (one pass over the bytes either way).
 void cloud_compute_score(EncryptedPredictions &enc_preds, const EncryptedData &enc_data, const Model &model, const IdashParams &params) {
     REQUIRE_DRAMATICALLY(params.k == 1, "blah");                                        // eval/idash.cpp:768
     REQUIRE_DRAMATICALLY(enc_preds.score.empty(), "shit happens again");                // createAndGet, eval/idash.h:181
-    const uint64_t n_rows = model.model.size();
     const bool timing = getenv("IDASH_HOST_TIMING") != nullptr;
     const double t_begin = now_s();
 
-    // Model -> CSR, rows in the map's iteration order (the order the reference walks them, eval/idash.cpp:772-777);
-    // row pointers serially, entries by a pool of threads
-    std::vector<uint32_t> out_bidx(n_rows);
-    std::vector<uint64_t> row_ptr(n_rows + 1, 0);
-    std::vector<const std::unordered_map<FeatBigIndex, int32_t> *> rows(n_rows);
-    {
-        uint64_t r = 0;
-        for (const auto &row : model.model) {
-            out_bidx[r] = row.first;
-            rows[r] = &row.second;
-            row_ptr[r + 1] = row_ptr[r] + row.second.size();
-            ++r;
-        }
+    std::shared_ptr<CompiledModel> cm = model.compiled;
+    if (!cm || cm->S != params.NUM_SAMPLES || cm->NR != params.NUM_REGIONS || cm->RS != params.REGION_SIZE ||
+        (!cm->from_cache && cm->n_rows != model.model.size())) {
+        warm_up_context();
+        cm = compile_from_map(model, params, string(), 0);                              // a hand-built / edited Model
     }
-    std::vector<uint32_t> col(row_ptr[n_rows]);
-    std::vector<int32_t> coef(row_ptr[n_rows]);
-    std::atomic<bool> missing(false);
-    parallel_ranges(n_rows, [&](size_t b, size_t e) {
-        for (size_t r = b; r < e; ++r) {
-            uint64_t k = row_ptr[r];
-            for (const auto &c : *rows[r]) {
-                if (c.first != params.constant_bigIndex() && enc_data.enc_data.find(params.feature_indexOf(c.first)) == enc_data.enc_data.end())
-                    missing = true;
-                col[k] = c.first; coef[k] = c.second;
-                ++k;
-            }
-        }
-    });
-    REQUIRE_DRAMATICALLY(!missing, "shit happens before");                              // getTLWE, eval/idash.h:164
-
-    const double t_csr0 = now_s();
-    idash_b200_ctx *ctx = gpu_ctx();
-    const double t0 = now_s();
-    idash_b200_model_desc desc;
-    desc.num_samples = params.NUM_SAMPLES; desc.num_regions = params.NUM_REGIONS; desc.region_size = params.REGION_SIZE;
-    desc.n_rows = n_rows; desc.out_bidx = out_bidx.data(); desc.row_ptr = row_ptr.data(); desc.col = col.data(); desc.coef = coef.data();
-    idash_b200_model *dm = nullptr;
-    if (idash_b200_model_upload(ctx, &desc, &dm) != IDASH_B200_OK) DIE_DRAMATICALLY("idash_b200_model_upload: " << idash_b200_last_error());
-    const double t_upload = now_s();
-    // outputs: one slab; the map is filled in the reference's insertion order, then record slot k goes to the k-th
-    // element in ITERATION order, so that the slab is the image of encrypted_prediction.bin (eval/idash.cpp:607)
+    const uint64_t n_rows = cm->n_rows;
+    const double t_model = now_s();
+    const auto &ctxs = gpu_ctxs();                                                       // dies without a GPU
+    const std::vector<idash_b200_model *> &dms = cm->device_models.get();
+    REQUIRE_DRAMATICALLY(dms.size() == ctxs.size() && !dms.empty(), "the compiled model was not uploaded");
+    const double t_ready = now_s();
     auto slab = take_output_slab(n_rows);
     const double t_slab = now_s();
-    for (uint64_t r = 0; r < n_rows; ++r) enc_preds.score.emplace(out_bidx[r], nullptr);
-    std::vector<uint32_t> slot_of_row(n_rows);
-    {
-        // the k-th element in iteration order gets slot k; its row is found through a bigIndex -> row table
-        std::unordered_map<FeatBigIndex, uint32_t> row_of;
-        row_of.reserve(n_rows);
-        for (uint64_t r = 0; r < n_rows; ++r) row_of.emplace(out_bidx[r], (uint32_t) r);
-        uint64_t k = 0;
-        for (auto &it : enc_preds.score) {
-            it.second = &slab->samples[k];
-            slot_of_row[row_of.at(it.first)] = (uint32_t) k;
-            ++k;
-        }
-    }
-    enc_preds.slab = slab;
 
     idash_b200_cts in, out;
     std::unique_ptr<PackedCts> staged;
-    if (all_views_of(enc_data.enc_data, enc_data.slab)) {
+    const bool in_views = all_views_of(enc_data.enc_data, enc_data.slab);
+    if (in_views) {
         enc_data.slab->push_variances();
         in = {IDASH_B200_LAYOUT_RECORDS, enc_data.slab->records(), enc_data.slab->count, nullptr, nullptr};
     } else {
@@ -623,16 +926,59 @@ void cloud_compute_score(EncryptedPredictions &enc_preds, const EncryptedData &e
         in = {IDASH_B200_LAYOUT_PACKED, staged->words(), staged->count, staged->index(), staged->variance()};
     }
     out = {IDASH_B200_LAYOUT_RECORDS, slab->records(), n_rows, nullptr, nullptr};
+
+    // the GPU work runs on helper threads (one per GPU) while this thread builds the output container
+    idash_b200_model_info info;
+    if (idash_b200_model_get_info(dms[0], &info) != IDASH_B200_OK) DIE_DRAMATICALLY("idash_b200_model_get_info: " << idash_b200_last_error());
+    const size_t n_gpus = (ctxs.size() > 1 && info.ring_ok && info.n_overflow_rows == 0 && info.n_tiles >= 2 * ctxs.size()) ? ctxs.size() : 1;
     const double t_eval0 = now_s();
-    const int rc = idash_b200_cloud_eval_host(ctx, dm, &in, &out, slot_of_row.data());
-    if (rc != IDASH_B200_OK) DIE_DRAMATICALLY("idash_b200_cloud_eval_host: " << idash_b200_last_error());
+    std::vector<std::future<std::pair<int, string>>> work;
+    for (size_t g = 0; g < n_gpus; ++g) {
+        work.push_back(std::async(std::launch::async, [&, g]() -> std::pair<int, string> {
+            int rc;
+            if (n_gpus == 1) {
+                rc = idash_b200_cloud_eval_host(ctxs[0], dms[0], &in, &out, nullptr);
+            } else {
+                const uint64_t T = info.n_tiles;
+                const uint64_t rb = (T * g / n_gpus) * IDASH_B200_TILE_ROWS, re = std::min<uint64_t>(n_rows, (T * (g + 1) / n_gpus) * IDASH_B200_TILE_ROWS);
+                idash_b200_cts part = in;
+                const auto &sidx = enc_data.slab ? enc_data.slab->sorted_index : std::vector<uint32_t>();
+                uint32_t ct_lo = 0, ct_hi = 0;
+                if (in_views && !sidx.empty() && idash_b200_model_input_range(dms[g], rb, re, &ct_lo, &ct_hi) == IDASH_B200_OK) {
+                    // the slab is sorted by ciphertext index: this GPU's share of the inputs is one contiguous run of records
+                    const size_t lo = (size_t) (std::lower_bound(sidx.begin(), sidx.end(), ct_lo) - sidx.begin());
+                    const size_t hi = (size_t) (std::lower_bound(sidx.begin(), sidx.end(), ct_hi) - sidx.begin());
+                    part.data = enc_data.slab->record(lo);
+                    part.count = hi - lo;
+                }
+                rc = idash_b200_cloud_eval_host_rows(ctxs[g], dms[g], &part, &out, rb, re);
+            }
+            return {rc, rc == IDASH_B200_OK ? string() : string(idash_b200_last_error())};
+        }));
+    }
+    // outputs: one ciphertext per model row, inserted in the order the reference walks its model (eval/idash.cpp:772-777), so that
+    // the map's iteration order -- the record order of encrypted_prediction.bin (eval/idash.cpp:607) -- is the reference's
+    {
+        const std::vector<uint32_t> &sb = cm->sorted_bidx;
+        for (const uint32_t bidx : cm->map_order) {
+            const size_t r = (size_t) (std::lower_bound(sb.begin(), sb.end(), bidx) - sb.begin());
+            enc_preds.score.emplace(bidx, &slab->samples[r]);
+        }
+    }
+    enc_preds.slab = slab;
+    const double t_cont = now_s();
+    int rc = IDASH_B200_OK;
+    string err;
+    for (auto &w : work) { const auto r = w.get(); if (r.first != IDASH_B200_OK && rc == IDASH_B200_OK) { rc = r.first; err = r.second; } }
+    REQUIRE_DRAMATICALLY(rc != IDASH_B200_ERR_MISSING_INPUT, "shit happens before");     // getTLWE, eval/idash.h:164
+    if (rc != IDASH_B200_OK) DIE_DRAMATICALLY("idash_b200_cloud_eval_host: " << err);
     const double t_eval1 = now_s();
-    idash_b200_model_free(dm);
-    g_last_gpu_seconds = (t_upload - t0) + (t_eval1 - t_eval0);
+    g_last_gpu_seconds = t_eval1 - t_eval0;
     slab->pull_variances();
     if (timing)
-        fprintf(stderr, "[idash_host] cloud_compute_score: csr %.3f s, context wait %.3f s, model_upload %.3f s, output slab wait %.3f s, containers %.3f s, cloud_eval_host %.3f s, total %.3f s\n",
-                t_csr0 - t_begin, t0 - t_csr0, t_upload - t0, t_slab - t_upload, t_eval0 - t_slab, t_eval1 - t_eval0, now_s() - t_begin);
+        fprintf(stderr, "[idash_host] cloud_compute_score: model %.3f s, wait for context + model upload %.3f s, output slab wait %.3f s, "
+                        "evaluation on %zu GPU(s) %.3f s (containers built meanwhile in %.3f s), total %.3f s\n",
+                t_model - t_begin, t_ready - t_model, t_slab - t_ready, n_gpus, t_eval1 - t_eval0, t_cont - t_eval0, now_s() - t_begin);
 }
 
 void decrypt_predictions(DecryptedPredictions &predictions, const EncryptedPredictions &enc_preds, const IdashKey &key) {

@@ -104,6 +104,8 @@ struct CtSlab {
     uint8_t *mem = nullptr;                 // pre-faulted huge-page mapping (pageable); see host_buf_alloc in idash_host.cpp
     int mem_kind = 0;
     size_t mem_bytes = 0;
+    bool registered = false;                // page-locked through idash_b200_host_register (unregistered by the destructor)
+    std::vector<uint32_t> sorted_index;     // non-empty: the records are sorted by ciphertext index and this is index_of(i) for every slot
     std::vector<TLweSample> samples;        // views: samples[i].a[0].coefsT / b->coefsT point into record i
     std::vector<TorusPolynomial> polys;
 

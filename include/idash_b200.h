@@ -163,6 +163,9 @@ int idash_b200_cloud_eval_device(idash_b200_ctx *ctx, const idash_b200_model *mo
  * order), and the device staging buffers are sized for the range. One host thread per GPU calls this on its own ctx / model copy. */
 int idash_b200_cloud_eval_host_rows(idash_b200_ctx *ctx, const idash_b200_model *model, const idash_b200_cts *in,
                                     const idash_b200_cts *out, uint64_t row_begin, uint64_t row_end);
+/* Input ciphertext indices [*ct_begin, *ct_end) that the windows of model rows [row_begin, row_end) touch (same row-range rules as
+ * cloud_eval_host_rows): the slab a GPU that owns that target range needs ("derive the slab from the model itself"). */
+int idash_b200_model_input_range(const idash_b200_model *model, uint64_t row_begin, uint64_t row_end, uint32_t *ct_begin, uint32_t *ct_end);
 /* The same model on n_batches input / output sets (in[b] -> out[b], b < n_batches) in one call: what a GPU that owns a target
  * range does for several sample batches (BASELINE configs[4]). When the ring kernel takes the model, all sets are PACKED
  * with inputs in identity order (index == NULL) and have the same sizes, they are evaluated by ONE launch (n_batches <= 8);
