@@ -191,3 +191,76 @@ def test_cloud_binary_dies_on_missing_input(host_bins, tmp_path):
     formats.build_ct_image(idx[keep], words[keep], var[keep]).tofile(tmp_path / "encrypted_data.bin")
     r = subprocess.run([str(host_bins / "cloud"), str(d / "model")], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode < 0 and "ERROR: shit happens before" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cloud_binary_model_cache(host_bins, tmp_path):
+    """models.bin: the first run compiles the .hr files and stores the device layout, the second run takes it from
+    the cache -- same bytes out; an edited .hr file changes the fingerprint, so the third run parses again (and sees the edit)."""
+    d = GOLDEN / "s1004_nr1"
+    _stage_dir(tmp_path, d)
+    shutil.copytree(d / "model", tmp_path / "model")
+    env = dict(os.environ, IDASH_HOST_TIMING="1")
+    want = (d / "encrypted_prediction.bin").read_bytes()
+    for k in range(2):
+        r = subprocess.run([str(host_bins / "cloud"), "model"], cwd=tmp_path, capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert ("compiled model taken from models.bin" in r.stderr) == (k == 1), r.stderr
+        assert (tmp_path / "encrypted_prediction.bin").read_bytes() == want
+    assert (tmp_path / "models.bin").stat().st_size > 0
+    # edit one coefficient (the Constant of the first file): the fingerprint covers size + mtime of every .hr file
+    f = sorted((tmp_path / "model").glob("*.hr"))[0]
+    lines = f.read_text().splitlines()
+    k = next(i for i, ln in enumerate(lines) if ln.startswith("Constant "))
+    lines[k] = "Constant %.1f" % (float(lines[k].split()[1]) + 3.0)
+    f.write_text("\n".join(lines) + "\n")
+    r = subprocess.run([str(host_bins / "cloud"), "model"], cwd=tmp_path, capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "compiled model taken from" not in r.stderr
+    got = (tmp_path / "encrypted_prediction.bin").read_bytes()
+    assert len(got) == len(want) and got != want
+    # ... and with the cache switched off nothing is written
+    (tmp_path / "models.bin").unlink()
+    r = subprocess.run([str(host_bins / "cloud"), "model"], cwd=tmp_path, capture_output=True, text=True, env=dict(env, IDASH_MODEL_CACHE="off"))
+    assert r.returncode == 0 and not (tmp_path / "models.bin").exists()
+    assert (tmp_path / "encrypted_prediction.bin").read_bytes() == got
+
+
+def _mid_size_run_dir(tmp_path, S=1004, T=600, G=3000, n=5, seed=77):
+    """reference keygen + encrypt + cloud on a synthetic case large enough for several tiles per GPU (3 G = 9000 rows = 141 tiles)"""
+    from idash2019_2_b200 import synth
+    if not po.have_ref() or not (po.REF_BIN / "keygen").exists():
+        pytest.skip("oracle/_ref (the compiled reference) is not available on this box")
+    tag, tgt = synth.make_positions(T, G, seed)
+    geno = synth.make_genotypes(T, S, seed, na_frac=0.01)
+    model = synth.make_model(tag, tgt, n, seed)
+    synth.write_tag_file(tmp_path / "tags.txt", tag, geno)
+    synth.write_target_file(tmp_path / "targets.txt", tgt)
+    synth.write_hr_dir(tmp_path / "model", model, tag, tgt)
+    po.run_ref_bin("keygen", [tmp_path / "targets.txt", tmp_path / "tags.txt", 1], tmp_path)
+    po.run_ref_bin("encrypt", [tmp_path / "tags.txt"], tmp_path)
+    for sub in ("ref", "b200"):
+        (tmp_path / sub).mkdir()
+        for f in ("params.bin", "keys.bin", "encrypted_data.bin"):
+            os.symlink(tmp_path / f, tmp_path / sub / f)
+    po.run_ref_bin("cloud", [tmp_path / "model"], tmp_path / "ref")
+    return (tmp_path / "ref" / "encrypted_prediction.bin").read_bytes()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gpus", ["0", "0,1", "0,1,2,3"])
+def test_cloud_binary_target_ranges_on_several_gpus(host_bins, tmp_path, gpus):
+    """IDASH_GPUS: the target range is cut at tile boundaries, every GPU copies only its part of the index-sorted input slab and
+    writes its rows of the output slab (eval/idash.cpp:779-790 is the loop being cut). Same file as the reference's
+    cloud, byte for byte -- also with one GPU, which takes the same sorted-slab + pipelined path."""
+    import torch
+    n_gpus = len(gpus.split(","))
+    if torch.cuda.device_count() < n_gpus:
+        pytest.skip(f"needs {n_gpus} GPUs")
+    want = _mid_size_run_dir(tmp_path)
+    r = subprocess.run([str(host_bins / "cloud"), str(tmp_path / "model")], cwd=tmp_path / "b200", capture_output=True, text=True,
+                       env=dict(os.environ, IDASH_HOST_TIMING="1", IDASH_GPUS=gpus, IDASH_MODEL_CACHE="off"))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert f"evaluation on {n_gpus} GPU(s)" in r.stderr, r.stderr
+    assert (tmp_path / "b200" / "encrypted_prediction.bin").read_bytes() == want
+    shutil.rmtree(tmp_path / "model", ignore_errors=True)
