@@ -44,7 +44,8 @@
 // Production schedule (measured on B200, profiles/r02_ring_schedule_sweep.txt): warp-converged MMA issue + TMEM stage handed back
 // after the epilogue's last tcgen05.ld (tune 8 | 64) + x16 TMEM loads (EPI 1): 0.470 / 0.507 / 0.602 / 0.537 ms at neighbors 5 / 20 /
 // 50 / NUM_REGIONS = 3, against 0.480 / 0.514 / 0.634 / 0.552 ms without the last two.
-#define RG_TUNE_DEFAULT (8u | 64u)               // RingParams::tune of the production library
+#define RG_TUNE_DEFAULT (8u | 64u | 128u)        // RingParams::tune of the production library: NUM_REGIONS = 1 ...
+#define RG_TUNE_ROT (8u | 64u)                   // ... and NUM_REGIONS > 1 (weight-stationary MMAs measured slower there: 0.58 vs 0.54 ms)
 #define RG_EPI_DEFAULT 1                         // ... and its epilogue schedule (template parameter EPI of the kernel)
 
 struct RingParams {
@@ -84,7 +85,7 @@ struct RingParams {
                                    // coefficient chunk of a K step is read from shared memory once, tcgen05.mma.ws + collector buffer); host side: 256 / 512 pick
                                    // the kernel's EPI template parameter (x16 loads / burst epilogue)
     uint32_t knockout;             // profiling aid (IDASH_B200_KNOCKOUT, results are wrong when non-zero):
-                                   // 1 no MMAs, 2 no output stores, 4 no epilogue TMEM loads, 8 no input loads, 16 no zero fill
+                                   // 1 no MMAs, 2 no output stores, 4 no epilogue TMEM loads, 8 no input loads, 16 no zero fill, 32 no bias / mask
 };
 
 __host__ __device__ constexpr uint32_t ring_smem_bytes(uint32_t n_slots, uint32_t n_bchunks, uint32_t max_chunk_tiles) {
@@ -187,7 +188,7 @@ __device__ __forceinline__ void progress_wait(const uint32_t *ctr, uint32_t at_l
 __device__ unsigned long long g_ring_trace[RG_TRACE_TILES * RG_TRACE_EVENTS];
 #define RG_TRACE(ev, it_)                                                                                     \
     do {                                                                                                      \
-        if (p.trace_cta == blockIdx.x + 1u && (it_) >= 64u && (it_) < 64u + RG_TRACE_TILES)                     \
+        if (k_trace == blockIdx.x + 1u && (it_) >= 64u && (it_) < 64u + RG_TRACE_TILES)                     \
             g_ring_trace[((it_) - 64u) * RG_TRACE_EVENTS + (ev)] = clock64();                                    \
     } while (0)
 
@@ -212,7 +213,7 @@ __device__ __forceinline__ RingTile ring_hdr(const uint32_t *hdr_s, uint32_t i) 
 
 #define RG_TRACE_V(ev, it_, val)                                                                             \
     do {                                                                                                      \
-        if (p.trace_cta == blockIdx.x + 1u && (it_) >= 64u && (it_) < 64u + RG_TRACE_TILES)                     \
+        if (k_trace == blockIdx.x + 1u && (it_) >= 64u && (it_) < 64u + RG_TRACE_TILES)                     \
             g_ring_trace[((it_) - 64u) * RG_TRACE_EVENTS + (ev)] = (unsigned long long) (val);                    \
     } while (0)
 
@@ -297,37 +298,97 @@ __device__ __forceinline__ bool ring_epilogue_w16(uint32_t taddr, uint8_t *base_
     return release_bar != nullptr;
 }
 
-// Burst variant (EPI = 2): ALL accumulators of the warp's 32 rows are pulled out of TMEM and recombined first (four rounds of
-// four x8 loads, 32 result registers), the stage is handed back, and only then are the 32 rows stored. The TMEM stage is held for
-// the loads only, not for the stores (~1300-1600 cycles under HBM back-pressure), and the loads -- which slow down concurrently
-// running MMAs by ~1.5x (tools/tmem_ld_rate.cu) -- are over quickly. 32 + 32 data registers.
+// Packed burst variant (EPI = 2): ALL accumulators of the warp's 32 rows are pulled out of TMEM with ONE round of loads, the
+// stage is handed back, and only then are the 32 rows recombined and stored. With the two-group schedule above the stage is
+// released after the first 16 rows have been stored -- under HBM back-pressure ~1000+ cycles after the tile completed -- and on
+// wide bands, where the tensor pipe is as busy as HBM, the MMAs of tile t + 2 wait for exactly that (2 TMEM stages; trace:
+// profiles/r02_trace_ring_n50.txt). Registers: out = P0 + 2^8 P1 + 2^16 P2 + 2^24 P3 mod 2^32 needs all of P0, 24 bits of P1, 16 of P2
+// and 8 of P3, so P2 and P3 are read with .pack::16b (the low halves of two adjacent columns in one register): 32 + 32 + 16 + 16 =
+// 96 data registers instead of 128.
+__device__ __forceinline__ void tc_ld16_pack(uint32_t taddr, uint32_t (&v)[16]) {     // 32 columns, low 16 bits each
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
 template <bool FAST, uint32_t STRIDE, bool BIAS, bool MASK>
 __device__ __forceinline__ bool ring_epilogue_burst(uint32_t taddr, uint8_t *base_lane, uint64_t ptr_own, uint32_t bias_own, uint32_t bias_flag,
                                                     uint32_t lane_off, uint32_t knockout, uint32_t keep_mask, uint64_t *release_bar) {
     if (knockout & 4u) return false;
-    uint32_t out[32];
-#pragma unroll
-    for (uint32_t g = 0; g < 4; ++g) {
-        uint32_t v[4][8];
-        ring_ld_chunk(taddr + g * 8u, v[0], v[1], v[2], v[3]);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (uint32_t c = 0; c < 8; ++c) out[g * 8u + c] = ((v[3][c] * 256u + v[2][c]) * 256u + v[1][c]) * 256u + v[0][c];
-    }
+    uint32_t p0[2][16], p1[2][16], p2[16], p3[16];
+    tc_ld16(taddr, p0[0]);
+    tc_ld16(taddr + 16u, p0[1]);
+    tc_ld16(taddr + TC_TN, p1[0]);
+    tc_ld16(taddr + TC_TN + 16u, p1[1]);
+    tc_ld16_pack(taddr + 2 * TC_TN, p2);
+    tc_ld16_pack(taddr + 3 * TC_TN, p3);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     if (release_bar) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if ((threadIdx.x & 31u) == 0) mbar_arrive(release_bar);
     }
 #pragma unroll
-    for (uint32_t n = 0; n < 32; ++n)
-        ring_emit<FAST, STRIDE, BIAS, MASK>(n, out[n], base_lane, ptr_own, bias_own, bias_flag, lane_off, knockout, keep_mask);
+    for (uint32_t n = 0; n < 32; ++n) {
+        const uint32_t q2 = p2[n >> 1], q3 = p3[n >> 1];
+        // column n of P2 / P3: low half of the pair register for even n, high half for odd n
+        const uint32_t hi = (n & 1u) ? (q2 & 0xFFFF0000u) + ((q3 & 0x00FF0000u) << 8) : (q2 << 16) + (q3 << 24);
+        const uint32_t x = p0[n >> 4][n & 15u] + (p1[n >> 4][n & 15u] << 8) + hi;
+        ring_emit<FAST, STRIDE, BIAS, MASK>(n, x, base_lane, ptr_own, bias_own, bias_flag, lane_off, knockout, keep_mask);
+    }
+    return release_bar != nullptr;
+}
+
+// Overlapped x16 variant (EPI = 3): as EPI = 1, but the loads of the second group of 16 rows are issued BEFORE the first group is
+// stored (the first group is recombined into 16 registers first, so 16 + 64 data registers are live): the TMEM round trip of the
+// second group -- exposed in EPI = 1, ~150-300 cycles per tile in which the warp issues nothing -- hides behind the 16 stores.
+__device__ __forceinline__ void tc_ld8_pack(uint32_t taddr, uint32_t (&v)[8]) {     // 16 columns, low 16 bits each
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
+template <bool FAST, uint32_t STRIDE, bool BIAS, bool MASK>
+__device__ __forceinline__ bool ring_epilogue_w16o(uint32_t taddr, uint8_t *base_lane, uint64_t ptr_own, uint32_t bias_own, uint32_t bias_flag,
+                                                   uint32_t lane_off, uint32_t knockout, uint32_t keep_mask, uint64_t *release_bar) {
+    if (knockout & 4u) return false;
+    uint32_t x0[16];
+    {
+        uint32_t v[4][16];
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) tc_ld16(taddr + j * TC_TN, v[j]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (uint32_t c = 0; c < 16; ++c) x0[c] = ((v[3][c] * 256u + v[2][c]) * 256u + v[1][c]) * 256u + v[0][c];
+    }
+    // second group: P2 / P3 packed (16 + 16 + 8 + 8 = 48 registers beside the 16 recombined words of the first group)
+    uint32_t p0[16], p1[16], p2[8], p3[8];
+    tc_ld16(taddr + 16u, p0);
+    tc_ld16(taddr + 16u + TC_TN, p1);
+    tc_ld8_pack(taddr + 16u + 2 * TC_TN, p2);
+    tc_ld8_pack(taddr + 16u + 3 * TC_TN, p3);
+#pragma unroll
+    for (uint32_t c = 0; c < 16; ++c)
+        ring_emit<FAST, STRIDE, BIAS, MASK>(c, x0[c], base_lane, ptr_own, bias_own, bias_flag, lane_off, knockout, keep_mask);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (release_bar) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if ((threadIdx.x & 31u) == 0) mbar_arrive(release_bar);
+    }
+#pragma unroll
+    for (uint32_t c = 0; c < 16; ++c) {
+        const uint32_t q2 = p2[c >> 1], q3 = p3[c >> 1];
+        const uint32_t hi = (c & 1u) ? (q2 & 0xFFFF0000u) + ((q3 & 0x00FF0000u) << 8) : (q2 << 16) + (q3 << 24);
+        const uint32_t x = p0[c] + (p1[c] << 8) + hi;
+        ring_emit<FAST, STRIDE, BIAS, MASK>(16u + c, x, base_lane, ptr_own, bias_own, bias_flag, lane_off, knockout, keep_mask);
+    }
     return release_bar != nullptr;
 }
 
 template <int EPI, bool FAST, uint32_t STRIDE, bool BIAS, bool MASK = false>
 __device__ __forceinline__ bool ring_epilogue(uint32_t taddr, uint8_t *base_lane, uint64_t ptr_own, uint32_t bias_own, uint32_t bias_flag,
                                               uint32_t lane_off, uint32_t knockout, uint32_t keep_mask, uint64_t *release_bar) {
+    if (EPI == 3) return ring_epilogue_w16o<FAST, STRIDE, BIAS, MASK>(taddr, base_lane, ptr_own, bias_own, bias_flag, lane_off, knockout, keep_mask, release_bar);
     if (EPI == 2) return ring_epilogue_burst<FAST, STRIDE, BIAS, MASK>(taddr, base_lane, ptr_own, bias_own, bias_flag, lane_off, knockout, keep_mask, release_bar);
     if (EPI == 1) return ring_epilogue_w16<FAST, STRIDE, BIAS, MASK>(taddr, base_lane, ptr_own, bias_own, bias_flag, lane_off, knockout, keep_mask, release_bar);
     if (knockout & 4u) return false;
@@ -361,6 +422,17 @@ __device__ __forceinline__ void stg128_zero_stream(void *p) {
 template <bool ROT, bool BATCHED, int EPI>
 __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    // The production library compiles ONE schedule: the switches are constants there and every other path (knock-outs, tracing, the
+    // alternative wait / issue variants) is dead code the compiler removes -- the kernel is ~6500 instructions with them, and five
+    // roles running different parts of it share the SM's instruction cache.
+#ifdef IDASH_B200_PROFILE
+    const uint32_t k_tune = p.tune, k_knockout = p.knockout, k_trace = p.trace_cta;
+#else
+    // (NUM_REGIONS > 1 keeps the schedule word in a register: with it folded, ptxas allocates the rotated-staging producers -- five
+    // 128-bit loads per feature, two blocks in flight -- differently and spills 76 bytes at the 128-register cap, which costs 60 %)
+    const uint32_t k_tune = ROT ? p.tune : RG_TUNE_DEFAULT;
+    constexpr uint32_t k_knockout = 0u, k_trace = 0u;
+#endif
     __shared__ __align__(8) uint64_t a_full[RG_MAX_SLOTS], b_full[RG_BBARS], t_full[2], t_empty[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ uint32_t tiles_done_s;       // tiles of this CTA whose MMAs are complete
@@ -390,7 +462,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
         hdr_s[i] = ring_pack_hdr(p.tiles + p.tile_base + (v - b * p.n_tiles)) + (b << RG_BATCH_SHIFT);
     }
     const uint32_t w_slice = slice * 128u;
-    const bool is_b = (w_slice & POLY_N) != 0;
+    const bool is_b = (w_slice & POLY_N) != 0 && !(k_knockout & 32u);     // knock-out 32: every slice runs the (cheaper) epilogue of polynomial a
     const uint32_t i_slice = w_slice & (POLY_N - 1);
 
     if (tid == 0) {
@@ -419,7 +491,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
         const uint32_t bias_flag = (is_b && i_slice + word_in_slice < p.S) ? 1u : 0u;
         const uint32_t keep_mask = (is_b && i_slice + word_in_slice >= p.RS) ? 0u : 0xFFFFFFFFu;
         const bool records = p.out.records != 0;
-        const bool early = (p.tune & 64u) != 0u;
+        const bool early = (k_tune & 64u) != 0u;
         // NUM_REGIONS > 1: the 16 - n_slices slices that lie entirely in b[RS..N) are not computed by anyone; the epilogue warps
         // of the n_slices computing CTAs zero-fill them, 512 bytes (one slice of one row) per warp instruction, tile by tile, so
         // that all 8 KB of an output ciphertext are still written at about the same time
@@ -459,7 +531,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                     row_q[u] = __ldg(p.tile_rows + (uint64_t) tt * TC_TN + col_base + lane);
                     bias_q[u] = __ldg(p.tile_bias + (uint64_t) tt * TC_TN + col_base + lane);
                 }
-                if (p.tune & 1u) mbar_wait(&t_full[st], (it >> 1) & 1u); else mbar_spin(&t_full[st], (it >> 1) & 1u);
+                if (k_tune & 1u) mbar_wait(&t_full[st], (it >> 1) & 1u); else mbar_spin(&t_full[st], (it >> 1) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (tid == 0) RG_TRACE(6, it);
                 const uint32_t taddr = tmem + ((quad * 32u) << 16) + st * 4u * TC_TN + col_base;
@@ -467,21 +539,21 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                 bool arrived;
                 if (fast) {
                     if (records) {
-                        if (is_b) arrived = ring_epilogue<EPI, true, IDASH_B200_RECORD_BYTES, true, ROT>(taddr, base_lane, 0, bias_own, bias_flag, lane_off, p.knockout, keep_mask, rel);
-                        else arrived = ring_epilogue<EPI, true, IDASH_B200_RECORD_BYTES, false>(taddr, base_lane, 0, 0, 0, lane_off, p.knockout, 0xFFFFFFFFu, rel);
+                        if (is_b) arrived = ring_epilogue<EPI, true, IDASH_B200_RECORD_BYTES, true, ROT>(taddr, base_lane, 0, bias_own, bias_flag, lane_off, k_knockout, keep_mask, rel);
+                        else arrived = ring_epilogue<EPI, true, IDASH_B200_RECORD_BYTES, false>(taddr, base_lane, 0, 0, 0, lane_off, k_knockout, 0xFFFFFFFFu, rel);
                     } else {
-                        if (is_b) arrived = ring_epilogue<EPI, true, IDASH_B200_CT_BYTES, true, ROT>(taddr, base_lane, 0, bias_own, bias_flag, lane_off, p.knockout, keep_mask, rel);
-                        else arrived = ring_epilogue<EPI, true, IDASH_B200_CT_BYTES, false>(taddr, base_lane, 0, 0, 0, lane_off, p.knockout, 0xFFFFFFFFu, rel);
+                        if (is_b) arrived = ring_epilogue<EPI, true, IDASH_B200_CT_BYTES, true, ROT>(taddr, base_lane, 0, bias_own, bias_flag, lane_off, k_knockout, keep_mask, rel);
+                        else arrived = ring_epilogue<EPI, true, IDASH_B200_CT_BYTES, false>(taddr, base_lane, 0, 0, 0, lane_off, k_knockout, 0xFFFFFFFFu, rel);
                     }
                 } else {
-                    arrived = ring_epilogue<EPI, false, 0, true, ROT>(taddr, nullptr, ptr_own, bias_own, bias_flag, lane_off, p.knockout, keep_mask, rel);
+                    arrived = ring_epilogue<EPI, false, 0, true, ROT>(taddr, nullptr, ptr_own, bias_own, bias_flag, lane_off, k_knockout, keep_mask, rel);
                 }
                 if (!arrived) {
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&t_empty[st]);      // one arrival per epilogue warp
                 }
-                if (ROT && zero_units && !(p.knockout & (2u | 16u))) {
+                if (ROT && zero_units && !(k_knockout & (2u | 16u))) {
                     // zero fill of b[128 n_slices - 1024 .. 1024) of this tile's rows: unit u = (tile row u / n_zero_seg, segment u % n_zero_seg)
                     const uint32_t row_lane0 = __shfl_sync(0xFFFFFFFFu, row, 0);       // caller row of tile row col_base
                     const uint32_t tt = real_tile(t);
@@ -504,7 +576,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
         // they get one stream each. Both warps walk every tile to keep the ring state, but wait and issue only for their own.
         const uint32_t q = warp == RG_WARP_MMA2 ? 1u : 0u;
         const uint32_t n_slots = p.n_slots, n_bchunks = p.n_bchunks;
-        const bool fifo = (p.tune & 32u) != 0u;
+        const bool fifo = (k_tune & 32u) != 0u;
         const uint64_t da_base = tc_desc(smem_u32(sA), TC_A_LBO, TC_A_SBO);
         const uint64_t db_base = tc_desc(smem_u32(sB), TC_B_LBO, TC_B_SBO);
         uint32_t it = 0;
@@ -554,6 +626,13 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                 const bool order_lane = fifo && lane == 31u && it != 0u;
                 uint32_t done = (bar || order_lane) ? 0u : 1u;
                 long long t_done = 0;
+                if (k_tune & 1024u) {
+                    // every lane blocks on its own barrier with try_wait (the hardware suspends the thread until the phase completes or a
+                    // time limit expires): no polling granularity between "TMEM stage released" and the first MMA of the next tile
+                    if (bar) mbar_wait(bar, par);
+                    if (k_trace) t_done = clock64();
+                    __syncwarp();
+                } else
                 for (;;) {
                     if (!done) {
                         if (order_lane) {
@@ -563,12 +642,12 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                         } else {
                             done = mbar_test(bar_addr, par);
                         }
-                        if (done && p.trace_cta) t_done = clock64();
+                        if (done && k_trace) t_done = clock64();
                     }
                     if (__all_sync(0xFFFFFFFFu, done)) break;
-                    if (!(p.tune & 4u)) __nanosleep(40);      // polling hot next to running MMAs slows them down (measured)
+                    if (!(k_tune & 4u)) __nanosleep(40);      // polling hot next to running MMAs slows them down (measured)
                 }
-                if (p.trace_cta) {
+                if (k_trace) {
                     if (lane == 0) { RG_TRACE_V(1, it, t_done); RG_TRACE(4, it); }
                     if (lane == 1) RG_TRACE_V(2, it, t_done);
                     if (lane == 2) RG_TRACE_V(3, it, t_done);
@@ -579,7 +658,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
             if (next_slot >= n_slots) { next_slot -= n_slots; next_par ^= 1u; }
             if (mine) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (p.tune & 8u) {
+            if (k_tune & 8u) {
                 // warp-converged issue: every operand is made provably warp-uniform (shuffle from lane 0), so that the
                 // compiler feeds the MMA's uniform-register operands without a per-instruction broadcast loop
                 const uint32_t nb_u = __shfl_sync(0xFFFFFFFFu, T.nb, 0);
@@ -587,8 +666,8 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                 const uint32_t d0 = tmem_u + st * 4u * TC_TN;
                 uint32_t bchunk = __shfl_sync(0xFFFFFFFFu, bpos, 0);
                 if (lane == 0) RG_TRACE(7, it);
-                if (!(p.knockout & 1u)) {
-                    if (p.tune & 128u) {
+                if (!(k_knockout & 1u)) {
+                    if (k_tune & 128u) {
                         for (uint32_t ks = 0; ks < nb_u; ++ks) {
                             const uint64_t da = da_base + (uint64_t) ((aslot * RG_BLOCK_BYTES) >> 4), db = db_base + (uint64_t) ((bchunk * TC_B_CHUNK) >> 4);
                             if (q) tc_mma_kstep_ws_p<1>(d0, da, RG_PLANE_BYTES >> 4, db, ks == 0, leader);
@@ -614,7 +693,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
             if (lane == 0) {
                 const uint32_t d0 = tmem + st * 4u * TC_TN;
                 uint32_t aslot = first_slot, bchunk = bpos;
-                if (!(p.knockout & 1u)) {
+                if (!(k_knockout & 1u)) {
                     for (uint32_t ks = 0; ks < T.nb; ++ks) {
                         tc_mma_kstep(d0, da_base + (uint64_t) ((aslot * RG_BLOCK_BYTES) >> 4), RG_PLANE_BYTES >> 4,
                                      db_base + (uint64_t) ((bchunk * TC_B_CHUNK) >> 4), ks == 0);
@@ -654,29 +733,35 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                     const uint4 hb = __ldg(reinterpret_cast<const uint4 *>(p.tiles + p.tile_base));
                     b_off = (uint64_t) hb.z | ((uint64_t) hb.w << 32);
                 }
-                // ring space: chunks of tiles whose MMAs are complete are free again
-                while (loaded + T.nb - freed > p.n_bchunks) {
-                    progress_wait(&tiles_done_s, done_it + 1u);
-                    freed += ring_hdr(hdr_s, done_it).nb;
-                    ++done_it;
-                }
                 // the barrier was last used by tile it - 8: its MMAs (hence its waiters) must be past it
                 if (it >= RG_BBARS) progress_wait(&tiles_done_s, it - RG_BBARS + 1u);
                 const uint32_t bytes = T.nb * TC_B_CHUNK;
                 uint64_t *const bar = &b_full[it & (RG_BBARS - 1u)];
                 RG_TRACE(10, it);
                 mbar_arrive_expect_tx(bar, bytes);
-                const uint32_t first = min(T.nb, p.n_bchunks - cpos) * TC_B_CHUNK;
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(smem_u32(sB + cpos * TC_B_CHUNK)), "l"(p.tile_coef + b_off), "r"(first), "r"(smem_u32(bar))
-                             : "memory");
-                if (first < bytes)
+                // Ring space is admitted chunk by chunk: whatever part of the image fits is copied NOW and the rest as soon as earlier
+                // tiles complete. (Waiting for room for the whole image put its copy -- ~1800 cycles for 28 KB at neighbors = 50, where
+                // three images are one chunk more than the ring holds -- on the critical path of every tile.)
+                uint32_t done_chunks = 0;
+                while (done_chunks < T.nb) {
+                    uint32_t room = p.n_bchunks - (loaded - freed);
+                    while (room == 0u) {
+                        progress_wait(&tiles_done_s, done_it + 1u);
+                        freed += ring_hdr(hdr_s, done_it).nb;
+                        ++done_it;
+                        room = p.n_bchunks - (loaded - freed);
+                    }
+                    // free chunks that are already known to be free (no waiting): take as much as possible in one copy
+                    const uint32_t n_now = min(min(T.nb - done_chunks, room), p.n_bchunks - cpos);
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(smem_u32(sB)), "l"(p.tile_coef + b_off + first), "r"(bytes - first), "r"(smem_u32(bar))
+                                 ::"r"(smem_u32(sB + cpos * TC_B_CHUNK)), "l"(p.tile_coef + b_off + (uint64_t) done_chunks * TC_B_CHUNK),
+                                   "r"(n_now * TC_B_CHUNK), "r"(smem_u32(bar))
                                  : "memory");
-                cpos += T.nb;
-                if (cpos >= p.n_bchunks) cpos -= p.n_bchunks;
-                loaded += T.nb;
+                    done_chunks += n_now;
+                    loaded += n_now;
+                    cpos += n_now;
+                    if (cpos >= p.n_bchunks) cpos -= p.n_bchunks;
+                }
                 b_off += bytes;
                 // The images are contiguous, so the ones a few tiles ahead are pulled into L2 now: a copy that starts when ring space
                 // frees up then pays the L2 latency, not HBM's (measured at neighbors = 50: 0.673 -> 0.640 ms).
@@ -700,7 +785,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                 uint32_t rb, re;
                 walk.advance(T, Tn, t + 1 < t_end, rb, re);
                 freed += re - rb;
-                if (p.tune & 2u) mbar_wait(&t_full[it & 1u], (it >> 1) & 1u); else mbar_spin(&t_full[it & 1u], (it >> 1) & 1u);
+                if (k_tune & 2u) mbar_wait(&t_full[it & 1u], (it >> 1) & 1u); else mbar_spin(&t_full[it & 1u], (it >> 1) & 1u);
                 RG_TRACE(9, it);
                 progress_publish(&blocks_freed_s, freed);
                 progress_publish(&tiles_done_s, it + 1u);
@@ -748,9 +833,9 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                 const uint32_t ct = ROT ? f / p.NR : f;
                 uint32_t sl = NO_SLOT;
                 if (ct < p.n_ct_slots) sl = p.slot_of_ct ? __ldg(p.slot_of_ct + ct) : ct;
-                if (p.knockout & 8u) sl = NO_SLOT;
+                if (k_knockout & 8u) sl = NO_SLOT;
                 if (sl == NO_SLOT) {
-                    if (sl == NO_SLOT && ((used_word >> k) & 1u) && !(p.knockout & 8u)) atomicOr(p.status, 1);
+                    if (sl == NO_SLOT && ((used_word >> k) & 1u) && !(k_knockout & 8u)) atomicOr(p.status, 1);
 #pragma unroll
                     for (int q = 0; q < NW; ++q) w[h][q] = make_uint4(0, 0, 0, 0);
                 } else if (!ROT) {

@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(128) cloud_eval_kernel(const CloudParams p) {
 
 // The production library carries one epilogue schedule; the profiling build all of them (IDASH_B200_TUNE bits 256 / 512).
 #ifdef IDASH_B200_PROFILE
-#define RG_EPI_VARIANTS 2
+#define RG_EPI_VARIANTS 4
 #else
 #define RG_EPI_VARIANTS 1
 #endif
@@ -204,6 +204,8 @@ static ring_kernel_t ring_kernel_pick(bool rot, bool batched) {
 }
 static ring_kernel_t ring_kernel_fn(bool rot, bool batched, int epi) {
 #ifdef IDASH_B200_PROFILE
+    if (epi == 3) return ring_kernel_pick<3>(rot, batched);
+    if (epi == 2) return ring_kernel_pick<2>(rot, batched);
     if (epi == 1) return ring_kernel_pick<1>(rot, batched);
     return ring_kernel_pick<0>(rot, batched);
 #else
@@ -831,14 +833,14 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
         if (const char *cp = debug_env("IDASH_B200_COEF_PREFETCH")) p.coef_prefetch = (uint32_t) atoi(cp);
         p.status = c->d_status;
         if (const char *ko = debug_env("IDASH_B200_KNOCKOUT")) p.knockout = (uint32_t) atoi(ko);
-        p.tune = RG_TUNE_DEFAULT;
+        p.tune = L->NR != 1 ? RG_TUNE_ROT : RG_TUNE_DEFAULT;
         if (const char *tu = debug_env("IDASH_B200_TUNE")) p.tune = (uint32_t) atoi(tu);
         if (const char *tr = debug_env("IDASH_B200_TRACE")) p.trace_cta = (uint32_t) atoi(tr) + 1u;
         const size_t ring_smem = ring_smem_bytes(p.n_slots, p.n_bchunks, p.max_chunk_tiles);
         const dim3 grid(p.n_slices * p.n_chunks);
         int epi = RG_EPI_DEFAULT;
 #ifdef IDASH_B200_PROFILE
-        if (debug_env("IDASH_B200_TUNE")) epi = (p.tune & 256u) ? 1 : 0;
+        if (debug_env("IDASH_B200_TUNE")) epi = (p.tune & 2048u) ? 3 : (p.tune & 512u) ? 2 : (p.tune & 256u) ? 1 : 0;
 #endif
         ring_kernel_fn(L->NR != 1, n_batches > 1, epi)<<<grid, RG_THREADS, ring_smem, st>>>(p);
         if (p.trace_cta) {   // debugging only: dump the timeline of the traced CTA to the file named by IDASH_B200_TRACE_FILE

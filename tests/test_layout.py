@@ -280,3 +280,19 @@ def test_read_hr_sscanf_semantics(tmp_path):
     f = tmp_path / "1_0.hr"
     f.write_text("Constant -107.0\n16050075_1 23.9\n16050075_2   -0.7\n16050115_0 12\n16050075_1 5.0\n")
     assert formats.read_hr(f) == {"Constant": -107, "16050075_1": 5, "16050075_2": 0, "16050115_0": 12}
+
+
+def test_ring_kernels_do_not_spill(built_lib):
+    """The persistent ring kernel runs at the 128-register cap (512 threads, one CTA per SM). A spill there is not a small cost:
+    local-memory traffic queues behind the epilogue's store backlog and the kernel gets 60 % slower (measured).
+    ptxas' log of the in-tree build must therefore show no spill for any instantiation of cloud_ring_kernel."""
+    log = (ROOT / "idash2019_2_b200" / "lib" / "ptxas.log")
+    if not log.exists():
+        pytest.skip("the library was not built here (no ptxas log)")
+    text = log.read_text()
+    entries = re.split(r"ptxas info\s+: Compiling entry function '", text)[1:]
+    ring = [e for e in entries if e.startswith("_Z17cloud_ring_kernel")]
+    assert ring, "no cloud_ring_kernel instantiation in the ptxas log"
+    for e in ring:
+        m = re.search(r"(\d+) bytes spill stores, (\d+) bytes spill loads", e)
+        assert m and m.group(1) == "0" and m.group(2) == "0", e.splitlines()[0] + ": " + (m.group(0) if m else "no spill line")
