@@ -16,6 +16,8 @@ import os
 PKG = Path(__file__).resolve().parent
 # tools/ (tuning sweeps, knock-out and trace runs) load the profiling build, which honours the IDASH_B200_* debug variables
 LIB_PATH = PKG / "lib" / ("libidash_b200_prof.so" if os.environ.get("IDASH_B200_USE_PROFILE_LIB") == "1" else "libidash_b200.so")
+if os.environ.get("IDASH_B200_LIB"):          # tools/: A/B timing of two builds of the library in one GPU session
+    LIB_PATH = Path(os.environ["IDASH_B200_LIB"]).resolve()
 
 N = 1024
 CT_WORDS = 2048

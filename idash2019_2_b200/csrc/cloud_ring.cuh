@@ -38,6 +38,8 @@
 #define RG_PLANE_BYTES (4u * TC_A_LBO)
 #define RG_MAX_SLOTS 9
 #define RG_BBARS 8u                              // per-tile "coefficients landed" barriers (tile it uses b_full[it % 8])
+#define RG_META_STAGES RG_BBARS                  // per-tile metadata ring: tile it uses record it % 8 (caller rows + Constants, 512 bytes)
+#define RG_META_BYTES (RG_META_STAGES * 8u * TC_TN)
 #define RG_MAX_BATCHES 8u
 #define RG_BATCH_SHIFT 14u                       // input blocks per batch < 2^14 (features < 524 288) in a batched launch
 #define RG_SMEM_MAX (226u * 1024u)               // dynamic shared memory budget of the one resident CTA
@@ -64,6 +66,7 @@ struct RingParams {
     uint32_t n_bchunks;            // coefficient ring: 4096-byte chunks (one 32-feature K step each), a tile takes K / 32 of them
     uint64_t coef_bytes;           // size of the coefficient image array (bound for the L2 prefetch)
     uint32_t coef_prefetch;        // the loader prefetches the images this many tiles ahead into L2 (0 = off)
+    uint32_t meta_off;             // byte offset of the ring of per-tile metadata records (RG_META_STAGES x {rows[64], Constant[64]})
     uint32_t hdr_off;              // byte offset (dynamic shared memory) of the CTA's tile-header table
     uint32_t max_chunk_tiles;      // capacity of that table (tiles per chunk, rounded up)
     CtView in, out;
@@ -89,7 +92,7 @@ struct RingParams {
 };
 
 __host__ __device__ constexpr uint32_t ring_smem_bytes(uint32_t n_slots, uint32_t n_bchunks, uint32_t max_chunk_tiles) {
-    return n_slots * RG_BLOCK_BYTES + n_bchunks * TC_B_CHUNK + 4u * max_chunk_tiles;
+    return n_slots * RG_BLOCK_BYTES + n_bchunks * TC_B_CHUNK + RG_META_BYTES + 4u * max_chunk_tiles;
 }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -256,11 +259,21 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
                  : "r"(taddr));
 }
 
+// Constants of four consecutive tile rows from the tile's metadata record in shared memory (one broadcast 128-bit load; the record is
+// brought in by the coefficient loader's bulk copies, so the epilogue issues no global load that could queue behind its own stores)
+template <bool BIAS>
+__device__ __forceinline__ uint4 ring_bias4(uint32_t bias_addr, uint32_t n) {
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (BIAS) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(bias_addr + 4u * n));
+    return q;
+}
+__device__ __forceinline__ uint32_t ring_q(const uint4 &q, uint32_t i) { return i == 0 ? q.x : i == 1 ? q.y : i == 2 ? q.z : q.w; }
+
 // One recombined output word -> its row (shared by the two load widths below)
 template <bool FAST, uint32_t STRIDE, bool BIAS, bool MASK>
-__device__ __forceinline__ void ring_emit(uint32_t n, uint32_t x, uint8_t *base_lane, uint64_t ptr_own, uint32_t bias_own, uint32_t bias_flag,
+__device__ __forceinline__ void ring_emit(uint32_t n, uint32_t x, uint8_t *base_lane, uint64_t ptr_own, uint32_t bias_n, uint32_t bias_flag,
                                           uint32_t lane_off, uint32_t knockout, uint32_t keep_mask) {
-    if (BIAS) x += __shfl_sync(0xFFFFFFFFu, bias_own, n) * bias_flag;
+    if (BIAS) x += bias_n * bias_flag;          // bias_flag = 2^18 (ONE_IN_T32) on the words b[0..S), else 0 (idash.cpp:805-810)
     if (MASK) x &= keep_mask;                                                  // b[RS..N) = 0 (idash.cpp:839-841)
     if (knockout & 2u) { if (x == 0x9E3779B9u && bias_flag == 77u) stg32_stream(base_lane, x); return; }
     if (FAST) {
@@ -283,6 +296,11 @@ __device__ __forceinline__ bool ring_epilogue_w16(uint32_t taddr, uint8_t *base_
     for (uint32_t g = 0; g < 2; ++g) {
 #pragma unroll
         for (uint32_t j = 0; j < 4; ++j) tc_ld16(taddr + g * 16u + j * TC_TN, v[j]);
+        // the group's 16 Constants come in while the TMEM loads are in flight (four broadcast 128-bit loads; on wide bands the MMAs'
+        // operand fetch saturates the shared-memory pipe and a load issued right before its use stalls the stores behind it)
+        uint4 bq[4];
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k) bq[k] = ring_bias4<BIAS>(bias_own, g * 16u + 4u * k);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (g == 1 && release_bar) {
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -292,7 +310,7 @@ __device__ __forceinline__ bool ring_epilogue_w16(uint32_t taddr, uint8_t *base_
 #pragma unroll
         for (uint32_t c = 0; c < 16; ++c) {
             const uint32_t x = ((v[3][c] * 256u + v[2][c]) * 256u + v[1][c]) * 256u + v[0][c];
-            ring_emit<FAST, STRIDE, BIAS, MASK>(g * 16u + c, x, base_lane, ptr_own, bias_own, bias_flag, lane_off, knockout, keep_mask);
+            ring_emit<FAST, STRIDE, BIAS, MASK>(g * 16u + c, x, base_lane, ptr_own, ring_q(bq[c >> 2], c & 3u), bias_flag, lane_off, knockout, keep_mask);
         }
     }
     return release_bar != nullptr;
@@ -329,12 +347,16 @@ __device__ __forceinline__ bool ring_epilogue_burst(uint32_t taddr, uint8_t *bas
         if ((threadIdx.x & 31u) == 0) mbar_arrive(release_bar);
     }
 #pragma unroll
-    for (uint32_t n = 0; n < 32; ++n) {
-        const uint32_t q2 = p2[n >> 1], q3 = p3[n >> 1];
-        // column n of P2 / P3: low half of the pair register for even n, high half for odd n
-        const uint32_t hi = (n & 1u) ? (q2 & 0xFFFF0000u) + ((q3 & 0x00FF0000u) << 8) : (q2 << 16) + (q3 << 24);
-        const uint32_t x = p0[n >> 4][n & 15u] + (p1[n >> 4][n & 15u] << 8) + hi;
-        ring_emit<FAST, STRIDE, BIAS, MASK>(n, x, base_lane, ptr_own, bias_own, bias_flag, lane_off, knockout, keep_mask);
+    for (uint32_t n4 = 0; n4 < 32; n4 += 4) {
+        const uint4 bq = ring_bias4<BIAS>(bias_own, n4);
+#pragma unroll
+        for (uint32_t n = n4; n < n4 + 4; ++n) {
+            const uint32_t q2 = p2[n >> 1], q3 = p3[n >> 1];
+            // column n of P2 / P3: low half of the pair register for even n, high half for odd n
+            const uint32_t hi = (n & 1u) ? (q2 & 0xFFFF0000u) + ((q3 & 0x00FF0000u) << 8) : (q2 << 16) + (q3 << 24);
+            const uint32_t x = p0[n >> 4][n & 15u] + (p1[n >> 4][n & 15u] << 8) + hi;
+            ring_emit<FAST, STRIDE, BIAS, MASK>(n, x, base_lane, ptr_own, ring_q(bq, n - n4), bias_flag, lane_off, knockout, keep_mask);
+        }
     }
     return release_bar != nullptr;
 }
@@ -367,8 +389,12 @@ __device__ __forceinline__ bool ring_epilogue_w16o(uint32_t taddr, uint8_t *base
     tc_ld8_pack(taddr + 16u + 2 * TC_TN, p2);
     tc_ld8_pack(taddr + 16u + 3 * TC_TN, p3);
 #pragma unroll
-    for (uint32_t c = 0; c < 16; ++c)
-        ring_emit<FAST, STRIDE, BIAS, MASK>(c, x0[c], base_lane, ptr_own, bias_own, bias_flag, lane_off, knockout, keep_mask);
+    for (uint32_t c4 = 0; c4 < 16; c4 += 4) {
+        const uint4 bq = ring_bias4<BIAS>(bias_own, c4);
+#pragma unroll
+        for (uint32_t c = c4; c < c4 + 4; ++c)
+            ring_emit<FAST, STRIDE, BIAS, MASK>(c, x0[c], base_lane, ptr_own, ring_q(bq, c - c4), bias_flag, lane_off, knockout, keep_mask);
+    }
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     if (release_bar) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -376,11 +402,15 @@ __device__ __forceinline__ bool ring_epilogue_w16o(uint32_t taddr, uint8_t *base
         if ((threadIdx.x & 31u) == 0) mbar_arrive(release_bar);
     }
 #pragma unroll
-    for (uint32_t c = 0; c < 16; ++c) {
-        const uint32_t q2 = p2[c >> 1], q3 = p3[c >> 1];
-        const uint32_t hi = (c & 1u) ? (q2 & 0xFFFF0000u) + ((q3 & 0x00FF0000u) << 8) : (q2 << 16) + (q3 << 24);
-        const uint32_t x = p0[c] + (p1[c] << 8) + hi;
-        ring_emit<FAST, STRIDE, BIAS, MASK>(16u + c, x, base_lane, ptr_own, bias_own, bias_flag, lane_off, knockout, keep_mask);
+    for (uint32_t c4 = 0; c4 < 16; c4 += 4) {
+        const uint4 bq = ring_bias4<BIAS>(bias_own, 16u + c4);
+#pragma unroll
+        for (uint32_t c = c4; c < c4 + 4; ++c) {
+            const uint32_t q2 = p2[c >> 1], q3 = p3[c >> 1];
+            const uint32_t hi = (c & 1u) ? (q2 & 0xFFFF0000u) + ((q3 & 0x00FF0000u) << 8) : (q2 << 16) + (q3 << 24);
+            const uint32_t x = p0[c] + (p1[c] << 8) + hi;
+            ring_emit<FAST, STRIDE, BIAS, MASK>(16u + c, x, base_lane, ptr_own, ring_q(bq, c - c4), bias_flag, lane_off, knockout, keep_mask);
+        }
     }
     return release_bar != nullptr;
 }
@@ -404,9 +434,13 @@ __device__ __forceinline__ bool ring_epilogue(uint32_t taddr, uint8_t *base_lane
             if ((threadIdx.x & 31u) == 0) mbar_arrive(release_bar);
         }
 #pragma unroll
-        for (uint32_t c = 0; c < 8; ++c) {
-            const uint32_t x = ((v[g & 1][3][c] * 256u + v[g & 1][2][c]) * 256u + v[g & 1][1][c]) * 256u + v[g & 1][0][c];
-            ring_emit<FAST, STRIDE, BIAS, MASK>(g * 8u + c, x, base_lane, ptr_own, bias_own, bias_flag, lane_off, knockout, keep_mask);
+        for (uint32_t c4 = 0; c4 < 8; c4 += 4) {
+            const uint4 bq = ring_bias4<BIAS>(bias_own, g * 8u + c4);
+#pragma unroll
+            for (uint32_t c = c4; c < c4 + 4; ++c) {
+                const uint32_t x = ((v[g & 1][3][c] * 256u + v[g & 1][2][c]) * 256u + v[g & 1][1][c]) * 256u + v[g & 1][0][c];
+                ring_emit<FAST, STRIDE, BIAS, MASK>(g * 8u + c, x, base_lane, ptr_own, ring_q(bq, c - c4), bias_flag, lane_off, knockout, keep_mask);
+            }
         }
     }
     return release_bar != nullptr;
@@ -497,76 +531,62 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
         // that all 8 KB of an output ciphertext are still written at about the same time
         const uint32_t n_zero_seg = 16u - p.n_slices;
         const uint32_t zero_units = n_zero_seg * TC_TN, zero_workers = p.n_slices * RG_EPI_WARPS, zero_me = slice * RG_EPI_WARPS + warp;
-        // Row information (caller row + Constant of row col_base + lane) comes from global memory. It is prefetched TWO
-        // tiles ahead into registers that are statically bound to the tile's parity (= its TMEM stage): the loop is
-        // unrolled by two, so no register is shifted between tiles and nothing waits for a load that was just issued.
-        uint32_t row_q[2];
-        int32_t bias_q[2];
-#pragma unroll
-        for (uint32_t u = 0; u < 2; ++u) {
-            const uint32_t tt = real_tile(min(t_begin + u, t_end - 1));
-            row_q[u] = __ldg(p.tile_rows + (uint64_t) tt * TC_TN + col_base + lane);
-            bias_q[u] = __ldg(p.tile_bias + (uint64_t) tt * TC_TN + col_base + lane);
-        }
-        for (uint32_t t2 = t_begin; t2 < t_end; t2 += 2) {
-#pragma unroll
-            for (uint32_t u = 0; u < 2; ++u) {
-                const uint32_t t = t2 + u;
-                if (t >= t_end) break;
-                const uint32_t it = t - t_begin, st = u;
-                const uint32_t row = row_q[u];
-                const uint32_t bias_own = (uint32_t) bias_q[u] * (uint32_t) IDASH_B200_ONE_IN_T32;
-                const bool fast = ring_hdr(hdr_s, it).fast && p.slot_of_row == nullptr;
-                uint64_t ptr_own = 0;
-                uint8_t *base_lane = nullptr;
-                uint8_t *const out_words = batched ? reinterpret_cast<uint8_t *>(p.batch_out[batch_of(t)]) : p.out.words;
-                if (fast) {
-                    const uint32_t row0 = __shfl_sync(0xFFFFFFFFu, row, 0);     // caller row of tile row col_base
-                    base_lane = out_words + (uint64_t) row0 * p.out.stride + 4u * w_slice + lane_off;
-                } else if (row != IDASH_B200_NO_ROW) {
-                    ptr_own = (uint64_t) (out_words + (uint64_t) (p.slot_of_row ? __ldg(p.slot_of_row + row) : row) * p.out.stride + 4u * w_slice);
-                }
-                {   // prefetch for tile t + 2 (same parity): consumed a whole tile pair later
-                    const uint32_t tt = real_tile(min(t + 2u, t_end - 1));
-                    row_q[u] = __ldg(p.tile_rows + (uint64_t) tt * TC_TN + col_base + lane);
-                    bias_q[u] = __ldg(p.tile_bias + (uint64_t) tt * TC_TN + col_base + lane);
-                }
-                if (k_tune & 1u) mbar_wait(&t_full[st], (it >> 1) & 1u); else mbar_spin(&t_full[st], (it >> 1) & 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (tid == 0) RG_TRACE(6, it);
-                const uint32_t taddr = tmem + ((quad * 32u) << 16) + st * 4u * TC_TN + col_base;
-                uint64_t *const rel = early ? &t_empty[st] : nullptr;
-                bool arrived;
-                if (fast) {
-                    if (records) {
-                        if (is_b) arrived = ring_epilogue<EPI, true, IDASH_B200_RECORD_BYTES, true, ROT>(taddr, base_lane, 0, bias_own, bias_flag, lane_off, k_knockout, keep_mask, rel);
-                        else arrived = ring_epilogue<EPI, true, IDASH_B200_RECORD_BYTES, false>(taddr, base_lane, 0, 0, 0, lane_off, k_knockout, 0xFFFFFFFFu, rel);
-                    } else {
-                        if (is_b) arrived = ring_epilogue<EPI, true, IDASH_B200_CT_BYTES, true, ROT>(taddr, base_lane, 0, bias_own, bias_flag, lane_off, k_knockout, keep_mask, rel);
-                        else arrived = ring_epilogue<EPI, true, IDASH_B200_CT_BYTES, false>(taddr, base_lane, 0, 0, 0, lane_off, k_knockout, 0xFFFFFFFFu, rel);
-                    }
-                } else {
-                    arrived = ring_epilogue<EPI, false, 0, true, ROT>(taddr, nullptr, ptr_own, bias_own, bias_flag, lane_off, k_knockout, keep_mask, rel);
-                }
-                if (!arrived) {
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&t_empty[st]);      // one arrival per epilogue warp
-                }
-                if (ROT && zero_units && !(k_knockout & (2u | 16u))) {
-                    // zero fill of b[128 n_slices - 1024 .. 1024) of this tile's rows: unit u = (tile row u / n_zero_seg, segment u % n_zero_seg)
-                    const uint32_t row_lane0 = __shfl_sync(0xFFFFFFFFu, row, 0);       // caller row of tile row col_base
-                    const uint32_t tt = real_tile(t);
-                    for (uint32_t u = zero_me; u < zero_units; u += zero_workers) {
-                        const uint32_t n = u / n_zero_seg, seg = u - n * n_zero_seg;
-                        uint32_t r = fast ? row_lane0 - col_base + n : __ldg(p.tile_rows + (uint64_t) tt * TC_TN + n);
-                        if (r == IDASH_B200_NO_ROW) continue;
-                        if (p.slot_of_row) r = __ldg(p.slot_of_row + r);
-                        stg128_zero_stream(out_words + (uint64_t) r * p.out.stride + 512u * (p.n_slices + seg) + 16u * lane);
-                    }
-                }
-                if (tid == 0) RG_TRACE(8, it);
+        // Row information (caller rows + Constants of the tile) is in the tile's metadata record in shared memory, put there by the
+        // coefficient loader's bulk copies together with the coefficient image (b_full of the tile covers both). The epilogue issues
+        // no global load: one issued here queues behind the warp's own store backlog (measured: a load issued two tiles -- ~4000
+        // cycles -- ahead still stalled its consumer for ~120 cycles per tile).
+        const uint32_t bias_mul = bias_flag ? (uint32_t) IDASH_B200_ONE_IN_T32 : 0u;
+        for (uint32_t t = t_begin; t < t_end; ++t) {
+            const uint32_t it = t - t_begin, st = it & 1u;
+            const uint32_t *meta = reinterpret_cast<const uint32_t *>(smem + p.meta_off + (it & (RG_META_STAGES - 1u)) * (8u * TC_TN));
+            // the record landed before the tile's MMAs were issued; observing its barrier makes the bulk copy's bytes visible here
+            mbar_spin(&b_full[it & (RG_BBARS - 1u)], (it / RG_BBARS) & 1u);
+            const uint32_t row = meta[col_base + lane];
+            const uint32_t bias_addr = smem_u32(meta + TC_TN + col_base);
+            const bool fast = ring_hdr(hdr_s, it).fast && p.slot_of_row == nullptr;
+            uint64_t ptr_own = 0;
+            uint8_t *base_lane = nullptr;
+            uint8_t *const out_words = batched ? reinterpret_cast<uint8_t *>(p.batch_out[batch_of(t)]) : p.out.words;
+            if (fast) {
+                const uint32_t row0 = __shfl_sync(0xFFFFFFFFu, row, 0);     // caller row of tile row col_base
+                base_lane = out_words + (uint64_t) row0 * p.out.stride + 4u * w_slice + lane_off;
+            } else if (row != IDASH_B200_NO_ROW) {
+                ptr_own = (uint64_t) (out_words + (uint64_t) (p.slot_of_row ? __ldg(p.slot_of_row + row) : row) * p.out.stride + 4u * w_slice);
             }
+            if (k_tune & 1u) mbar_wait(&t_full[st], (it >> 1) & 1u); else mbar_spin(&t_full[st], (it >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (tid == 0) RG_TRACE(6, it);
+            const uint32_t taddr = tmem + ((quad * 32u) << 16) + st * 4u * TC_TN + col_base;
+            uint64_t *const rel = early ? &t_empty[st] : nullptr;
+            bool arrived;
+            if (fast) {
+                if (records) {
+                    if (is_b) arrived = ring_epilogue<EPI, true, IDASH_B200_RECORD_BYTES, true, ROT>(taddr, base_lane, 0, bias_addr, bias_mul, lane_off, k_knockout, keep_mask, rel);
+                    else arrived = ring_epilogue<EPI, true, IDASH_B200_RECORD_BYTES, false>(taddr, base_lane, 0, 0, 0, lane_off, k_knockout, 0xFFFFFFFFu, rel);
+                } else {
+                    if (is_b) arrived = ring_epilogue<EPI, true, IDASH_B200_CT_BYTES, true, ROT>(taddr, base_lane, 0, bias_addr, bias_mul, lane_off, k_knockout, keep_mask, rel);
+                    else arrived = ring_epilogue<EPI, true, IDASH_B200_CT_BYTES, false>(taddr, base_lane, 0, 0, 0, lane_off, k_knockout, 0xFFFFFFFFu, rel);
+                }
+            } else {
+                arrived = ring_epilogue<EPI, false, 0, true, ROT>(taddr, nullptr, ptr_own, bias_addr, bias_mul, lane_off, k_knockout, keep_mask, rel);
+            }
+            if (!arrived) {
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&t_empty[st]);      // one arrival per epilogue warp
+            }
+            if (ROT && zero_units && !(k_knockout & (2u | 16u))) {
+                // zero fill of b[128 n_slices - 1024 .. 1024) of this tile's rows: unit u = (tile row u / n_zero_seg, segment u % n_zero_seg)
+                const uint32_t row_lane0 = __shfl_sync(0xFFFFFFFFu, row, 0);       // caller row of tile row col_base
+                for (uint32_t u = zero_me; u < zero_units; u += zero_workers) {
+                    const uint32_t n = u / n_zero_seg, seg = u - n * n_zero_seg;
+                    uint32_t r = fast ? row_lane0 - col_base + n : meta[n];
+                    if (r == IDASH_B200_NO_ROW) continue;
+                    if (p.slot_of_row) r = __ldg(p.slot_of_row + r);
+                    stg128_zero_stream(out_words + (uint64_t) r * p.out.stride + 512u * (p.n_slices + seg) + 16u * lane);
+                }
+            }
+            if (tid == 0) RG_TRACE(8, it);
         }
     } else if (warp == RG_WARP_MMA || warp == RG_WARP_MMA2) {
         // ================= MMA issuers =================
@@ -733,12 +753,22 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                     const uint4 hb = __ldg(reinterpret_cast<const uint4 *>(p.tiles + p.tile_base));
                     b_off = (uint64_t) hb.z | ((uint64_t) hb.w << 32);
                 }
-                // the barrier was last used by tile it - 8: its MMAs (hence its waiters) must be past it
-                if (it >= RG_BBARS) progress_wait(&tiles_done_s, it - RG_BBARS + 1u);
+                // Barrier and metadata record it % 8 were last used by tile it - 8, whose epilogue reads the record until its last
+                // store. The MMAs of tile it - 4 being complete implies that: they needed the TMEM stage of tile it - 6, which the
+                // epilogue warps hand back only after they have finished tiles it - 7 and it - 8.
+                if (it >= 4u) progress_wait(&tiles_done_s, it - 3u);
                 const uint32_t bytes = T.nb * TC_B_CHUNK;
                 uint64_t *const bar = &b_full[it & (RG_BBARS - 1u)];
                 RG_TRACE(10, it);
-                mbar_arrive_expect_tx(bar, bytes);
+                mbar_arrive_expect_tx(bar, bytes + 8u * TC_TN);
+                {   // metadata record: caller rows, then Constants, of the tile's 64 rows (256 bytes each, consecutive tiles contiguous)
+                    const uint32_t tt = real_tile(t);
+                    uint8_t *const rec = smem + p.meta_off + (it & (RG_META_STAGES - 1u)) * (8u * TC_TN);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(smem_u32(rec)), "l"(p.tile_rows + (uint64_t) tt * TC_TN), "r"(4u * TC_TN), "r"(smem_u32(bar)) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(smem_u32(rec + 4u * TC_TN)), "l"(p.tile_bias + (uint64_t) tt * TC_TN), "r"(4u * TC_TN), "r"(smem_u32(bar)) : "memory");
+                }
                 // Ring space is admitted chunk by chunk: whatever part of the image fits is copied NOW and the rest as soon as earlier
                 // tiles complete. (Waiting for room for the whole image put its copy -- ~1800 cycles for 28 KB at neighbors = 50, where
                 // three images are one chunk more than the ring holds -- on the critical path of every tile.)

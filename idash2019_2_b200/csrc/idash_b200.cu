@@ -824,7 +824,8 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
         const uint32_t max_nb = L->tile_kmax / 32u;
         p.n_batches = n_batches;
         for (uint32_t b = 0; b < n_batches && n_batches > 1; ++b) { p.batch_in[b] = (unsigned long long) ins[b].words; p.batch_out[b] = (unsigned long long) outs[b].words; }
-        p.hdr_off = p.n_slots * RG_BLOCK_BYTES + p.n_bchunks * TC_B_CHUNK;
+        p.meta_off = p.n_slots * RG_BLOCK_BYTES + p.n_bchunks * TC_B_CHUNK;
+        p.hdr_off = p.meta_off + RG_META_BYTES;
         p.in = in; p.out = out;
         p.slot_of_ct = d_slot_of_ct; p.n_ct_slots = n_ct_slots; p.slot_of_row = d_slot_of_row;
         p.S = L->S; p.NR = L->NR; p.RS = L->RS;
@@ -904,15 +905,17 @@ static bool ring_plan(const idash_b200_ctx *c, const idash_b200_layout *L, uint6
     rp->max_chunk_tiles = (uint32_t) chunk_tiles;
     const uint32_t max_nb = L->tile_kmax / 32u;
     const auto chunks_for = [&](uint32_t slots) -> uint32_t {
-        const uint32_t used = slots * RG_BLOCK_BYTES + 4u * rp->max_chunk_tiles;
+        const uint32_t used = slots * RG_BLOCK_BYTES + RG_META_BYTES + 4u * rp->max_chunk_tiles;
         return used >= RG_SMEM_MAX ? 0u : std::min<uint32_t>(64u, (RG_SMEM_MAX - used) / TC_B_CHUNK);
     };
-    // as many input-block slots as leave room for the coefficient images of almost three tiles of the widest band (the image of tile
-    // t + 2 is then in flight while t and t + 1 are resident); failing that, two tiles
-    const uint32_t lo = max_nb + 1u;
+    // Input-block slots: the widest tile's blocks + 2 (one being staged, one ahead), and at least two and a half tiles of coefficient
+    // chunks beside them (the loader admits an image chunk by chunk, so that is as good as three). Measured per workload (A/B runs,
+    // profiles/r02_ring_slots.txt): MORE slots are slower -- producers that run far ahead of the MMAs only add read traffic in front
+    // of the stores: neighbors = 5: 9 slots 0.4577 ms, 5 slots 0.4538; 20: 9 slots 0.4766, 6 slots 0.4692; 50: 9 slots 0.590, 8 slots 0.553.
+    const uint32_t lo = max_nb + 1u, hi = std::min<uint32_t>(RG_MAX_SLOTS, max_nb + 2u);
     uint32_t slots = 0;
-    for (uint32_t s = RG_MAX_SLOTS; s >= lo && !slots; --s) if (chunks_for(s) >= std::max(3u * max_nb - 1u, 4u)) slots = s;
-    for (uint32_t s = RG_MAX_SLOTS; s >= lo && !slots; --s) if (chunks_for(s) >= 2u * max_nb) slots = s;
+    for (uint32_t s = hi; s >= lo && !slots; --s) if (chunks_for(s) >= 2u * max_nb + max_nb / 2u) slots = s;
+    for (uint32_t s = hi; s >= lo && !slots; --s) if (chunks_for(s) >= 2u * max_nb) slots = s;
     if (!slots) return false;
     if (const char *rs = debug_env("IDASH_B200_RING_SLOTS")) {   // experiments
         const uint32_t s = (uint32_t) atoi(rs);
