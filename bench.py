@@ -389,6 +389,92 @@ def run_b200(args):
            for _ in range(n_batches)]
     outs = [torch.empty((n_rows, 2048), dtype=torch.int32, device="cuda") for _ in range(n_batches)]
 
+    # ---- N > 1: the data plane of the sharded job. The job's ciphertexts are resident on GPU 0 -- all tag ciphertexts of
+    # every batch -- and its results are wanted there: rank r RECEIVES the slab its target range reads, of every batch (scatter), and
+    # SENDS BACK its rows of every batch's output (gather), as grouped NCCL send / recv over NVLink / NVSwitch. There is no collective
+    # inside the evaluation itself. The timed steps below consume the scattered slabs, and the gathered result of batch 0 is compared
+    # on GPU 0 with the UNSHARDED evaluation of the whole model on the same inputs (sharded == unsharded, bit for bit).
+    nvlink = None
+    if world > 1:
+        real = model.col != np.uint32(0xFFFFFFFF)
+        n_in_total = int(model.col[real].max()) // NR + 1
+        metas = [shard_mod.make_shard(model, NR, args.targets, r, world) for r in range(world)]
+        meta = [(s_.ct_min, s_.n_ct, s_.row_lo, s_.row_hi) for s_ in metas]
+        del metas
+        full_ins = full_outs = None
+        if rank == 0:
+            g0 = torch.Generator(device="cuda").manual_seed(SEED + 1000)
+            full_ins = [torch.randint(-2 ** 31, 2 ** 31, (n_in_total, 2048), dtype=torch.int32, device="cuda", generator=g0) for _ in range(n_batches)]
+            full_outs = [torch.empty((3 * args.targets, 2048), dtype=torch.int32, device="cuda") for _ in range(n_batches)]
+
+        def scatter():
+            ops = []
+            if rank == 0:
+                for b in range(n_batches):
+                    ins[b].copy_(full_ins[b][meta[0][0]:meta[0][0] + meta[0][1]])
+                    for r in range(1, world):
+                        ops.append(dist.P2POp(dist.isend, full_ins[b][meta[r][0]:meta[r][0] + meta[r][1]], r))
+            else:
+                for b in range(n_batches):
+                    ops.append(dist.P2POp(dist.irecv, ins[b], 0))
+            for q in dist.batch_isend_irecv(ops):
+                q.wait()
+
+        def gather():
+            ops = []
+            if rank == 0:
+                for b in range(n_batches):
+                    full_outs[b][meta[0][2]:meta[0][3]].copy_(outs[b])
+                    for r in range(1, world):
+                        ops.append(dist.P2POp(dist.irecv, full_outs[b][meta[r][2]:meta[r][3]], r))
+            else:
+                for b in range(n_batches):
+                    ops.append(dist.P2POp(dist.isend, outs[b], 0))
+            for q in dist.batch_isend_irecv(ops):
+                q.wait()
+
+        def timed(fn, reps=3):
+            fn()                                   # warm-up: NCCL sets up its peer channels on first use
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            tt = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt[0])
+
+        scatter_ms = timed(scatter)
+        if n_batches > 1 and not args.no_batched:
+            api.cloud_compute_score_device_batched(ctx, m, ins, outs)
+        else:
+            for b in range(n_batches):
+                api.cloud_compute_score_device(ctx, m, ins[b], outs[b])
+        torch.cuda.synchronize()
+        gather_ms = timed(gather)
+        same = None
+        if rank == 0:
+            mf = api.Model(ctx, args.samples, NR, RS, model.out_bidx, model.row_ptr, model.col, model.coef)
+            whole = torch.empty((3 * args.targets, 2048), dtype=torch.int32, device="cuda")
+            api.cloud_compute_score_device(ctx, mf, full_ins[0], whole)
+            torch.cuda.synchronize()
+            same = bool(torch.equal(whole, full_outs[0]))
+            mf.free()
+            del whole
+        sc_bytes = n_batches * sum(meta[r][1] for r in range(1, world)) * CT_BYTES
+        ga_bytes = n_batches * sum(meta[r][3] - meta[r][2] for r in range(1, world)) * CT_BYTES
+        nvlink = {"scatter_ms": scatter_ms, "gather_ms": gather_ms, "scatter_bytes": sc_bytes, "gather_bytes": ga_bytes,
+                  "scatter_gbs": sc_bytes / (scatter_ms * 1e-3) * 1e-9, "gather_gbs": ga_bytes / (gather_ms * 1e-3) * 1e-9,
+                  "sharded_equals_unsharded": same,
+                  "how": "job data resident on GPU 0: every rank receives its slab of every batch and returns its rows of every batch, grouped "
+                         "ncclSend / ncclRecv (torch.distributed.batch_isend_irecv), CUDA events, max over ranks; the timed steps consume the "
+                         "scattered slabs; GPU 0 compares the gathered batch 0 with its own unsharded evaluation of the whole model"}
+        del full_ins, full_outs
+        torch.cuda.empty_cache()
+
     # The batches of a step are independent evaluations of the same model on the rank's target range. With more than one they
     # go through the batched entry point: ONE launch of the persistent kernel walks the tiles of every batch, so the kernel's
     # ramp-up and tail are paid once per step and not once per batch (--no-batched: one launch per batch, round-robin on two
@@ -579,6 +665,11 @@ def run_b200(args):
             line["sustained"] = sustained
         if decrypt:
             line["decrypt"] = decrypt
+        if nvlink:
+            nvlink["job_ms_gpu0_resident"] = nvlink["scatter_ms"] + ms_total / args.steps + nvlink["gather_ms"]
+            line["nvlink"] = nvlink
+            if nvlink["sharded_equals_unsharded"] is False:
+                all_equal = False
         if world == 1 and parity is not None:
             try:
                 best = ref_secs
@@ -594,7 +685,7 @@ def run_b200(args):
                                         "seconds": best}
             except Exception as e:  # the checker is optional for the bench line; say why it is missing
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
-        if parity is not None and not all_equal:
+        if (parity is not None and not all_equal) or (nvlink and nvlink["sharded_equals_unsharded"] is False):
             # parity is a gate -- no value without it
             line["value"] = None
             line["e2e"]["value"] = None

@@ -108,6 +108,17 @@ class Model:
         self.out_bidx = None
         return self
 
+    def clone(self, ctx: Context) -> "Model":
+        """The same model on another GPU (idash_b200_model_clone): the compiled layout is shared, the device arrays are uploaded again."""
+        other = Model.__new__(Model)
+        other.ctx = ctx
+        other.S, other.NR, other.RS = getattr(self, "S", None), getattr(self, "NR", None), getattr(self, "RS", None)
+        other.out_bidx = self.out_bidx
+        other._h = C.c_void_p()
+        L.check(L.lib().idash_b200_model_clone(ctx.handle, self.handle, C.byref(other._h)))
+        other._read_info()
+        return other
+
     def _read_info(self):
         info = L.ModelInfo()
         L.check(L.lib().idash_b200_model_get_info(self._h, C.byref(info)))
@@ -195,6 +206,23 @@ def cloud_compute_score_device(ctx: Context, model: Model, in_ct, out_ct, in_ind
     cout = L.Cts(LAYOUT_PACKED, dp(out_ct) if n_out else None, n_out, dp(out_index), dp(out_var))
     L.check(L.lib().idash_b200_cloud_eval_device(ctx.handle, model.handle, C.byref(cin), C.byref(cout), dp(slot_of_row),
                                                  C.c_void_p(stream)))
+
+
+def cloud_compute_score_multi_device(ctxs, models, in_ct, out_ct, in_var=None, out_index=None, out_var=None) -> None:
+    """One evaluation sharded over several GPUs of this process by contiguous target ranges (idash_b200_cloud_eval_multi_device):
+    in_ct / out_ct (and the optional arrays) are torch CUDA tensors on ctxs[0]'s GPU, PACKED, inputs in identity order. models[g] is
+    models[0].clone(ctxs[g]). Synchronous; the caller's work on in_ct must be complete (torch.cuda.synchronize())."""
+    n = len(ctxs)
+    if n != len(models) or n == 0:
+        raise ValueError("one model per context")
+    n_in = in_ct.numel() // CT_WORDS
+    n_out = out_ct.numel() // CT_WORDS
+    dp = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+    cin = L.Cts(LAYOUT_PACKED, dp(in_ct) if n_in else None, n_in, None, dp(in_var))
+    cout = L.Cts(LAYOUT_PACKED, dp(out_ct) if n_out else None, n_out, dp(out_index), dp(out_var))
+    hc = (C.c_void_p * n)(*[c.handle.value for c in ctxs])
+    hm = (C.c_void_p * n)(*[m.handle.value for m in models])
+    L.check(L.lib().idash_b200_cloud_eval_multi_device(n, hc, hm, C.byref(cin), C.byref(cout)))
 
 
 def cloud_compute_score_device_batched(ctx: Context, model: Model, in_cts, out_cts, stream=None) -> None:

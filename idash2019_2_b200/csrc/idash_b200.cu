@@ -1195,6 +1195,116 @@ extern "C" int idash_b200_cloud_eval_host_rows(idash_b200_ctx *c, const idash_b2
                                      (uint32_t) ((row_end + IDASH_B200_TILE_ROWS - 1) / IDASH_B200_TILE_ROWS));
 }
 
+// One evaluation sharded over several GPUs of this process, the data resident on the FIRST of them ("GPU-resident data ->
+// cudaMemcpyPeerAsync over NVLink"). GPU g takes a contiguous tile-aligned target range; it receives the slab of input ciphertexts
+// the range reads by a peer copy and WRITES ITS ROWS STRAIGHT INTO THE OUTPUT ARRAY ON GPU 0 -- the ring kernel's epilogue stores (and
+// the per-row finalize kernel's) go through the peer mapping, so the gather is fused into the kernel: no staging buffer and no
+// second pass over the 8 KB rows. Where peer access is not available the rows are staged locally and copied back.
+extern "C" int idash_b200_cloud_eval_multi_device(uint32_t n_gpus, idash_b200_ctx *const *cs, const idash_b200_model *const *ms,
+                                                  const idash_b200_cts *in, const idash_b200_cts *out) {
+    clear_error();
+    if (!n_gpus || !cs || !ms || !in || !out) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_multi_device: null argument");
+    for (uint32_t g = 0; g < n_gpus; ++g) {
+        if (!cs[g] || !ms[g]) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_multi_device: null ctx / model %u", g);
+        if (ms[g]->device != cs[g]->device) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_multi_device: model %u lives on device %d, ctx on %d", g, ms[g]->device, cs[g]->device);
+        if (ms[g]->layout != ms[0]->layout) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_multi_device: model %u is not a clone of model 0", g);
+        for (uint32_t h = 0; h < g; ++h)
+            if (cs[h]->device == cs[g]->device) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_multi_device: device %d listed twice", cs[g]->device);
+    }
+    const idash_b200_layout *L = ms[0]->layout;
+    if (in->layout != IDASH_B200_LAYOUT_PACKED || in->index)
+        return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_multi_device: inputs must be PACKED in identity order (slot i = ciphertext i)");
+    CtView vin0, vout0;
+    int rc;
+    if ((rc = make_view(in, false, &vin0, "cloud_eval_multi_device(in)"))) return rc;
+    if ((rc = make_view(out, true, &vout0, "cloud_eval_multi_device(out)"))) return rc;
+    if (out->count != L->n_rows) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_multi_device: out->count (%llu) != model rows (%llu)",
+                                                  (unsigned long long) out->count, (unsigned long long) L->n_rows);
+    if (L->n_rows == 0) return IDASH_B200_OK;
+    if (n_gpus == 1) {
+        CUDA_TRY(cudaSetDevice(cs[0]->device));
+        if ((rc = launch_cloud(cs[0], ms[0], vin0, vout0, nullptr, cs[0]->stream))) return rc;
+        CUDA_TRY(cudaStreamSynchronize(cs[0]->stream));
+        return idash_b200_check_device_status(cs[0]);
+    }
+    for (uint32_t g = 0; g < n_gpus; ++g)
+        if (!ring_selected(cs[g], L) || L->n_overflow_rows || !rows_identity(ms[g]))
+            return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_multi_device: needs a model with rows sorted by output bigIndex that the persistent "
+                                                     "ring kernel evaluates whole (no overflow rows)");
+    const uint64_t T = L->tiles.size();
+    const int dev0 = cs[0]->device;
+    const size_t ostride = vout0.stride;
+    struct Staged { uint32_t g; uint64_t row_lo, row_hi; };
+    std::vector<Staged> staged;
+    for (uint32_t g = 0; g < n_gpus; ++g) {
+        idash_b200_ctx *c = cs[g];
+        Piece pc;
+        pc.tile_lo = (uint32_t) (T * g / n_gpus); pc.tile_hi = (uint32_t) (T * (g + 1) / n_gpus);
+        if (pc.tile_lo == pc.tile_hi) continue;
+        pc.row_lo = (uint64_t) pc.tile_lo * IDASH_B200_TILE_ROWS;
+        pc.row_hi = std::min<uint64_t>(L->n_rows, (uint64_t) pc.tile_hi * IDASH_B200_TILE_ROWS);
+        pc.first = true;
+        CUDA_TRY(cudaSetDevice(c->device));
+        CtView vin = vin0, vout = vout0;
+        if (g != 0) {
+            int can = 0;
+            CUDA_TRY(cudaDeviceCanAccessPeer(&can, c->device, dev0));
+            if (can) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(dev0, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); can = 0; }
+                else cudaGetLastError();
+            }
+            // the slab this range reads: [ct_lo, ct_hi)
+            uint64_t f_lo = UINT64_MAX, f_hi = 0;
+            for (uint32_t t = pc.tile_lo; t < pc.tile_hi; ++t) {
+                f_lo = std::min<uint64_t>(f_lo, L->tiles[t].f_base);
+                f_hi = std::max<uint64_t>(f_hi, (uint64_t) L->tiles[t].f_base + L->tiles[t].K);
+            }
+            const uint64_t ct_lo = std::min<uint64_t>(f_lo / L->NR, in->count), ct_hi = std::min<uint64_t>((f_hi + L->NR - 1) / L->NR, in->count);
+            if ((rc = c->in_buf.ensure((size_t) (ct_hi - ct_lo) * IDASH_B200_CT_BYTES + 16))) return rc;
+            if (ct_hi > ct_lo)
+                CUDA_TRY(cudaMemcpyPeerAsync(c->in_buf.p, c->device, vin0.words + ct_lo * IDASH_B200_CT_BYTES, dev0, (size_t) (ct_hi - ct_lo) * IDASH_B200_CT_BYTES, c->stream));
+            vin.words = (uint8_t *) c->in_buf.p - ct_lo * IDASH_B200_CT_BYTES;          // virtual base: slot ct_lo is the first one resident
+            if (vin0.variance) {
+                if ((rc = c->aux_in_var.ensure((size_t) in->count * 8 + 8))) return rc;
+                CUDA_TRY(cudaMemcpyPeerAsync(c->aux_in_var.p, c->device, vin0.variance, dev0, (size_t) in->count * 8, c->stream));
+                vin.variance = (double *) c->aux_in_var.p;
+            }
+            if (!can) {
+                // no peer mapping: rows of the range into a local buffer (virtual base like the input's), copied back below
+                const uint64_t nr = pc.row_hi - pc.row_lo;
+                if ((rc = c->out_buf.ensure((size_t) nr * ostride + 32))) return rc;
+                uint8_t *const obase = (uint8_t *) c->out_buf.p + (vout0.records ? 16 : 0) - pc.row_lo * ostride;
+                vout.words = obase;
+                if (vout0.index) { if ((rc = c->aux_out_idx.ensure((size_t) nr * 4 + 4))) return rc; vout.index = (uint32_t *) c->aux_out_idx.p - pc.row_lo; }
+                if (vout0.variance) { if ((rc = c->aux_out_var.ensure((size_t) nr * 8 + 8))) return rc; vout.variance = (double *) c->aux_out_var.p - pc.row_lo; }
+                staged.push_back({g, pc.row_lo, pc.row_hi});
+            }
+        }
+        if ((rc = launch_cloud(c, ms[g], vin, vout, nullptr, c->stream, &pc))) {
+            for (uint32_t h = 0; h <= g; ++h) { cudaSetDevice(cs[h]->device); cudaStreamSynchronize(cs[h]->stream); }
+            return rc;
+        }
+    }
+    for (const Staged &s : staged) {
+        idash_b200_ctx *c = cs[s.g];
+        CUDA_TRY(cudaSetDevice(c->device));
+        const uint64_t nr = s.row_hi - s.row_lo;
+        const size_t head = vout0.records ? 8 : 0;          // a record starts 8 bytes before its words
+        CUDA_TRY(cudaMemcpyPeerAsync(vout0.words - head + s.row_lo * ostride, dev0, (uint8_t *) c->out_buf.p + (vout0.records ? 16 : 0) - head, c->device, nr * ostride, c->stream));
+        if (vout0.index) CUDA_TRY(cudaMemcpyPeerAsync(vout0.index + s.row_lo, dev0, c->aux_out_idx.p, c->device, nr * 4, c->stream));
+        if (vout0.variance) CUDA_TRY(cudaMemcpyPeerAsync(vout0.variance + s.row_lo, dev0, c->aux_out_var.p, c->device, nr * 8, c->stream));
+    }
+    int result = IDASH_B200_OK;
+    for (uint32_t g = 0; g < n_gpus; ++g) {
+        CUDA_TRY(cudaSetDevice(cs[g]->device));
+        CUDA_TRY(cudaStreamSynchronize(cs[g]->stream));
+        const int r = idash_b200_check_device_status(cs[g]);
+        if (r != IDASH_B200_OK && result == IDASH_B200_OK) result = r;
+    }
+    return result;
+}
+
 extern "C" int idash_b200_model_input_range(const idash_b200_model *m, uint64_t row_begin, uint64_t row_end, uint32_t *ct_begin, uint32_t *ct_end) {
     clear_error();
     if (!m || !ct_begin || !ct_end) return set_error(IDASH_B200_ERR_INVALID, "model_input_range: null argument");

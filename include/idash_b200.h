@@ -173,6 +173,15 @@ int idash_b200_model_input_range(const idash_b200_model *model, uint64_t row_beg
 int idash_b200_cloud_eval_device_batched(idash_b200_ctx *ctx, const idash_b200_model *model, uint32_t n_batches,
                                          const idash_b200_cts *in, const idash_b200_cts *out, void *cuda_stream);
 
+/* One evaluation sharded over n_gpus GPUs of this process by contiguous target ranges, with the data resident on the FIRST GPU
+ * (scatter of the input slabs and gather of the outputs over NVLink; the loop being cut is eval/idash.cpp:779-790).
+ * ctx[g] / model[g]: one context per GPU and the model uploaded to it (model[0] and its idash_b200_model_clone()s). `in` (PACKED, identity
+ * order) and `out` (PACKED or RECORDS, rows in output-bigIndex order) are DEVICE memory of ctx[0]'s GPU. GPU g > 0 receives the slab its
+ * range reads with a peer copy and its kernels store their rows directly into `out` through the peer mapping (fused gather). Synchronous:
+ * returns when every GPU has finished (IDASH_B200_ERR_MISSING_INPUT as for cloud_eval_host). The caller's earlier work on `in` must be complete. */
+int idash_b200_cloud_eval_multi_device(uint32_t n_gpus, idash_b200_ctx *const *ctx, const idash_b200_model *const *model,
+                                       const idash_b200_cts *in, const idash_b200_cts *out);
+
 /* After a *_device call and a stream synchronise: IDASH_B200_ERR_MISSING_INPUT if a kernel met a model
  * entry whose ciphertext was not supplied, else IDASH_B200_OK. Clears the flag. */
 int idash_b200_check_device_status(idash_b200_ctx *ctx);

@@ -40,7 +40,7 @@ def _equal_on_device(out_dev, ref_host, piece=16384):
     import torch
     bad = 0
     for lo in range(0, len(ref_host), piece):
-        r = torch.from_numpy(ref_host[lo:lo + piece].view(np.int32)).cuda()
+        r = torch.from_numpy(ref_host[lo:lo + piece].view(np.int32)).to(out_dev.device)
         bad += int((out_dev[lo:lo + piece] != r).any(dim=1).sum())
     return bad
 
@@ -195,3 +195,46 @@ def test_config0_full_pipeline_keygen_encrypt_cloud_decrypt(built_lib, tmp_path)
             assert ours[k] == want, k
             k += 1
     shutil.rmtree(tmp_path / "model", ignore_errors=True)
+
+
+@pytest.mark.parametrize("n_gpus", [2, 4, 8])
+def test_cloud_sharded_over_gpus_equals_unsharded_equals_reference(built_lib, n_gpus):
+    """SURVEY 8e on real GPUs: the target range cut over n GPUs of one process (idash_b200_cloud_eval_multi_device: peer-copied input
+    slabs, rows stored straight into GPU 0's output array through the peer mapping) == the unsharded evaluation on GPU 0 == the
+    reference, every word, index and variance; full iDASH size, neighbors = 20 (BASELINE configs[4] geometry)."""
+    import torch
+    if torch.cuda.device_count() < n_gpus:
+        pytest.skip(f"needs {n_gpus} GPUs")
+    S, n = 1004, 20
+    geo = synth.Geometry(S, T_FULL, G_FULL)
+    tag, tgt = synth.make_positions(T_FULL, G_FULL, SEED)
+    model = synth.make_model(tag, tgt, n, SEED)
+    n_in = geo.n_in_ct_used
+    cts = synth.random_ciphertexts(n_in, SEED + 7)
+    var = np.full(n_in, ALPHA2)
+    var[::7] = 2.0 ** -48                               # not uniform: the per-row variance sums run on every GPU
+    ctxs = [api.Context(g) for g in range(n_gpus)]
+    m0 = api.Model(ctxs[0], S, geo.NR, geo.RS, model.out_bidx, model.row_ptr, model.col, model.coef)
+    models = [m0] + [m0.clone(ctxs[g]) for g in range(1, n_gpus)]
+    with torch.cuda.device(0):
+        x = torch.from_numpy(cts.view(np.int32)).cuda()
+        xv = torch.from_numpy(var).cuda()
+        n_rows = 3 * G_FULL
+        whole = torch.zeros((n_rows, 2048), dtype=torch.int32, device="cuda")
+        wvar = torch.zeros(n_rows, dtype=torch.float64, device="cuda")
+        widx = torch.zeros(n_rows, dtype=torch.int32, device="cuda")
+        api.cloud_compute_score_device(ctxs[0], m0, x, whole, in_var=xv, out_index=widx, out_var=wvar)
+        torch.cuda.synchronize()
+        out = torch.zeros_like(whole)
+        ovar = torch.zeros_like(wvar)
+        oidx = torch.zeros_like(widx)
+        api.cloud_compute_score_multi_device(ctxs, models, x, out, in_var=xv, out_index=oidx, out_var=ovar)
+        assert torch.equal(out, whole) and torch.equal(ovar, wvar) and torch.equal(oidx, widx)
+        ref_out, ref_var, _ = _reference(S, geo.NR, geo.RS, cts, var, model)
+        assert _equal_on_device(out, ref_out) == 0
+        assert np.array_equal(ovar.cpu().numpy(), ref_var)
+        assert np.array_equal(oidx.cpu().numpy().view(np.uint32), model.out_bidx)
+    for m in models:
+        m.free()
+    for c in ctxs:
+        c.close()
