@@ -11,8 +11,9 @@
 //     work: they are gathered into a packed staging buffer first.
 //   * cloud_compute_score / decrypt_predictions have no arithmetic in them: they flatten the Model to CSR,
 //     call idash_b200_cloud_eval_host / idash_b200_decrypt_host and fan the results back into the containers.
-//   * no TFHE library is needed at run time (tfhe_min.h carries the five plain structs); build with
-//     -DIDASH_B200_WITH_TFHE to use <tfhe.h> instead, e.g. inside the reference tree.
+//   * no TFHE library is needed: tfhe_min.h carries the five plain structs with the reference's member names. (TFHE's own
+//     TorusPolynomial / TLweSample own their arrays and have const members, so they cannot be views into a slab; code that must keep
+//     <tfhe.h>'s types binds the C ABI through host/reference_glue/idash_b200_glue.cpp instead -- INTEGRATION.md section B.)
 #ifndef IDASH_B200_HOST_H
 #define IDASH_B200_HOST_H
 
@@ -25,11 +26,7 @@
 #include <unordered_map>
 #include <vector>
 
-#ifdef IDASH_B200_WITH_TFHE
-#include <tfhe.h>
-#else
 #include "tfhe_min.h"
-#endif
 
 #define REQUIRE_DRAMATICALLY(cond, message) \
     do { if (!(cond)) { std::cout << "ERROR: " << message << std::endl; abort(); } } while (0)

@@ -1,7 +1,7 @@
 // tfhe_min.h -- the handful of TFHE data types the imputation path touches, as plain data holders, for
 // building the host layer where the TFHE library is not installed (the GPU box). Field names, order and
 // types follow tfhe/src/include/polynomials.h:10-34, tlwe.h:9-60 so that code written against <tfhe.h>
-// (compile with -DIDASH_B200_WITH_TFHE to use the real headers instead) reads the same members.
+// reads the same members (the structs themselves are plain: no constructors, no ownership).
 // No TFHE arithmetic lives here: on this path all of it runs in libidash_b200.so.
 #ifndef IDASH_B200_TFHE_MIN_H
 #define IDASH_B200_TFHE_MIN_H

@@ -12,7 +12,10 @@
  * exact glue): plain pointers and sizes, no C++ or torch types, int return codes, never abort().
  *
  * Conventions
- *   - one idash_b200_ctx per GPU (one process per GPU); a ctx is not thread-safe.
+ *   - one idash_b200_ctx per GPU (one process per GPU, or one ctx per GPU of a process that shards an evaluation). A ctx is not
+ *     thread-safe and is used FROM ONE STREAM AT A TIME: the *_device entry points keep per-ctx scratch (ciphertext -> slot table,
+ *     variance flags, status word, one fork / join event pair) that is not ordered against work the caller has queued on another
+ *     stream. Two evaluations in flight on different streams need two contexts.
  *   - a TRLWE ciphertext ("ct") is 2048 uint32 words: polynomial a[1024] then b[1024]
  *     (tfhe/src/libtfhe/tlwe.cpp:42-52, k = 1, N = 1024, eval/idash.h:49-50).
  *   - all torus arithmetic is mod 2^32; results are bit-identical to the reference.

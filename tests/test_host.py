@@ -264,3 +264,22 @@ def test_cloud_binary_target_ranges_on_several_gpus(host_bins, tmp_path, gpus):
     assert f"evaluation on {n_gpus} GPU(s)" in r.stderr, r.stderr
     assert (tmp_path / "b200" / "encrypted_prediction.bin").read_bytes() == want
     shutil.rmtree(tmp_path / "model", ignore_errors=True)
+
+
+def test_reference_glue_compiles_against_reference_headers():
+    """INTEGRATION.md section B is code, not prose: host/reference_glue/idash_b200_glue.cpp -- new bodies of cloud_compute_score /
+    decrypt_predictions over the C ABI, written against the reference's own eval/idash.h and <tfhe.h> -- must type-check against the
+    reference tree (g++ -fsyntax-only; `-include array` is the same work-around the reference build needs), and the
+    snippet printed in INTEGRATION.md must be that file."""
+    glue = ROOT / "idash2019_2_b200" / "host" / "reference_glue" / "idash_b200_glue.cpp"
+    body = glue.read_text()
+    doc = (ROOT / "INTEGRATION.md").read_text()
+    for line in ("idash_b200_cloud_eval_host(ctx(), m, &in, &out, nullptr)", "idash_b200_decrypt_host(ctx(), key.tlweKey->key[0].coefs, S, &in, scores, nullptr)",
+                 "TLweSample *s = enc_preds.createAndGet(out_bidx[r], params.tlweParams);"):
+        assert line in body and line in doc
+    ref = Path("/root/reference")
+    if not (ref / "eval" / "idash.h").exists() or not Path("/usr/bin/g++").exists():
+        pytest.skip("the reference tree is not on this box")
+    r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-fsyntax-only", "-include", "array", f"-I{ref / 'eval'}", f"-I{ref / 'tfhe' / 'src' / 'include'}",
+                        f"-I{ROOT / 'include'}", str(glue)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
