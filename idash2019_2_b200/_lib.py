@@ -95,6 +95,7 @@ EXPORTS = {
     "idash_b200_cloud_eval_device": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Cts), C.POINTER(Cts), C.c_void_p,
                                                C.c_void_p]),
     "idash_b200_model_input_range": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "idash_b200_cloud_eval_device_multi_model": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(Cts), C.POINTER(Cts), C.c_void_p]),
     "idash_b200_cloud_eval_multi_device": (C.c_int, [C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(Cts), C.POINTER(Cts)]),
     "idash_b200_cloud_eval_host_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Cts), C.POINTER(Cts), C.c_uint64, C.c_uint64]),
     "idash_b200_cloud_eval_device_batched": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(Cts), C.POINTER(Cts), C.c_void_p]),

@@ -208,6 +208,24 @@ def cloud_compute_score_device(ctx: Context, model: Model, in_ct, out_ct, in_ind
                                                  C.c_void_p(stream)))
 
 
+def cloud_compute_score_device_multi_model(ctx: Context, models, in_cts, out_cts, stream=None) -> None:
+    """models[b] on (in_cts[b], out_cts[b]) for every b in one call (idash_b200_cloud_eval_device_multi_model): one launch of the ring
+    kernel when the models have the same shape -- the population-stratified model sets of BASELINE configs[3]."""
+    import torch
+    if stream is None:
+        stream = torch.cuda.current_stream().cuda_stream
+    n = len(models)
+    if n != len(in_cts) or n != len(out_cts):
+        raise ValueError("models / in_cts / out_cts length mismatch")
+    cin = (L.Cts * n)()
+    cout = (L.Cts * n)()
+    for b in range(n):
+        cin[b] = L.Cts(LAYOUT_PACKED, in_cts[b].data_ptr(), in_cts[b].numel() // CT_WORDS, None, None)
+        cout[b] = L.Cts(LAYOUT_PACKED, out_cts[b].data_ptr(), out_cts[b].numel() // CT_WORDS, None, None)
+    hm = (C.c_void_p * n)(*[m.handle.value for m in models])
+    L.check(L.lib().idash_b200_cloud_eval_device_multi_model(ctx.handle, n, hm, cin, cout, C.c_void_p(stream)))
+
+
 def cloud_compute_score_multi_device(ctxs, models, in_ct, out_ct, in_var=None, out_index=None, out_var=None) -> None:
     """One evaluation sharded over several GPUs of this process by contiguous target ranges (idash_b200_cloud_eval_multi_device):
     in_ct / out_ct (and the optional arrays) are torch CUDA tensors on ctxs[0]'s GPU, PACKED, inputs in identity order. models[g] is

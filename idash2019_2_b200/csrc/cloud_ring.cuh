@@ -76,6 +76,16 @@ struct RingParams {
     // it forms a global address. in / out describe batch 0 (layout, stride, count are common to all batches).
     uint32_t n_batches;
     unsigned long long batch_in[RG_MAX_BATCHES], batch_out[RG_MAX_BATCHES];   // words pointers of every batch
+    // ... and several MODELS: batch b may bring its own model of the same shape (same row count, hence tile count, same NUM_REGIONS /
+    // REGION_SIZE; NUM_SAMPLES and all coefficients may differ) -- BASELINE configs[3], the population-stratified model sets evaluated
+    // in one launch. For batches that share the model the entries repeat tiles / tile_rows / ... above.
+    const idash_b200_tile *batch_tiles[RG_MAX_BATCHES];
+    const uint32_t *batch_rows[RG_MAX_BATCHES];
+    const int32_t *batch_bias[RG_MAX_BATCHES];
+    const uint8_t *batch_coef[RG_MAX_BATCHES];
+    const uint32_t *batch_feat_used[RG_MAX_BATCHES];
+    uint32_t batch_nfw[RG_MAX_BATCHES], batch_S[RG_MAX_BATCHES];
+    unsigned long long batch_coef_bytes[RG_MAX_BATCHES];
     const uint32_t *slot_of_ct;
     uint32_t n_ct_slots;
     const uint32_t *slot_of_row;
@@ -493,7 +503,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
     const uint32_t n_my = t_end - t_begin;             // <= p.max_chunk_tiles
     for (uint32_t i = tid; i < n_my; i += RG_THREADS) {
         const uint32_t v = t_begin + i, b = batched ? v / p.n_tiles : 0u;
-        hdr_s[i] = ring_pack_hdr(p.tiles + p.tile_base + (v - b * p.n_tiles)) + (b << RG_BATCH_SHIFT);
+        hdr_s[i] = ring_pack_hdr((batched ? p.batch_tiles[b] : p.tiles) + p.tile_base + (v - b * p.n_tiles)) + (b << RG_BATCH_SHIFT);
     }
     const uint32_t w_slice = slice * 128u;
     const bool is_b = (w_slice & POLY_N) != 0 && !(k_knockout & 32u);     // knock-out 32: every slice runs the (cheaper) epilogue of polynomial a
@@ -546,7 +556,10 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
             const bool fast = ring_hdr(hdr_s, it).fast && p.slot_of_row == nullptr;
             uint64_t ptr_own = 0;
             uint8_t *base_lane = nullptr;
-            uint8_t *const out_words = batched ? reinterpret_cast<uint8_t *>(p.batch_out[batch_of(t)]) : p.out.words;
+            const uint32_t bt_ = batched ? batch_of(t) : 0u;
+            uint8_t *const out_words = batched ? reinterpret_cast<uint8_t *>(p.batch_out[bt_]) : p.out.words;
+            // (batched launches: the batch's own NUM_SAMPLES decides which words get the Constant)
+            const uint32_t bias_mul_t = !batched ? bias_mul : ((is_b && i_slice + word_in_slice < p.batch_S[bt_]) ? (uint32_t) IDASH_B200_ONE_IN_T32 : 0u);
             if (fast) {
                 const uint32_t row0 = __shfl_sync(0xFFFFFFFFu, row, 0);     // caller row of tile row col_base
                 base_lane = out_words + (uint64_t) row0 * p.out.stride + 4u * w_slice + lane_off;
@@ -561,14 +574,14 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
             bool arrived;
             if (fast) {
                 if (records) {
-                    if (is_b) arrived = ring_epilogue<EPI, true, IDASH_B200_RECORD_BYTES, true, ROT>(taddr, base_lane, 0, bias_addr, bias_mul, lane_off, k_knockout, keep_mask, rel);
+                    if (is_b) arrived = ring_epilogue<EPI, true, IDASH_B200_RECORD_BYTES, true, ROT>(taddr, base_lane, 0, bias_addr, bias_mul_t, lane_off, k_knockout, keep_mask, rel);
                     else arrived = ring_epilogue<EPI, true, IDASH_B200_RECORD_BYTES, false>(taddr, base_lane, 0, 0, 0, lane_off, k_knockout, 0xFFFFFFFFu, rel);
                 } else {
-                    if (is_b) arrived = ring_epilogue<EPI, true, IDASH_B200_CT_BYTES, true, ROT>(taddr, base_lane, 0, bias_addr, bias_mul, lane_off, k_knockout, keep_mask, rel);
+                    if (is_b) arrived = ring_epilogue<EPI, true, IDASH_B200_CT_BYTES, true, ROT>(taddr, base_lane, 0, bias_addr, bias_mul_t, lane_off, k_knockout, keep_mask, rel);
                     else arrived = ring_epilogue<EPI, true, IDASH_B200_CT_BYTES, false>(taddr, base_lane, 0, 0, 0, lane_off, k_knockout, 0xFFFFFFFFu, rel);
                 }
             } else {
-                arrived = ring_epilogue<EPI, false, 0, true, ROT>(taddr, nullptr, ptr_own, bias_addr, bias_mul, lane_off, k_knockout, keep_mask, rel);
+                arrived = ring_epilogue<EPI, false, 0, true, ROT>(taddr, nullptr, ptr_own, bias_addr, bias_mul_t, lane_off, k_knockout, keep_mask, rel);
             }
             if (!arrived) {
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -745,14 +758,17 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
         if (lane == 0) {
             uint32_t it = 0, cpos = 0, loaded = 0, freed = 0, done_it = 0;
             // the coefficient images of consecutive tiles are contiguous (layout.cpp): b_off advances by the tile's size
-            const uint4 h0 = __ldg(reinterpret_cast<const uint4 *>(p.tiles + real_tile(t_begin)));
+            uint32_t lb = batched ? batch_of(t_begin) : 0u;            // batch (= model) of the tile being loaded
+            const uint4 h0 = __ldg(reinterpret_cast<const uint4 *>((batched ? p.batch_tiles[lb] : p.tiles) + real_tile(t_begin)));
             uint64_t b_off = (uint64_t) h0.z | ((uint64_t) h0.w << 32);
             for (uint32_t t = t_begin; t < t_end; ++t, ++it) {
                 const RingTile T = ring_hdr(hdr_s, it);
-                if (batched && t != t_begin && real_tile(t) == p.tile_base) {     // next batch: back to the first image
-                    const uint4 hb = __ldg(reinterpret_cast<const uint4 *>(p.tiles + p.tile_base));
+                if (batched && t != t_begin && real_tile(t) == p.tile_base) {     // next batch: back to the first image (of that batch's model)
+                    lb = batch_of(t);
+                    const uint4 hb = __ldg(reinterpret_cast<const uint4 *>(p.batch_tiles[lb] + p.tile_base));
                     b_off = (uint64_t) hb.z | ((uint64_t) hb.w << 32);
                 }
+                const uint8_t *const coef_base = batched ? p.batch_coef[lb] : p.tile_coef;
                 // Barrier and metadata record it % 8 were last used by tile it - 8, whose epilogue reads the record until its last
                 // store. The MMAs of tile it - 4 being complete implies that: they needed the TMEM stage of tile it - 6, which the
                 // epilogue warps hand back only after they have finished tiles it - 7 and it - 8.
@@ -765,9 +781,9 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                     const uint32_t tt = real_tile(t);
                     uint8_t *const rec = smem + p.meta_off + (it & (RG_META_STAGES - 1u)) * (8u * TC_TN);
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(smem_u32(rec)), "l"(p.tile_rows + (uint64_t) tt * TC_TN), "r"(4u * TC_TN), "r"(smem_u32(bar)) : "memory");
+                                 ::"r"(smem_u32(rec)), "l"((batched ? p.batch_rows[lb] : p.tile_rows) + (uint64_t) tt * TC_TN), "r"(4u * TC_TN), "r"(smem_u32(bar)) : "memory");
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(smem_u32(rec + 4u * TC_TN)), "l"(p.tile_bias + (uint64_t) tt * TC_TN), "r"(4u * TC_TN), "r"(smem_u32(bar)) : "memory");
+                                 ::"r"(smem_u32(rec + 4u * TC_TN)), "l"((batched ? p.batch_bias[lb] : p.tile_bias) + (uint64_t) tt * TC_TN), "r"(4u * TC_TN), "r"(smem_u32(bar)) : "memory");
                 }
                 // Ring space is admitted chunk by chunk: whatever part of the image fits is copied NOW and the rest as soon as earlier
                 // tiles complete. (Waiting for room for the whole image put its copy -- ~1800 cycles for 28 KB at neighbors = 50, where
@@ -784,7 +800,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                     // free chunks that are already known to be free (no waiting): take as much as possible in one copy
                     const uint32_t n_now = min(min(T.nb - done_chunks, room), p.n_bchunks - cpos);
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(smem_u32(sB + cpos * TC_B_CHUNK)), "l"(p.tile_coef + b_off + (uint64_t) done_chunks * TC_B_CHUNK),
+                                 ::"r"(smem_u32(sB + cpos * TC_B_CHUNK)), "l"(coef_base + b_off + (uint64_t) done_chunks * TC_B_CHUNK),
                                    "r"(n_now * TC_B_CHUNK), "r"(smem_u32(bar))
                                  : "memory");
                     done_chunks += n_now;
@@ -797,8 +813,8 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                 // frees up then pays the L2 latency, not HBM's (measured at neighbors = 50: 0.673 -> 0.640 ms).
                 if (p.coef_prefetch) {
                     const uint64_t pf = b_off + (uint64_t) p.coef_prefetch * bytes;
-                    if (pf + bytes <= p.coef_bytes)
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.tile_coef + pf), "r"(bytes) : "memory");
+                    if (pf + bytes <= (batched ? p.batch_coef_bytes[lb] : p.coef_bytes))
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(coef_base + pf), "r"(bytes) : "memory");
                 }
             }
         }
@@ -855,7 +871,8 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
         auto load_block = [&](uint32_t kbv, uint4 (&w)[2][NW]) {
             const uint32_t kb = batched ? kbv & ((1u << RG_BATCH_SHIFT) - 1u) : kbv;
             const uint8_t *const in_words = batched ? reinterpret_cast<const uint8_t *>(p.batch_in[kbv >> RG_BATCH_SHIFT]) : p.in.words;
-            const uint32_t used_word = kb < p.n_feat_words ? __ldg(p.feat_used + kb) : 0u;
+            const uint32_t pb = batched ? kbv >> RG_BATCH_SHIFT : 0u;
+            const uint32_t used_word = kb < (batched ? p.batch_nfw[pb] : p.n_feat_words) ? __ldg((batched ? p.batch_feat_used[pb] : p.feat_used) + kb) : 0u;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const uint32_t k = k0 + 16u * h;

@@ -723,7 +723,8 @@ static inline const char *debug_env(const char *name) {
 // that the ring kernel takes the model and that the inputs are in identity order.
 static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtView &in, const CtView &out,
                         const uint32_t *d_slot_of_row, cudaStream_t st, const Piece *piece = nullptr,
-                        uint32_t n_batches = 1, const CtView *ins = nullptr, const CtView *outs = nullptr) {
+                        uint32_t n_batches = 1, const CtView *ins = nullptr, const CtView *outs = nullptr,
+                        const idash_b200_model *const *bms = nullptr) {     // bms: the model of every batch (null: all batches share m)
     const idash_b200_layout *L = m->layout;
     if (out.count != L->n_rows) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: out->count (%llu) != model rows (%llu)",
                                                  (unsigned long long) out.count, (unsigned long long) L->n_rows);
@@ -795,6 +796,7 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
     f.var_wsum = m->d_var_wsum;
     for (uint32_t b = 0; b < n_batches; ++b) {
         if (n_batches > 1) { f.in = ins[b]; f.out = outs[b]; }
+        if (bms) { f.var_ptr = bms[b]->d_var_ptr; f.var_ct = bms[b]->d_var_ct; f.var_w = bms[b]->d_var_w; f.out_bidx = bms[b]->d_out_bidx; f.var_wsum = bms[b]->d_var_wsum; }
         f.var_uniform = nullptr;
         if ((f.in.records || f.in.variance) && f.in.count) {
             CUDA_TRY(cudaMemsetAsync(c->d_var_flag, 0, 2 * sizeof(uint64_t), c->s_aux));
@@ -823,7 +825,13 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
         p.n_slices = rp.n_slices; p.n_chunks = rp.n_chunks; p.n_slots = rp.n_slots; p.n_bchunks = rp.n_bchunks; p.max_chunk_tiles = rp.max_chunk_tiles;
         const uint32_t max_nb = L->tile_kmax / 32u;
         p.n_batches = n_batches;
-        for (uint32_t b = 0; b < n_batches && n_batches > 1; ++b) { p.batch_in[b] = (unsigned long long) ins[b].words; p.batch_out[b] = (unsigned long long) outs[b].words; }
+        for (uint32_t b = 0; b < n_batches && n_batches > 1; ++b) {
+            const idash_b200_model *mb = bms ? bms[b] : m;
+            p.batch_in[b] = (unsigned long long) ins[b].words; p.batch_out[b] = (unsigned long long) outs[b].words;
+            p.batch_tiles[b] = mb->d_tiles; p.batch_rows[b] = mb->d_tile_rows; p.batch_bias[b] = mb->d_tile_bias; p.batch_coef[b] = mb->d_tile_coef;
+            p.batch_feat_used[b] = mb->d_feat_used; p.batch_nfw[b] = (uint32_t) mb->layout->feat_used.size(); p.batch_S[b] = mb->layout->S;
+            p.batch_coef_bytes[b] = mb->layout->tile_coef.size();
+        }
         p.meta_off = p.n_slots * RG_BLOCK_BYTES + p.n_bchunks * TC_B_CHUNK;
         p.hdr_off = p.meta_off + RG_META_BYTES;
         p.in = in; p.out = out;
@@ -980,6 +988,49 @@ extern "C" int idash_b200_cloud_eval_device_batched(idash_b200_ctx *c, const ida
     if (one_launch) return launch_cloud(c, m, vin[0], vout[0], nullptr, (cudaStream_t) stream, nullptr, n_batches, vin.data(), vout.data());
     for (uint32_t b = 0; b < n_batches; ++b)
         if ((rc = launch_cloud(c, m, vin[b], vout[b], nullptr, (cudaStream_t) stream))) return rc;
+    return IDASH_B200_OK;
+}
+
+// Several MODELS of the same shape on their own input / output sets in ONE launch of the persistent ring kernel: BASELINE configs[3],
+// the population-stratified model sets (_AFR / _AMR / _EUR: three `cloud` runs of the reference, eval/idash.cpp:763-848 once per
+// population). The launch walks the tiles of every (model, input set) pair as virtual tiles, like the batched launch of one model;
+// every pair brings its own tile list, coefficient images, row / Constant tables and NUM_SAMPLES. Falls back to one launch per pair
+// when the models do not have the same shape or the ring kernel does not take them.
+extern "C" int idash_b200_cloud_eval_device_multi_model(idash_b200_ctx *c, uint32_t n, const idash_b200_model *const *ms,
+                                                        const idash_b200_cts *in, const idash_b200_cts *out, void *stream) {
+    clear_error();
+    if (!c || !ms || !in || !out) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_device_multi_model: null argument");
+    if (n == 0) return IDASH_B200_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    std::vector<CtView> vin(n), vout(n);
+    int rc;
+    bool one_launch = n > 1 && n <= RG_MAX_BATCHES;
+    const idash_b200_model *widest = ms[0];
+    for (uint32_t b = 0; b < n; ++b) {
+        if (!ms[b]) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_device_multi_model: null model %u", b);
+        if (ms[b]->device != c->device) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_device_multi_model: model %u lives on device %d, ctx on %d", b, ms[b]->device, c->device);
+        if ((rc = make_view(&in[b], false, &vin[b], "cloud_eval_device_multi_model(in)"))) return rc;
+        if ((rc = make_view(&out[b], true, &vout[b], "cloud_eval_device_multi_model(out)"))) return rc;
+        const idash_b200_layout *L = ms[b]->layout, *L0 = ms[0]->layout;
+        if (vout[b].count != L->n_rows) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval_device_multi_model: out[%u].count != model rows", b);
+        one_launch = one_launch && ring_selected(c, L) && L->n_overflow_rows == 0 && L->NR == L0->NR && L->RS == L0->RS && L->n_rows == L0->n_rows &&
+                     L->tiles.size() == L0->tiles.size() &&
+                     !vin[b].records && vin[b].index == nullptr && vin[b].count == vin[0].count && vin[b].stride == vin[0].stride &&
+                     (vin[b].variance != nullptr) == (vin[0].variance != nullptr) &&
+                     vout[b].records == vout[0].records && vout[b].stride == vout[0].stride &&
+                     (vout[b].index != nullptr) == (vout[0].index != nullptr) && (vout[b].variance != nullptr) == (vout[0].variance != nullptr);
+        if (L->tile_kmax > widest->layout->tile_kmax) widest = ms[b];
+    }
+    if (one_launch) {
+        RingPlan rp;
+        uint64_t blocks = 0;
+        for (uint32_t b = 0; b < n; ++b) blocks = std::max<uint64_t>(blocks, (ms[b]->layout->tiles.back().f_base >> 5) + IDASH_B200_TILE_KMAX / 32u);
+        one_launch = ring_plan(c, widest->layout, widest->layout->tiles.size(), n, &rp) && blocks < (1u << RG_BATCH_SHIFT);
+    }
+    // the widest model sizes the shared-memory plan; its arrays also stand in RingParams' single-model fields (unused by a batched launch)
+    if (one_launch) return launch_cloud(c, widest, vin[0], vout[0], nullptr, (cudaStream_t) stream, nullptr, n, vin.data(), vout.data(), ms);
+    for (uint32_t b = 0; b < n; ++b)
+        if ((rc = launch_cloud(c, ms[b], vin[b], vout[b], nullptr, (cudaStream_t) stream))) return rc;
     return IDASH_B200_OK;
 }
 

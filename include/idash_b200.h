@@ -176,6 +176,13 @@ int idash_b200_model_input_range(const idash_b200_model *model, uint64_t row_beg
 int idash_b200_cloud_eval_device_batched(idash_b200_ctx *ctx, const idash_b200_model *model, uint32_t n_batches,
                                          const idash_b200_cts *in, const idash_b200_cts *out, void *cuda_stream);
 
+/* n models of the same shape (same output rows, NUM_REGIONS, REGION_SIZE; NUM_SAMPLES and coefficients may differ), each on its own
+ * input / output set: in[b] -> out[b] under model[b]. BASELINE configs[3] -- the population-stratified model sets, which the reference
+ * evaluates as separate `cloud` runs -- in ONE launch of the persistent kernel (n <= 8, PACKED identity inputs of equal size);
+ * otherwise one launch per pair on the same stream. Results are identical to n calls of cloud_eval_device. */
+int idash_b200_cloud_eval_device_multi_model(idash_b200_ctx *ctx, uint32_t n, const idash_b200_model *const *model,
+                                             const idash_b200_cts *in, const idash_b200_cts *out, void *cuda_stream);
+
 /* One evaluation sharded over n_gpus GPUs of this process by contiguous target ranges, with the data resident on the FIRST GPU
  * (scatter of the input slabs and gather of the outputs over NVLink; the loop being cut is eval/idash.cpp:779-790).
  * ctx[g] / model[g]: one context per GPU and the model uploaded to it (model[0] and its idash_b200_model_clone()s). `in` (PACKED, identity

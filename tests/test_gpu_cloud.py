@@ -132,6 +132,38 @@ def test_cloud_batched_launch_matches_single_launches(gpu_ctx, S, n_batches, G):
     m.free()
 
 
+@pytest.mark.parametrize("sizes,n,G", [((335, 334, 335), 5, 2600), ((335, 334, 335), 20, 900), ((1004, 1000, 980, 1004), 5, 1500)])
+def test_cloud_population_models_in_one_launch(gpu_ctx, sizes, n, G):
+    """BASELINE configs[3]: the population-stratified model sets -- one model and one set of ciphertexts per population, sample counts
+    that differ (335 / 334 / 335 columns of the same tag file, so NUM_REGIONS and REGION_SIZE agree) -- evaluated by ONE launch of
+    the ring kernel (idash_b200_cloud_eval_device_multi_model) == one launch per population == the oracle, for every population:
+    each model's own coefficients, Constants and NUM_SAMPLES (the Constant is added to b[0..S) of ITS population only)."""
+    import torch
+    cases = [make_case(S, T=500, G=G, n=n, seed=31 * k + S) for k, S in enumerate(sizes)]
+    assert len({(c[0].NR, c[0].RS) for c in cases}) == 1
+    gpu_ctx.set_kernel(api.KERNEL_AUTO)
+    models = [api.Model(gpu_ctx, S, geo.NR, geo.RS, model.out_bidx, model.row_ptr, model.col, model.coef) for S, (geo, model, _, _) in zip(sizes, cases)]
+    ins = [torch.from_numpy(c[2].view(np.int32)).cuda() for c in cases]
+    n_out = cases[0][1].n_out
+    outs_m = [torch.zeros((n_out, 2048), dtype=torch.int32, device="cuda") for _ in cases]
+    outs_s = [torch.zeros((n_out, 2048), dtype=torch.int32, device="cuda") for _ in cases]
+    l0 = gpu_ctx.kernel_launches()
+    api.cloud_compute_score_device_multi_model(gpu_ctx, models, ins, outs_m)
+    torch.cuda.synchronize()
+    main_launches = gpu_ctx.kernel_launches() - l0
+    assert gpu_ctx.last_kernel() == _lib.KERNEL_TENSOR_RING
+    assert main_launches == 1 + len(cases)               # one ring launch + one (tiny) per-row finalize launch per population
+    for b, (S, (geo, model, cts, var)) in enumerate(zip(sizes, cases)):
+        api.cloud_compute_score_device(gpu_ctx, models[b], ins[b], outs_s[b])
+        torch.cuda.synchronize()
+        assert torch.equal(outs_m[b], outs_s[b]), b
+        ref_out, _ = _oracle(S, geo, model, cts, var)
+        assert np.array_equal(outs_m[b].cpu().numpy().view(np.uint32), ref_out), b
+    gpu_ctx.check_device_status()
+    for m in models:
+        m.free()
+
+
 def test_cloud_permuted_input_slots_and_scattered_outputs(kctx):
     S = 400
     geo, model, cts, var = make_case(S, T=50, G=80, n=5, seed=21)
