@@ -59,7 +59,8 @@ struct RingParams {
     uint32_t n_feat_words;
     uint32_t n_tiles;              // tiles of this launch: [tile_base, tile_base + n_tiles)
     uint32_t tile_base;
-    uint32_t n_chunks;             // gridDim.x = n_slices * n_chunks
+    uint32_t n_chunks;             // regular chunks; gridDim.x = n_slices * (n_chunks + (extra_tiles ? 1 : 0))
+    uint32_t extra_tiles;          // virtual tiles of the short extra chunk at the end of the list (0: none), see the kernel
     uint32_t n_slices;             // 128-word slices of the ciphertext axis that are COMPUTED: 16, or 8 + ceil(RS / 128) when
                                    // NUM_REGIONS > 1 (b[RS..N) is zero, eval/idash.cpp:839-841: those slices are only zero-filled)
     uint32_t n_slots;              // input-block ring slots (>= widest tile in blocks, + prefetch)
@@ -484,11 +485,17 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
     __shared__ uint32_t mma_issued_s;       // tiles of this CTA whose MMAs have all been handed to the tensor pipe (tune & 32)
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // CTAs [0, n_slices * n_chunks) are the (slice, chunk) pairs that fill the GPU. The SMs that division leaves over (148 = 16 x 9 + 4)
+    // get one more, SHORT chunk at the end of the tile list (extra_tiles > 0: n_slices more CTAs): its CTAs run in waves on the spare SMs
+    // -- the first few at once, the others as those retire -- so the chunk is 1 / waves as long as a regular one and all SMs finish
+    // together. (Measured: the kernel's time follows the number of SMs it uses -- 9 / 8 / 7 chunks at neighbors = 5: 0.454 / 0.499 /
+    // 0.544 ms, profiles/r02_ring_sm_count.txt.)
     const uint32_t chunk = blockIdx.x / p.n_slices, slice = blockIdx.x - chunk * p.n_slices;
+    const bool extra = chunk >= p.n_chunks;
     // virtual tiles of this chunk: v in [t_begin, t_end), real tile = tile_base + v % n_tiles, batch = v / n_tiles
-    const uint32_t n_virtual = p.n_tiles * p.n_batches;
-    const uint32_t t_begin = (uint32_t) ((uint64_t) n_virtual * chunk / p.n_chunks);
-    const uint32_t t_end = (uint32_t) ((uint64_t) n_virtual * (chunk + 1) / p.n_chunks);
+    const uint32_t n_virtual = p.n_tiles * p.n_batches, n_main = n_virtual - p.extra_tiles;
+    const uint32_t t_begin = extra ? n_main : (uint32_t) ((uint64_t) n_main * chunk / p.n_chunks);
+    const uint32_t t_end = extra ? n_virtual : (uint32_t) ((uint64_t) n_main * (chunk + 1) / p.n_chunks);
     if (t_begin >= t_end) return;
     constexpr bool batched = BATCHED;
     uint32_t *hdr_s = reinterpret_cast<uint32_t *>(smem + p.hdr_off);
@@ -610,6 +617,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
         const uint32_t q = warp == RG_WARP_MMA2 ? 1u : 0u;
         const uint32_t n_slots = p.n_slots, n_bchunks = p.n_bchunks;
         const bool fifo = (k_tune & 32u) != 0u;
+        const uint32_t stagger = ((k_tune >> 12) & 15u) ? min((k_tune >> 12) & 15u, 8u) : 8u;     // eighths of a tile, see pub_ks below
         const uint64_t da_base = tc_desc(smem_u32(sA), TC_A_LBO, TC_A_SBO);
         const uint64_t db_base = tc_desc(smem_u32(sB), TC_B_LBO, TC_B_SBO);
         uint32_t it = 0;
@@ -663,6 +671,11 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                     // every lane blocks on its own barrier with try_wait (the hardware suspends the thread until the phase completes or a
                     // time limit expires): no polling granularity between "TMEM stage released" and the first MMA of the next tile
                     if (bar) mbar_wait(bar, par);
+                    if (order_lane) {
+                        uint32_t v;
+                        do asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(&mma_issued_s)) : "memory");
+                        while ((int32_t) (v - it) < 0);
+                    }
                     if (k_trace) t_done = clock64();
                     __syncwarp();
                 } else
@@ -698,6 +711,9 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                 uint32_t aslot = __shfl_sync(0xFFFFFFFFu, first_slot, 0);
                 const uint32_t d0 = tmem_u + st * 4u * TC_TN;
                 uint32_t bchunk = __shfl_sync(0xFFFFFFFFu, bpos, 0);
+                // staggered hand-over (tune & 32): the other warp may start on tile it + 1 once stagger / 8 of this tile's K steps have been
+                // handed to the tensor pipe (8 / 8 = strictly one tile after the other)
+                const uint32_t pub_ks = fifo ? (nb_u * stagger + 7u) / 8u - 1u : 0xFFFFFFFFu;
                 if (lane == 0) RG_TRACE(7, it);
                 if (!(k_knockout & 1u)) {
                     if (k_tune & 128u) {
@@ -705,6 +721,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                             const uint64_t da = da_base + (uint64_t) ((aslot * RG_BLOCK_BYTES) >> 4), db = db_base + (uint64_t) ((bchunk * TC_B_CHUNK) >> 4);
                             if (q) tc_mma_kstep_ws_p<1>(d0, da, RG_PLANE_BYTES >> 4, db, ks == 0, leader);
                             else tc_mma_kstep_ws_p<0>(d0, da, RG_PLANE_BYTES >> 4, db, ks == 0, leader);
+                            if (ks == pub_ks && leader) progress_publish(&mma_issued_s, it + 1u);
                             if (++aslot == n_slots) aslot = 0;
                             if (++bchunk == n_bchunks) bchunk = 0;
                         }
@@ -712,6 +729,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                     for (uint32_t ks = 0; ks < nb_u; ++ks) {
                         tc_mma_kstep_p(d0, da_base + (uint64_t) ((aslot * RG_BLOCK_BYTES) >> 4), RG_PLANE_BYTES >> 4,
                                        db_base + (uint64_t) ((bchunk * TC_B_CHUNK) >> 4), ks == 0, leader);
+                        if (ks == pub_ks && leader) progress_publish(&mma_issued_s, it + 1u);
                         if (++aslot == n_slots) aslot = 0;
                         if (++bchunk == n_bchunks) bchunk = 0;
                     }

@@ -52,7 +52,10 @@
 #define DT_WARP_MMA 4u
 #define DT_WARP_PROD 5u
 #define DT_PROD_WARPS 8u
-#define DT_THREADS ((DT_WARP_PROD + DT_PROD_WARPS) * 32u)
+#define DT_WARP_BLOAD (DT_WARP_PROD + DT_PROD_WARPS)          // one thread: bulk copies of the b words into the b ring
+#define DT_THREADS ((DT_WARP_BLOAD + 1u) * 32u)
+#define DT_B_STAGE_BYTES (16u * 512u)                          // one stage of the b ring: the 128 b words of a j block of HALF a group (16 ciphertexts)
+#define DT_MAX_BSTAGES 8u
 
 struct DecTcParams {
     CtView in;
@@ -60,14 +63,18 @@ struct DecTcParams {
     uint64_t n_groups;
     uint32_t S;
     uint32_t n_slots;       // ring slots (>= DT_GROUP_SLOTS)
+    uint32_t n_bstages;     // stages of the b ring (>= 2; a j block of a group takes two)
     float *scores;          // [n_ct][S] or null
     uint32_t *phase;        // [n_ct][1024] or null
     KeyBits key;
     uint32_t knockout;      // profiling aid (IDASH_B200_DECRYPT_KNOCKOUT, results are wrong when non-zero): 1 no MMAs, 2 no output
-                            // stores, 4 no b loads, 8 no a loads, 16 no operand stores, 32 no epilogue TMEM loads
+                            // stores, 4 no b loads, 8 no a loads, 16 no operand stores, 32 no epilogue TMEM loads, 64 MMAs one j block
+                            // at a time without the weight-stationary pairing
 };
 
-__host__ __device__ constexpr uint32_t dec_tc_smem_bytes(uint32_t n_slots) { return DT_TOEP_BYTES + n_slots * DT_SLOT_BYTES; }
+__host__ __device__ constexpr uint32_t dec_tc_smem_bytes(uint32_t n_slots, uint32_t n_bstages) {
+    return DT_TOEP_BYTES + n_slots * DT_SLOT_BYTES + n_bstages * DT_B_STAGE_BYTES;
+}
 
 // instruction descriptor: D = s32, A = s8 MN-major, B = u8 K-major, M = 128, N = n
 __host__ __device__ constexpr uint32_t dec_idesc(uint32_t n) {
@@ -86,24 +93,36 @@ __device__ __forceinline__ void dec_split_rev(const uint4 w, uint32_t &l0, uint3
 
 __device__ __forceinline__ uint32_t ldg32_nc(const void *p) { return __ldg(reinterpret_cast<const uint32_t *>(p)); }
 
-// One pass of one epilogue warp: 32 phase coefficients (lanes) x 32 ciphertexts. STRIDE (bytes between ciphertexts),
-// PHASE and FULL (all 32 ciphertexts of the group exist) are compile-time, so that every load / phase store is base +
-// immediate and the score address is one pointer walk: ~9 instructions per output (the first version spent ~40 and the
-// epilogue warps, not the tensor pipe or HBM, set the pace -- profiles/r01_ncu_decrypt_tc.txt).
-// bw[] holds this pass's b words on entry; as soon as a chunk of 8 is consumed its registers are refilled with the b
-// words of the NEXT pass (bj_next, n_next ciphertexts; n_next = 0: none), so the b loads of pass p+1 are in flight
-// while pass p is processed and while the warp waits for the next accumulator -- their latency is never exposed.
-template <uint32_t STRIDE, bool PHASE, bool FULL>
-__device__ __forceinline__ void dec_epilogue_pass(uint32_t (&bw)[DT_CTS], const uint8_t *bj_next, uint32_t n_next, uint32_t n_here,
-                                                  uint32_t taddr, float *sc, uint32_t S, bool sc_on, uint32_t *ph, uint64_t *tempty) {
+// One pass of one epilogue warp: 32 phase coefficients (lanes) x 32 ciphertexts. PHASE and FULL (all 32 ciphertexts of the group
+// exist) are compile-time, so that every phase store is base + immediate and the score address is one pointer walk: ~9 instructions
+// per output (the first version spent ~40 and the epilogue warps, not the tensor pipe or HBM, set the pace).
+// The b words come from the b ring in shared memory (b_addr = this lane's word of ciphertext 0 of the stage; + 512 bytes per
+// ciphertext), filled by bulk copies one or more j blocks ahead. They used to be 32-bit global loads prefetched one pass ahead into
+// 32 registers per lane: 4 KB in flight per warp, 16 KB per SM -- with ~1 us of latency that caps the b stream at ~2.4 TB/s over the
+// GPU, and the epilogue alone (b in, scores out) took 0.52 of the kernel's 0.71 ms (knock-outs, profiles/r02_decrypt_knockout.txt).
+template <bool PHASE, bool FULL>
+__device__ __forceinline__ void dec_epilogue_pass(uint32_t b_addr0, uint32_t b_addr1, uint64_t *bfull0, uint64_t *bfull1, uint32_t bpar0, uint32_t bpar1,
+                                                  uint64_t *bempty0, uint64_t *bempty1, uint32_t n_here, uint32_t taddr, float *sc, uint32_t S,
+                                                  bool sc_on, uint32_t *ph, uint64_t *tempty) {
     uint8_t *scp = reinterpret_cast<uint8_t *>(sc);   // walks down the 32 score rows of the group: + 4 S bytes per ciphertext
     const uint32_t s4 = 4u * S;
 #pragma unroll
     for (uint32_t chunk = 0; chunk < 4; ++chunk) {
         uint32_t v[4][8];     // v[m][4 e + l]: plane l of ciphertext 8 chunk + 2 m + e
+        uint32_t bw[8];
 #pragma unroll
         for (uint32_t m = 0; m < 4; ++m) tc_ld8(taddr + chunk * 32u + m * 8u, v[m]);
+        // b words: ciphertexts 0-15 of the group from the first half stage, 16-31 from the second
+        if (chunk == 0) mbar_wait(bfull0, bpar0);
+        if (chunk == 2) mbar_wait(bfull1, bpar1);
+        const uint32_t ba = (chunk < 2 ? b_addr0 : b_addr1) + (chunk & 1u) * 8u * 512u;
+#pragma unroll
+        for (uint32_t c = 0; c < 8; ++c) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(bw[c]) : "r"(ba + c * 512u));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (chunk & 1u) {      // the half stage's words are in registers: hand it back to the loader
+            __syncwarp();
+            if ((threadIdx.x & 31u) == 0) mbar_arrive(chunk == 1 ? bempty0 : bempty1);
+        }
         if (chunk == 3) {
             // the accumulator is in registers: hand the TMEM stage back before the last 8 outputs are computed and stored
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -113,8 +132,7 @@ __device__ __forceinline__ void dec_epilogue_pass(uint32_t (&bw)[DT_CTS], const 
         for (uint32_t c = 0; c < 8; ++c) {
             const uint32_t cc = chunk * 8u + c;
             const uint32_t *q = &v[c >> 1][4u * (c & 1u)];
-            const uint32_t phs = bw[cc] - (q[0] + (q[1] << 8) + (q[2] << 16) + (q[3] << 24));
-            bw[cc] = cc < n_next ? ldg32_nc(bj_next + cc * STRIDE) : 0u;
+            const uint32_t phs = bw[c] - (q[0] + (q[1] << 8) + (q[2] << 16) + (q[3] << 24));
             const bool here = FULL || cc < n_here;
             if (PHASE && here) stg32_stream(ph + cc * POLY_N, phs);
             // (float) (double(int32) / 2^32): one rounding to 24 bits, then an exact power-of-two scale --
@@ -130,6 +148,7 @@ template <uint32_t STRIDE, bool PHASE>
 __global__ void __launch_bounds__(DT_THREADS, 1) decrypt_tc_kernel(const DecTcParams p) {   // 13 warps: 4 on one SM sub-partition (16 K registers) -> 128 per thread
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar[DT_MAX_SLOTS], empty_bar[DT_MAX_SLOTS], tfull_bar[4], tempty_bar[4];
+    __shared__ __align__(8) uint64_t bfull_bar[DT_MAX_BSTAGES], bempty_bar[DT_MAX_BSTAGES];
     __shared__ uint32_t tmem_base_s;
     __shared__ uint32_t key_s[32];
 
@@ -137,11 +156,14 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decrypt_tc_kernel(const DecTcPa
     const uint32_t NS = p.n_slots;
     uint8_t *toep = smem;
     uint8_t *ring = smem + DT_TOEP_BYTES;
+    uint8_t *bring = ring + NS * DT_SLOT_BYTES;
+    const uint32_t NB = p.n_bstages;
 
     if (tid < 32) key_s[tid] = p.key.w[tid];
     if (tid == 0) {
         for (uint32_t i = 0; i < NS; ++i) { mbar_init(&full_bar[i], DT_PROD_WARPS * 32u); mbar_init(&empty_bar[i], 1); }
         for (uint32_t i = 0; i < 4; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], DT_EPI_WARPS * 32u); }
+        for (uint32_t i = 0; i < NB; ++i) { mbar_init(&bfull_bar[i], 1); mbar_init(&bempty_bar[i], DT_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == DT_WARP_MMA) {
@@ -173,21 +195,12 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decrypt_tc_kernel(const DecTcPa
         // ---------------- epilogue: phase = b - sum_l 2^(8l) P_l, decode, store. Warp = TMEM lane quadrant; every j block.
         const uint32_t qd = warp;
         const uint32_t j_w = qd * 32u + lane;        // + 128 jb
-        const bool st_on = !(p.knockout & 2u), ld_on = !(p.knockout & 4u);
-        uint32_t pc = 0;                             // j blocks done: TMEM stage pc % 4
-        uint32_t bw[DT_CTS];
-        {   // b words of the first j block
-            const uint64_t g = blockIdx.x;
-            const uint32_t n0 = (g < p.n_groups && ld_on) ? (uint32_t) min((uint64_t) DT_CTS, p.n_ct - g * DT_CTS) : 0u;
-            const uint8_t *bj = p.in.words + g * DT_CTS * STRIDE + 4u * POLY_N + 4u * j_w;
-#pragma unroll
-            for (uint32_t c = 0; c < DT_CTS; ++c) bw[c] = c < n0 ? ldg32_nc(bj + c * STRIDE) : 0u;
-        }
+        const bool st_on = !(p.knockout & 2u);
+        uint32_t pc = 0;                             // j blocks done: TMEM stage pc % 4, b stage pc % NB
+        uint32_t bst = 0, bph = 0;
         for (uint64_t g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
             const uint64_t ct0 = g * DT_CTS;
             const uint32_t n_here = (uint32_t) min((uint64_t) DT_CTS, p.n_ct - ct0);
-            const uint64_t g_next = g + gridDim.x;
-            const uint32_t n_after = (g_next < p.n_groups && ld_on) ? (uint32_t) min((uint64_t) DT_CTS, p.n_ct - g_next * DT_CTS) : 0u;
 #pragma unroll 1
             for (uint32_t jb = 0; jb < 8; ++jb, ++pc) {
                 const uint32_t stage = pc & 3u;
@@ -195,15 +208,44 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decrypt_tc_kernel(const DecTcPa
                 const uint32_t taddr = tmem + ((qd * 32u) << 16) + stage * DT_N;
                 float *sc = p.scores ? p.scores + ct0 * p.S + j : nullptr;
                 uint32_t *ph = p.phase ? p.phase + ct0 * POLY_N + j : nullptr;
-                // the j block after this one: same group, next 128 coefficients -- or the first j block of the CTA's next group
-                const uint8_t *bj_next = jb < 7u ? p.in.words + ct0 * STRIDE + 4u * POLY_N + 4u * (j + 128u)
-                                                 : p.in.words + g_next * DT_CTS * STRIDE + 4u * POLY_N + 4u * j_w;
-                const uint32_t n_next = jb < 7u ? (ld_on ? n_here : 0u) : n_after;
                 mbar_wait(&tfull_bar[stage], (pc >> 2) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const bool sc_on = sc != nullptr && j < p.S && st_on;
-                if (n_here == DT_CTS) dec_epilogue_pass<STRIDE, PHASE, true>(bw, bj_next, n_next, n_here, taddr, sc, p.S, sc_on, ph, &tempty_bar[stage]);
-                else dec_epilogue_pass<STRIDE, PHASE, false>(bw, bj_next, n_next, n_here, taddr, sc, p.S, sc_on, ph, &tempty_bar[stage]);
+                const uint32_t h0 = bst, p0 = bph;
+                if (++bst == NB) { bst = 0; bph ^= 1u; }
+                const uint32_t h1 = bst, p1 = bph;
+                if (++bst == NB) { bst = 0; bph ^= 1u; }
+                const uint32_t a0 = smem_u32(bring + h0 * DT_B_STAGE_BYTES) + 4u * j_w, a1 = smem_u32(bring + h1 * DT_B_STAGE_BYTES) + 4u * j_w;
+                if (n_here == DT_CTS) dec_epilogue_pass<PHASE, true>(a0, a1, &bfull_bar[h0], &bfull_bar[h1], p0, p1, &bempty_bar[h0], &bempty_bar[h1], n_here, taddr, sc, p.S, sc_on, ph, &tempty_bar[stage]);
+                else dec_epilogue_pass<PHASE, false>(a0, a1, &bfull_bar[h0], &bfull_bar[h1], p0, p1, &bempty_bar[h0], &bempty_bar[h1], n_here, taddr, sc, p.S, sc_on, ph, &tempty_bar[stage]);
+            }
+        }
+    } else if (warp == DT_WARP_BLOAD) {
+        // ---------------- b loader: lane c copies the 128 b words (512 bytes) of ciphertext c of the group for every j block
+        // into the b ring -- 32 bulk copies per warp instruction (issued one by one from a single thread they took about as long as the
+        // pass itself)
+        uint32_t bst = 0, bph = 0;
+        const uint32_t half = lane >> 4, cl = lane & 15u;           // lanes 0-15 fill the stage of ciphertexts 0-15, lanes 16-31 the next one
+        for (uint64_t g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
+            const uint64_t ct0 = g * DT_CTS;
+            const uint32_t n_here = (p.knockout & 4u) ? 0u : (uint32_t) min((uint64_t) DT_CTS, p.n_ct - ct0);
+            const uint8_t *src = p.in.words + (ct0 + lane) * STRIDE + 4u * POLY_N;
+#pragma unroll 1
+            for (uint32_t jb = 0; jb < 8; ++jb) {
+                uint32_t my = bst + half, myph = bph;
+                if (my >= NB) { my -= NB; myph ^= 1u; }
+                uint64_t *const bar = &bfull_bar[my];
+                if (cl == 0) {
+                    mbar_wait(&bempty_bar[my], myph ^ 1u);
+                    const uint32_t n_half = n_here > 16u * half ? min(16u, n_here - 16u * half) : 0u;
+                    mbar_arrive_expect_tx(bar, n_half * 512u);
+                }
+                __syncwarp();
+                if (lane < n_here)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(smem_u32(bring + my * DT_B_STAGE_BYTES) + cl * 512u), "l"(src + 512u * jb), "r"(512u), "r"(smem_u32(bar)) : "memory");
+                bst += 2u;
+                if (bst >= NB) { bst -= NB; bph ^= 1u; }
             }
         }
     } else if (warp == DT_WARP_MMA) {
@@ -215,6 +257,45 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decrypt_tc_kernel(const DecTcPa
         const uint32_t b_lo0 = ((smem_u32(ring) >> 4) & 0x3FFFu) | ((DT_B_LBO >> 4) << 16), b_hi = (DT_B_SBO >> 4) | (1u << 14);
         auto mk = [](uint32_t lo, uint32_t hi) { uint64_t d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi)); return d; };
         uint32_t slot0 = 0, ph0 = 0, pc = 0;       // pc counts j blocks: 8 per group, TMEM stage pc % 4
+        if (!(p.knockout & 64u)) {
+            // Weight-stationary schedule (the production schedule; knock-out 64 selects the one-j-block-at-a-time loop below): the j blocks are taken in PAIRS. For every K step the byte-plane chunk B (4 KB) is fetched
+            // into the tensor core's collector buffer once and multiplied by the Toeplitz tiles of both j blocks (tcgen05.mma.ws,
+            // fill -> lastuse), so an MMA reads 6 KB of operands from shared memory instead of 8 KB -- the pipe the producers' operand
+            // stores and the epilogue share with the MMAs. Two accumulators (TMEM stages pc % 4 and pc % 4 + 1) are written per pair.
+            for (uint64_t g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
+#pragma unroll 1
+                for (uint32_t jp = 0; jp < 4; ++jp, pc += 2) {
+                    const uint32_t st0 = pc & 3u;               // even: st0 + 1 <= 3
+                    mbar_wait(&tempty_bar[st0], ((pc >> 2) & 1u) ^ 1u);
+                    mbar_wait(&tempty_bar[st0 + 1u], ((pc >> 2) & 1u) ^ 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    uint32_t slot = slot0, ph = ph0;
+                    uint32_t a_lo = a_lo0 + 128u * (2u * jp);
+                    const uint32_t d0 = tmem + st0 * DT_N, d1 = d0 + DT_N;
+#pragma unroll 1
+                    for (uint32_t s = 0; s < DT_GROUP_SLOTS; ++s, a_lo += 128u) {
+                        if (jp == 0) {
+                            mbar_wait(&full_bar[slot], ph);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        }
+                        const uint32_t b_lo = b_lo0 + slot * (DT_SLOT_BYTES >> 4);
+                        if (!(p.knockout & 1u))
+#pragma unroll
+                        for (uint32_t kk = 0; kk < 4; ++kk) {
+                            const uint64_t db = mk(b_lo + kk * ((2u * DT_B_LBO) >> 4), b_hi);
+                            tc_mma_ws_p<0, 0>(d0, mk(a_lo + 32u * kk, a_hi), db, dec_idesc(DT_N), (s | kk) != 0u, leader);
+                            tc_mma_ws_p<0, 2>(d1, mk(a_lo + 128u + 32u * kk, a_hi), db, dec_idesc(DT_N), (s | kk) != 0u, leader);
+                        }
+                        if (jp == 3 && leader) tc_commit(&empty_bar[slot]);   // the group is done with this slot
+                        if (++slot == NS) { slot = 0; ph ^= 1u; }
+                    }
+                    if (leader) { tc_commit(&tfull_bar[st0]); tc_commit(&tfull_bar[st0 + 1u]); }
+                    __syncwarp();
+                }
+                slot0 += DT_GROUP_SLOTS;
+                if (slot0 >= NS) { slot0 -= NS; ph0 ^= 1u; }
+            }
+        } else
         for (uint64_t g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
 #pragma unroll 1
             for (uint32_t jb = 0; jb < 8; ++jb, ++pc) {

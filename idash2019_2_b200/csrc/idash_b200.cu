@@ -449,10 +449,10 @@ extern "C" int idash_b200_init(idash_b200_ctx **out, int device) {
     CUDA_TRY(cudaFuncSetAttribute(cloud_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_max));
     CUDA_TRY(cudaFuncSetAttribute(cloud_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_max));
     CUDA_TRY(cudaFuncSetAttribute(cloud_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_max));
-    CUDA_TRY(cudaFuncSetAttribute(decrypt_tc_kernel<IDASH_B200_CT_BYTES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dec_tc_smem_bytes(DT_MAX_SLOTS)));
-    CUDA_TRY(cudaFuncSetAttribute(decrypt_tc_kernel<IDASH_B200_CT_BYTES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dec_tc_smem_bytes(DT_MAX_SLOTS)));
-    CUDA_TRY(cudaFuncSetAttribute(decrypt_tc_kernel<IDASH_B200_RECORD_BYTES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dec_tc_smem_bytes(DT_MAX_SLOTS)));
-    CUDA_TRY(cudaFuncSetAttribute(decrypt_tc_kernel<IDASH_B200_RECORD_BYTES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dec_tc_smem_bytes(DT_MAX_SLOTS)));
+    CUDA_TRY(cudaFuncSetAttribute(decrypt_tc_kernel<IDASH_B200_CT_BYTES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) RG_SMEM_MAX));
+    CUDA_TRY(cudaFuncSetAttribute(decrypt_tc_kernel<IDASH_B200_CT_BYTES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) RG_SMEM_MAX));
+    CUDA_TRY(cudaFuncSetAttribute(decrypt_tc_kernel<IDASH_B200_RECORD_BYTES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) RG_SMEM_MAX));
+    CUDA_TRY(cudaFuncSetAttribute(decrypt_tc_kernel<IDASH_B200_RECORD_BYTES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) RG_SMEM_MAX));
     for (int rot = 0; rot < 2; ++rot)
         for (int bat = 0; bat < 2; ++bat)
             for (int epi = 0; epi < RG_EPI_VARIANTS; ++epi)
@@ -704,7 +704,7 @@ static int make_view(const idash_b200_cts *a, bool is_output, CtView *v, const c
 
 // Launch geometry of the persistent ring kernel for a model on this device (shared by the eligibility checks and the launch, so
 // that a shape whose shared-memory budget does not work out selects another kernel / per-batch launches instead of failing).
-struct RingPlan { uint32_t n_slices, n_chunks, n_slots, n_bchunks, max_chunk_tiles; };
+struct RingPlan { uint32_t n_slices, n_chunks, n_slots, n_bchunks, max_chunk_tiles, extra_tiles; };
 static bool ring_plan(const idash_b200_ctx *c, const idash_b200_layout *L, uint64_t n_tiles, uint32_t n_batches, RingPlan *rp);
 static bool ring_selected(const idash_b200_ctx *c, const idash_b200_layout *L);
 
@@ -823,6 +823,7 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
         RingPlan rp;
         if (!ring_plan(c, L, p.n_tiles, n_batches, &rp)) return set_error(IDASH_B200_ERR_INVALID, "cloud_eval: internal: ring kernel shared-memory budget");
         p.n_slices = rp.n_slices; p.n_chunks = rp.n_chunks; p.n_slots = rp.n_slots; p.n_bchunks = rp.n_bchunks; p.max_chunk_tiles = rp.max_chunk_tiles;
+        p.extra_tiles = rp.extra_tiles;
         const uint32_t max_nb = L->tile_kmax / 32u;
         p.n_batches = n_batches;
         for (uint32_t b = 0; b < n_batches && n_batches > 1; ++b) {
@@ -846,7 +847,7 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
         if (const char *tu = debug_env("IDASH_B200_TUNE")) p.tune = (uint32_t) atoi(tu);
         if (const char *tr = debug_env("IDASH_B200_TRACE")) p.trace_cta = (uint32_t) atoi(tr) + 1u;
         const size_t ring_smem = ring_smem_bytes(p.n_slots, p.n_bchunks, p.max_chunk_tiles);
-        const dim3 grid(p.n_slices * p.n_chunks);
+        const dim3 grid(p.n_slices * (p.n_chunks + (p.extra_tiles ? 1u : 0u)));
         int epi = RG_EPI_DEFAULT;
 #ifdef IDASH_B200_PROFILE
         if (debug_env("IDASH_B200_TUNE")) epi = (p.tune & 2048u) ? 3 : (p.tune & 512u) ? 2 : (p.tune & 256u) ? 1 : 0;
@@ -908,6 +909,19 @@ static bool ring_plan(const idash_b200_ctx *c, const idash_b200_layout *L, uint6
     if (const char *ns = debug_env("IDASH_B200_RING_SLICES")) rp->n_slices = std::max(rp->n_slices, std::min(16u, (uint32_t) atoi(ns)));   // experiments
     if ((uint32_t) c->sm_count < rp->n_slices || n_tiles == 0 || L->tile_kmax == 0) return false;
     rp->n_chunks = (uint32_t) c->sm_count / rp->n_slices;
+    // SMs left over by that division (148 = 16 x 9 + 4, or 11 x 13 + 5) take one more, short chunk of X tiles at the end of the list: its
+    // n_slices CTAs run on the spare SMs in `waves` waves, each paying the pipeline's ramp-up (counted as `fill` tiles), so
+    // waves (X + fill) = R, the regular chunk's length, and n_chunks R + X = tiles
+    uint32_t n_spare = (uint32_t) c->sm_count - rp->n_slices * rp->n_chunks, fill = 4;     // fill: measured 2 .. 12, profiles/r02_ring_extra_chunk.txt
+    rp->extra_tiles = 0;
+    if (const char *nc = debug_env("IDASH_B200_RING_CHUNKS")) { rp->n_chunks = std::max(1u, std::min(rp->n_chunks, (uint32_t) atoi(nc))); n_spare = 0; }   // experiments
+    if (const char *ne = debug_env("IDASH_B200_RING_EXTRA")) n_spare = std::min(n_spare, (uint32_t) atoi(ne));
+    if (const char *ef = debug_env("IDASH_B200_RING_EXTRA_FILL")) fill = (uint32_t) atoi(ef);
+    if (n_spare) {
+        const uint64_t waves = (rp->n_slices + n_spare - 1u) / n_spare, total = n_tiles * n_batches;
+        const uint64_t lost = (uint64_t) rp->n_chunks * waves * fill;
+        rp->extra_tiles = total > lost ? (uint32_t) ((total - lost) / (rp->n_chunks * waves + 1u)) : 0u;
+    }
     const uint64_t chunk_tiles = (n_tiles * n_batches + rp->n_chunks - 1u) / rp->n_chunks + 1u;
     if (chunk_tiles * 4u > 65536u) return false;
     rp->max_chunk_tiles = (uint32_t) chunk_tiles;
@@ -1461,7 +1475,11 @@ static int launch_decrypt(idash_b200_ctx *c, const KeyBits &kb, uint32_t S, cons
         p.n_ct = in.count;
         p.n_groups = (in.count + DT_CTS - 1) / DT_CTS;
         p.S = S;
-        p.n_slots = DT_MAX_SLOTS;
+        // shared memory: Toeplitz table 32 KB + operand ring (16.5 KB per slot) + b ring (8 KB per stage = the b words of a j block of
+        // half a group). 9 slots = one slot of lookahead beyond a group; 5 b stages = two and a half j blocks in flight
+        p.n_slots = 9u;
+        p.n_bstages = 5u;
+        if (const char *bs = debug_env("IDASH_B200_DECRYPT_BSTAGES")) p.n_bstages = std::max<uint32_t>(2u, std::min<uint32_t>(DT_MAX_BSTAGES, (uint32_t) atoi(bs)));
         p.scores = d_scores;
         p.phase = d_phase;
         p.key = kb;
@@ -1469,7 +1487,9 @@ static int launch_decrypt(idash_b200_ctx *c, const KeyBits &kb, uint32_t S, cons
         if (const char *gs = debug_env("IDASH_B200_DECRYPT_GRID")) grid = std::max<uint64_t>(1, std::min<uint64_t>(grid, (uint64_t) atoi(gs)));   // tests: many groups per CTA
         if (const char *ns = debug_env("IDASH_B200_DECRYPT_SLOTS")) p.n_slots = std::max<uint32_t>(DT_GROUP_SLOTS, std::min<uint32_t>(DT_MAX_SLOTS, (uint32_t) atoi(ns)));
         if (const char *ko = debug_env("IDASH_B200_DECRYPT_KNOCKOUT")) p.knockout = (uint32_t) atoi(ko);
-        const size_t smem = dec_tc_smem_bytes(p.n_slots);
+        while (dec_tc_smem_bytes(p.n_slots, p.n_bstages) > RG_SMEM_MAX && p.n_slots > DT_GROUP_SLOTS) --p.n_slots;
+        while (dec_tc_smem_bytes(p.n_slots, p.n_bstages) > RG_SMEM_MAX && p.n_bstages > 2u) --p.n_bstages;
+        const size_t smem = dec_tc_smem_bytes(p.n_slots, p.n_bstages);
         if (in.stride == IDASH_B200_RECORD_BYTES) {
             if (d_phase) decrypt_tc_kernel<IDASH_B200_RECORD_BYTES, true><<<(unsigned) grid, DT_THREADS, smem, st>>>(p);
             else decrypt_tc_kernel<IDASH_B200_RECORD_BYTES, false><<<(unsigned) grid, DT_THREADS, smem, st>>>(p);

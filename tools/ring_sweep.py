@@ -26,7 +26,8 @@ from idash2019_2_b200 import api, synth  # noqa: E402
 
 T, G, SEED = 16184, 80882, 1234
 ENV = {"slots": "IDASH_B200_RING_SLOTS", "bchunks": "IDASH_B200_RING_BCHUNKS", "prefetch": "IDASH_B200_COEF_PREFETCH",
-       "ko": "IDASH_B200_KNOCKOUT", "slices": "IDASH_B200_RING_SLICES"}
+       "ko": "IDASH_B200_KNOCKOUT", "slices": "IDASH_B200_RING_SLICES", "chunks": "IDASH_B200_RING_CHUNKS",
+       "extra": "IDASH_B200_RING_EXTRA", "fill": "IDASH_B200_RING_EXTRA_FILL"}
 
 
 def apply(setting: str):
