@@ -106,12 +106,16 @@ __device__ __forceinline__ void dec_epilogue_pass(uint32_t b_addr0, uint32_t b_a
                                                   bool sc_on, uint32_t *ph, uint64_t *tempty) {
     uint8_t *scp = reinterpret_cast<uint8_t *>(sc);   // walks down the 32 score rows of the group: + 4 S bytes per ciphertext
     const uint32_t s4 = 4u * S;
+    // The accumulator is read in four chunks of 8 ciphertexts; the TMEM loads of chunk c + 1 are issued before chunk c is recombined
+    // and stored (two register sets), so only the first round trip of a pass is exposed -- with one set the warp sat out four per pass,
+    // ~1000 of the ~2500 cycles a pass took with the epilogue running alone (knock-outs, profiles/r02_decrypt_knockout.txt)
+    uint32_t vv[2][4][8];     // vv[set][m][4 e + l]: plane l of ciphertext 8 chunk + 2 m + e
+#pragma unroll
+    for (uint32_t m = 0; m < 4; ++m) tc_ld8(taddr + m * 8u, vv[0][m]);
 #pragma unroll
     for (uint32_t chunk = 0; chunk < 4; ++chunk) {
-        uint32_t v[4][8];     // v[m][4 e + l]: plane l of ciphertext 8 chunk + 2 m + e
+        uint32_t (&v)[4][8] = vv[chunk & 1u];
         uint32_t bw[8];
-#pragma unroll
-        for (uint32_t m = 0; m < 4; ++m) tc_ld8(taddr + chunk * 32u + m * 8u, v[m]);
         // b words: ciphertexts 0-15 of the group from the first half stage, 16-31 from the second
         if (chunk == 0) mbar_wait(bfull0, bpar0);
         if (chunk == 2) mbar_wait(bfull1, bpar1);
@@ -119,6 +123,10 @@ __device__ __forceinline__ void dec_epilogue_pass(uint32_t b_addr0, uint32_t b_a
 #pragma unroll
         for (uint32_t c = 0; c < 8; ++c) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(bw[c]) : "r"(ba + c * 512u));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (chunk < 3) {
+#pragma unroll
+            for (uint32_t m = 0; m < 4; ++m) tc_ld8(taddr + (chunk + 1u) * 32u + m * 8u, vv[(chunk + 1u) & 1u][m]);
+        }
         if (chunk & 1u) {      // the half stage's words are in registers: hand it back to the loader
             __syncwarp();
             if ((threadIdx.x & 31u) == 0) mbar_arrive(chunk == 1 ? bempty0 : bempty1);
@@ -145,7 +153,7 @@ __device__ __forceinline__ void dec_epilogue_pass(uint32_t b_addr0, uint32_t b_a
 }
 
 template <uint32_t STRIDE, bool PHASE>
-__global__ void __launch_bounds__(DT_THREADS, 1) decrypt_tc_kernel(const DecTcParams p) {   // 13 warps: 4 on one SM sub-partition (16 K registers) -> 128 per thread
+__global__ void __launch_bounds__(DT_THREADS, 1) decrypt_tc_kernel(const DecTcParams p, const __grid_constant__ CUtensorMap bmap) {   // 13 warps: 4 on one SM sub-partition (16 K registers) -> 128 per thread
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar[DT_MAX_SLOTS], empty_bar[DT_MAX_SLOTS], tfull_bar[4], tempty_bar[4];
     __shared__ __align__(8) uint64_t bfull_bar[DT_MAX_BSTAGES], bempty_bar[DT_MAX_BSTAGES];
@@ -221,31 +229,31 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decrypt_tc_kernel(const DecTcPa
             }
         }
     } else if (warp == DT_WARP_BLOAD) {
-        // ---------------- b loader: lane c copies the 128 b words (512 bytes) of ciphertext c of the group for every j block
-        // into the b ring -- 32 bulk copies per warp instruction (issued one by one from a single thread they took about as long as the
-        // pass itself)
-        uint32_t bst = 0, bph = 0;
-        const uint32_t half = lane >> 4, cl = lane & 15u;           // lanes 0-15 fill the stage of ciphertexts 0-15, lanes 16-31 the next one
-        for (uint64_t g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
-            const uint64_t ct0 = g * DT_CTS;
-            const uint32_t n_here = (p.knockout & 4u) ? 0u : (uint32_t) min((uint64_t) DT_CTS, p.n_ct - ct0);
-            const uint8_t *src = p.in.words + (ct0 + lane) * STRIDE + 4u * POLY_N;
+        // ---------------- b loader: ONE tensor copy (TMA, cp.async.bulk.tensor.2d) per half stage = the 128 b words of a j block of 16
+        // ciphertexts, a 512-byte x 16-row box of the array {b polynomial of every ciphertext, row pitch = ciphertext stride}. As 32
+        // per-ciphertext bulk copies per j block the issue loop alone (elect, broadcast, copy, branch per lane) took most of a pass and
+        // the epilogue waited for b words 43 % of its time (ncu, profiles/r02_ncu_decrypt_tc.txt). Rows past the last ciphertext are
+        // zero-filled by the copy and count towards the barrier's bytes like any other.
+        if (lane == 0) {
+            uint32_t bst = 0, bph = 0;
+            const uint64_t map = reinterpret_cast<uint64_t>(&bmap);
+            for (uint64_t g = blockIdx.x; g < p.n_groups; g += gridDim.x) {
+                const uint32_t row0 = (uint32_t) (g * DT_CTS);
 #pragma unroll 1
-            for (uint32_t jb = 0; jb < 8; ++jb) {
-                uint32_t my = bst + half, myph = bph;
-                if (my >= NB) { my -= NB; myph ^= 1u; }
-                uint64_t *const bar = &bfull_bar[my];
-                if (cl == 0) {
-                    mbar_wait(&bempty_bar[my], myph ^ 1u);
-                    const uint32_t n_half = n_here > 16u * half ? min(16u, n_here - 16u * half) : 0u;
-                    mbar_arrive_expect_tx(bar, n_half * 512u);
+                for (uint32_t jb = 0; jb < 8; ++jb) {
+#pragma unroll 1
+                    for (uint32_t half = 0; half < 2; ++half) {
+                        uint64_t *const bar = &bfull_bar[bst];
+                        mbar_wait(&bempty_bar[bst], bph ^ 1u);
+                        if (p.knockout & 4u) mbar_arrive(bar);
+                        else {
+                            mbar_arrive_expect_tx(bar, DT_B_STAGE_BYTES);
+                            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                         ::"r"(smem_u32(bring + bst * DT_B_STAGE_BYTES)), "l"(map), "r"(jb * 128u), "r"(row0 + 16u * half), "r"(smem_u32(bar)) : "memory");
+                        }
+                        if (++bst == NB) { bst = 0; bph ^= 1u; }
+                    }
                 }
-                __syncwarp();
-                if (lane < n_here)
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(smem_u32(bring + my * DT_B_STAGE_BYTES) + cl * 512u), "l"(src + 512u * jb), "r"(512u), "r"(smem_u32(bar)) : "memory");
-                bst += 2u;
-                if (bst >= NB) { bst -= NB; bph ^= 1u; }
             }
         }
     } else if (warp == DT_WARP_MMA) {
@@ -345,8 +353,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decrypt_tc_kernel(const DecTcPa
         };
         uint32_t slot = 0, ph = 0;
         const bool odd = piece & 1u, hi = piece & 2u;
-        auto store_unit = [&](const uint4 (&w)[4]) {
-            uint4 row[4];
+        // raw words of a unit -> operand rows, in place (registers only)
+        auto transform_unit = [&](uint4 (&w)[4]) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 // byte planes of this lane's 4 coefficients (reversed), then a 4 x 4 transpose over the 4 lanes of the block:
@@ -358,8 +366,10 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decrypt_tc_kernel(const DecTcPa
                 const uint32_t s0 = __shfl_xor_sync(0xFFFFFFFFu, hi ? a0 : a2, 2), s1 = __shfl_xor_sync(0xFFFFFFFFu, hi ? a1 : a3, 2);
                 // t[i] = plane `piece` of the coefficients held by lane i of the block; row bytes run from the highest coefficient down
                 const uint32_t t0 = hi ? s0 : a0, t1 = hi ? s1 : a1, t2 = hi ? a2 : s0, t3 = hi ? a3 : s1;
-                row[q] = make_uint4(t3, t2, t1, t0);
+                w[q] = make_uint4(t3, t2, t1, t0);
             }
+        };
+        auto store_unit = [&](const uint4 (&row)[4]) {
             mbar_wait(&empty_bar[slot], ph ^ 1u);
             uint8_t *dst = ring + slot * DT_SLOT_BYTES + ub * DT_B_LBO + (pw * 16u + piece) * 16u;   // n = 4 ct + plane
             if (!(p.knockout & 16u)) {
@@ -370,10 +380,12 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decrypt_tc_kernel(const DecTcPa
             mbar_arrive(&full_bar[slot]);
             if (++slot == NS) { slot = 0; ph ^= 1u; }
         };
-        // six units (4 x 16-byte loads each) in flight per thread, register sets bound statically: with the 3 ring slots beyond
-        // a group that is 9 slots of lookahead -- more than a group, so the first pass of the next group never waits for a
-        // load that was issued only when the previous group released its slots (with 4 units the MMA warp spent ~25 % of its
-        // time waiting for full slots)
+        // Six units (4 x 16-byte loads each) in flight per thread, register sets bound statically; a unit goes load -> (four units
+        // later) split + transpose in registers -> (two units later) store, as soon as the MMAs of the previous group have let go of
+        // its slot. A group's slots come free only during its last pass over them, one every ~512 cycles, and what a producer warp
+        // does between two stores has to fit in there: with the split + transpose (~160 instructions of one warp) done right before
+        // the store, the first pass of every group waited for its operands ~19 % of the MMA warp's time (ncu,
+        // profiles/r02_ncu_decrypt_tc.txt); done two units ahead, a freed slot is filled by a wait, four stores and an arrive.
         uint4 w0[4], w1[4], w2[4], w3[4], w4[4], w5[4];
         load_unit(0, w0);
         load_unit(1, w1);
@@ -381,14 +393,22 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decrypt_tc_kernel(const DecTcPa
         load_unit(3, w3);
         load_unit(4, w4);
         load_unit(5, w5);
+        transform_unit(w0);
+        transform_unit(w1);
         for (uint64_t i = 0; i < total; i += 6) {
             store_unit(w0);
             load_unit(i + 6, w0);
+            transform_unit(w2);
             if (i + 1 < total) { store_unit(w1); load_unit(i + 7, w1); }
+            transform_unit(w3);
             if (i + 2 < total) { store_unit(w2); load_unit(i + 8, w2); }
+            transform_unit(w4);
             if (i + 3 < total) { store_unit(w3); load_unit(i + 9, w3); }
+            transform_unit(w5);
             if (i + 4 < total) { store_unit(w4); load_unit(i + 10, w4); }
+            transform_unit(w0);
             if (i + 5 < total) { store_unit(w5); load_unit(i + 11, w5); }
+            transform_unit(w1);
         }
     }
 

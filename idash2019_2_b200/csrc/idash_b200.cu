@@ -11,6 +11,7 @@
 //                           integer product of multiplication.cpp:53-65) fused with the decode of
 //                           eval/idash.cpp:717-719
 // There is no CPU fallback: every entry point fails with IDASH_B200_ERR_CUDA when no device works.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -1464,6 +1465,28 @@ static int pack_key(const int32_t *key, KeyBits *kb) {
     return IDASH_B200_OK;
 }
 
+// Tensor map (TMA descriptor) of the b polynomials of a ciphertext array: 1024 words x count rows, row pitch = the ciphertext stride
+// (8192 packed, 8208 in a record stream -- both multiples of 16), box = 128 words x 16 ciphertexts. Encoded by the driver
+// (cuTensorMapEncodeTiled, looked up through the runtime: the library does not link libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_b_map(const CtView &in, CUtensorMap *map) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) return set_error(IDASH_B200_ERR_CUDA, "decrypt: the driver does not export cuTensorMapEncodeTiled");
+        encode = (EncodeTiledFn) fn;
+    }
+    const cuuint64_t dims[2] = {POLY_N, (cuuint64_t) in.count}, pitch[1] = {(cuuint64_t) in.stride};
+    const cuuint32_t box[2] = {128u, 16u}, unit[2] = {1u, 1u};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void *) (in.words + 4u * POLY_N), dims, pitch, box, unit, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(IDASH_B200_ERR_CUDA, "decrypt: cuTensorMapEncodeTiled failed (%d)", (int) r);
+    return IDASH_B200_OK;
+}
+
 static int launch_decrypt(idash_b200_ctx *c, const KeyBits &kb, uint32_t S, const CtView &in, float *d_scores, uint32_t *d_phase, cudaStream_t st) {
     if (in.count == 0) return IDASH_B200_OK;
     const bool timed = c->t_used < (int) c->t_begin.size();
@@ -1490,12 +1513,14 @@ static int launch_decrypt(idash_b200_ctx *c, const KeyBits &kb, uint32_t S, cons
         while (dec_tc_smem_bytes(p.n_slots, p.n_bstages) > RG_SMEM_MAX && p.n_slots > DT_GROUP_SLOTS) --p.n_slots;
         while (dec_tc_smem_bytes(p.n_slots, p.n_bstages) > RG_SMEM_MAX && p.n_bstages > 2u) --p.n_bstages;
         const size_t smem = dec_tc_smem_bytes(p.n_slots, p.n_bstages);
+        CUtensorMap bmap;
+        if (int rc = make_b_map(in, &bmap)) return rc;
         if (in.stride == IDASH_B200_RECORD_BYTES) {
-            if (d_phase) decrypt_tc_kernel<IDASH_B200_RECORD_BYTES, true><<<(unsigned) grid, DT_THREADS, smem, st>>>(p);
-            else decrypt_tc_kernel<IDASH_B200_RECORD_BYTES, false><<<(unsigned) grid, DT_THREADS, smem, st>>>(p);
+            if (d_phase) decrypt_tc_kernel<IDASH_B200_RECORD_BYTES, true><<<(unsigned) grid, DT_THREADS, smem, st>>>(p, bmap);
+            else decrypt_tc_kernel<IDASH_B200_RECORD_BYTES, false><<<(unsigned) grid, DT_THREADS, smem, st>>>(p, bmap);
         } else {
-            if (d_phase) decrypt_tc_kernel<IDASH_B200_CT_BYTES, true><<<(unsigned) grid, DT_THREADS, smem, st>>>(p);
-            else decrypt_tc_kernel<IDASH_B200_CT_BYTES, false><<<(unsigned) grid, DT_THREADS, smem, st>>>(p);
+            if (d_phase) decrypt_tc_kernel<IDASH_B200_CT_BYTES, true><<<(unsigned) grid, DT_THREADS, smem, st>>>(p, bmap);
+            else decrypt_tc_kernel<IDASH_B200_CT_BYTES, false><<<(unsigned) grid, DT_THREADS, smem, st>>>(p, bmap);
         }
         c->last_decrypt_kernel = IDASH_B200_DECRYPT_TENSOR;
     } else {
