@@ -68,6 +68,7 @@ struct RingParams {
     uint64_t coef_bytes;           // size of the coefficient image array (bound for the L2 prefetch)
     uint32_t coef_prefetch;        // the loader prefetches the images this many tiles ahead into L2 (0 = off)
     uint32_t meta_off;             // byte offset of the ring of per-tile metadata records (RG_META_STAGES x {rows[64], Constant[64]})
+    uint32_t zero_off;             // NUM_REGIONS > 1: byte offset of RG_ZERO_BYTES of zeros (512-byte aligned)
     uint32_t hdr_off;              // byte offset (dynamic shared memory) of the CTA's tile-header table
     uint32_t max_chunk_tiles;      // capacity of that table (tiles per chunk, rounded up)
     CtView in, out;
@@ -102,8 +103,9 @@ struct RingParams {
                                    // 1 no MMAs, 2 no output stores, 4 no epilogue TMEM loads, 8 no input loads, 16 no zero fill, 32 no bias / mask
 };
 
-__host__ __device__ constexpr uint32_t ring_smem_bytes(uint32_t n_slots, uint32_t n_bchunks, uint32_t max_chunk_tiles) {
-    return n_slots * RG_BLOCK_BYTES + n_bchunks * TC_B_CHUNK + RG_META_BYTES + 4u * max_chunk_tiles;
+#define RG_ZERO_BYTES 4096u                      // NUM_REGIONS > 1: a block of zeros, the source of the bulk stores that fill b[RS'..N) of every output row
+__host__ __device__ constexpr uint32_t ring_smem_bytes(uint32_t n_slots, uint32_t n_bchunks, uint32_t max_chunk_tiles, bool rot) {
+    return n_slots * RG_BLOCK_BYTES + n_bchunks * TC_B_CHUNK + RG_META_BYTES + (rot ? RG_ZERO_BYTES : 0u) + 4u * max_chunk_tiles;
 }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -512,6 +514,10 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
         const uint32_t v = t_begin + i, b = batched ? v / p.n_tiles : 0u;
         hdr_s[i] = ring_pack_hdr((batched ? p.batch_tiles[b] : p.tiles) + p.tile_base + (v - b * p.n_tiles)) + (b << RG_BATCH_SHIFT);
     }
+    if (ROT) {
+        for (uint32_t i = tid; i < RG_ZERO_BYTES / 16u; i += RG_THREADS) reinterpret_cast<uint4 *>(smem + p.zero_off)[i] = make_uint4(0, 0, 0, 0);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // read by bulk stores (async proxy) after the barrier below
+    }
     const uint32_t w_slice = slice * 128u;
     const bool is_b = (w_slice & POLY_N) != 0 && !(k_knockout & 32u);     // knock-out 32: every slice runs the (cheaper) epilogue of polynomial a
     const uint32_t i_slice = w_slice & (POLY_N - 1);
@@ -595,8 +601,25 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&t_empty[st]);      // one arrival per epilogue warp
             }
-            if (ROT && zero_units && !(k_knockout & (2u | 16u))) {
-                // zero fill of b[128 n_slices - 1024 .. 1024) of this tile's rows: unit u = (tile row u / n_zero_seg, segment u % n_zero_seg)
+            if (ROT && zero_units && !(k_tune & 16u) && !(k_knockout & (2u | 16u))) {
+                // Zero fill of b[128 n_slices - 1024 .. 1024) of this tile's rows: the segments of a row are contiguous (2560 bytes at
+                // REGION_SIZE = 341), so a row is ONE bulk store from the block of zeros in shared memory, issued by one lane and carried
+                // out by the copy engine -- as 128-bit stores of all lanes the fill took 15 % of the kernel (knock-out 16,
+                // profiles/r02_ring_knockout.txt). The tile's rows go round the n_slices x 8 epilogue warps of the chunk.
+                const uint32_t row_lane0 = __shfl_sync(0xFFFFFFFFu, row, 0);       // caller row of tile row col_base
+                if (lane == 0) {
+                    const uint32_t first = (zero_me + zero_workers - it % zero_workers) % zero_workers;
+                    for (uint32_t n = first; n < TC_TN; n += zero_workers) {
+                        uint32_t r = fast ? row_lane0 - col_base + n : meta[n];
+                        if (r == IDASH_B200_NO_ROW) continue;
+                        if (p.slot_of_row) r = __ldg(p.slot_of_row + r);
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     ::"l"(out_words + (uint64_t) r * p.out.stride + 512u * p.n_slices), "r"(smem_u32(smem + p.zero_off)), "r"(512u * n_zero_seg) : "memory");
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            } else if (ROT && zero_units && !(k_knockout & (2u | 16u))) {
+                // (tune & 16: the same fill as 512-byte units of 128-bit stores, unit u = (tile row u / n_zero_seg, segment u % n_zero_seg))
                 const uint32_t row_lane0 = __shfl_sync(0xFFFFFFFFu, row, 0);       // caller row of tile row col_base
                 for (uint32_t u = zero_me; u < zero_units; u += zero_workers) {
                     const uint32_t n = u / n_zero_seg, seg = u - n * n_zero_seg;
@@ -608,6 +631,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
             }
             if (tid == 0) RG_TRACE(8, it);
         }
+        if (ROT && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // the zero-fill stores of this lane are complete
     } else if (warp == RG_WARP_MMA || warp == RG_WARP_MMA2) {
         // ================= MMA issuers =================
         // Two warps: warp RG_WARP_MMA issues the even tiles of the chunk (TMEM stage 0), RG_WARP_MMA2 the odd ones (stage 1).

@@ -835,7 +835,8 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
             p.batch_coef_bytes[b] = mb->layout->tile_coef.size();
         }
         p.meta_off = p.n_slots * RG_BLOCK_BYTES + p.n_bchunks * TC_B_CHUNK;
-        p.hdr_off = p.meta_off + RG_META_BYTES;
+        p.zero_off = p.meta_off + RG_META_BYTES;
+        p.hdr_off = p.zero_off + (L->NR != 1 ? RG_ZERO_BYTES : 0u);
         p.in = in; p.out = out;
         p.slot_of_ct = d_slot_of_ct; p.n_ct_slots = n_ct_slots; p.slot_of_row = d_slot_of_row;
         p.S = L->S; p.NR = L->NR; p.RS = L->RS;
@@ -847,7 +848,7 @@ static int launch_cloud(idash_b200_ctx *c, const idash_b200_model *m, const CtVi
         p.tune = L->NR != 1 ? RG_TUNE_ROT : RG_TUNE_DEFAULT;
         if (const char *tu = debug_env("IDASH_B200_TUNE")) p.tune = (uint32_t) atoi(tu);
         if (const char *tr = debug_env("IDASH_B200_TRACE")) p.trace_cta = (uint32_t) atoi(tr) + 1u;
-        const size_t ring_smem = ring_smem_bytes(p.n_slots, p.n_bchunks, p.max_chunk_tiles);
+        const size_t ring_smem = ring_smem_bytes(p.n_slots, p.n_bchunks, p.max_chunk_tiles, L->NR != 1);
         const dim3 grid(p.n_slices * (p.n_chunks + (p.extra_tiles ? 1u : 0u)));
         int epi = RG_EPI_DEFAULT;
 #ifdef IDASH_B200_PROFILE
@@ -928,7 +929,7 @@ static bool ring_plan(const idash_b200_ctx *c, const idash_b200_layout *L, uint6
     rp->max_chunk_tiles = (uint32_t) chunk_tiles;
     const uint32_t max_nb = L->tile_kmax / 32u;
     const auto chunks_for = [&](uint32_t slots) -> uint32_t {
-        const uint32_t used = slots * RG_BLOCK_BYTES + RG_META_BYTES + 4u * rp->max_chunk_tiles;
+        const uint32_t used = slots * RG_BLOCK_BYTES + RG_META_BYTES + (L->NR != 1 ? RG_ZERO_BYTES : 0u) + 4u * rp->max_chunk_tiles;
         return used >= RG_SMEM_MAX ? 0u : std::min<uint32_t>(64u, (RG_SMEM_MAX - used) / TC_B_CHUNK);
     };
     // Input-block slots: the widest tile's blocks + 2 (one being staged, one ahead), and at least two and a half tiles of coefficient
@@ -1499,9 +1500,10 @@ static int launch_decrypt(idash_b200_ctx *c, const KeyBits &kb, uint32_t S, cons
         p.n_groups = (in.count + DT_CTS - 1) / DT_CTS;
         p.S = S;
         // shared memory: Toeplitz table 32 KB + operand ring (16.5 KB per slot) + b ring (8 KB per stage = the b words of a j block of
-        // half a group). 9 slots = one slot of lookahead beyond a group; 5 b stages = two and a half j blocks in flight
-        p.n_slots = 9u;
-        p.n_bstages = 5u;
+        // half a group). 10 slots = two slots of lookahead beyond a group; 3 b stages = one and a half j blocks in flight (measured with the
+        // tensor-copy loader: 10 + 3 and 10 + 2 0.684 ms, 9 + 5 / 9 + 4 / 9 + 3 0.696 ms on the same box)
+        p.n_slots = 10u;
+        p.n_bstages = 3u;
         if (const char *bs = debug_env("IDASH_B200_DECRYPT_BSTAGES")) p.n_bstages = std::max<uint32_t>(2u, std::min<uint32_t>(DT_MAX_BSTAGES, (uint32_t) atoi(bs)));
         p.scores = d_scores;
         p.phase = d_phase;
