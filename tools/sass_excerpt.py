@@ -29,8 +29,8 @@ for line in sass.splitlines():
             ex[fn].append(ins)
 print(f"# cuobjdump -sass {lib} (sm_100a)")
 print("# UTCIMMA = tcgen05.mma kind::i8 (.WS = weight-stationary), UTCBAR = tcgen05.commit, LDTM = tcgen05.ld (.PACK16BIT = pack::16b),")
-print("# UBLKCP = cp.async.bulk (TMA bulk copy), UBLKPF = cp.async.bulk.prefetch.L2, SYNCS = mbarrier; no UTMALDG / UTMASTG: the ciphertext words")
-print("# are staged through registers (byte-plane split) and not by tensor-map TMA -- DESIGN.md section 3.2")
+print("# UBLKCP = cp.async.bulk (TMA bulk copy; .S.G global -> shared, .G.S shared -> global: the zero fill), UBLKPF = cp.async.bulk.prefetch.L2, SYNCS = mbarrier,")
+print("# UTMALDG = cp.async.bulk.tensor (tensor-map TMA: the decrypt kernel's b words). The cloud kernels' ciphertext words are staged through registers (byte-plane split), DESIGN.md 3.2")
 for f in sorted(cnt):
     if not any(cnt[f][k] for k in ("UTCIMMA", "LDTM", "UBLKCP")):
         continue
