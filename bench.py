@@ -303,7 +303,7 @@ def bench_decrypt(args, api, ctx, out_ct, n_rows, peak):
     d_ms = statistics.mean(ctx.timing_read(10))
     ctx.timing_enable(0)
     d_bytes = n_rows * (CT_BYTES + 4 * args.samples)
-    kname = "decrypt_tc_kernel" if ctx.last_decrypt_kernel() == api.DECRYPT_TENSOR else "decrypt_kernel"
+    kname = {api.DECRYPT_TENSOR_PAIR: "decrypt_pair_kernel", api.DECRYPT_TENSOR: "decrypt_tc_kernel"}.get(ctx.last_decrypt_kernel(), "decrypt_kernel")
     rec = {"metric": "decrypted output ciphertexts/sec", "value": n_rows / (d_ms * 1e-3), "unit": "ct/s", "ciphertexts": n_rows,
            "roofline": {"bound": "hbm", "achieved": d_bytes / (d_ms * 1e-3) * 1e-9, "peak": peak, "unit": "GB/s",
                         "frac": d_bytes / (d_ms * 1e-3) * 1e-9 / peak, "traffic": None, "kernel": kname, "kernel_ms": d_ms,

@@ -68,7 +68,7 @@ assert ENTRY_DTYPE.itemsize == 32 and GROUP_DTYPE.itemsize == 64 and TILE_DTYPE.
 TILE_ROWS, TILE_KMAX, RING_KMAX = 64, 256, 224
 COMPILE_DEFAULT, COMPILE_GROUPS_ALL = 0, 1
 KERNEL_AUTO, KERNEL_IMAD, KERNEL_TENSOR, KERNEL_TENSOR_TILE, KERNEL_TENSOR_RING = 0, 1, 2, 3, 4
-DECRYPT_AUTO, DECRYPT_IADD, DECRYPT_TENSOR = 0, 1, 2
+DECRYPT_AUTO, DECRYPT_IADD, DECRYPT_TENSOR, DECRYPT_TENSOR_PAIR = 0, 1, 2, 3
 
 # every symbol include/idash_b200.h and include/idash_b200_layout.h declare
 EXPORTS = {

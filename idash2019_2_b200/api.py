@@ -18,7 +18,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib as L
-from ._lib import (COMPILE_DEFAULT, COMPILE_GROUPS_ALL, CONSTANT_BIDX, CT_BYTES, CT_WORDS, DECRYPT_AUTO, DECRYPT_IADD, DECRYPT_TENSOR,  # noqa: F401
+from ._lib import (COMPILE_DEFAULT, COMPILE_GROUPS_ALL, CONSTANT_BIDX, CT_BYTES, CT_WORDS, DECRYPT_AUTO, DECRYPT_IADD, DECRYPT_TENSOR, DECRYPT_TENSOR_PAIR,  # noqa: F401
                    KERNEL_AUTO, KERNEL_IMAD, KERNEL_TENSOR, KERNEL_TENSOR_RING, KERNEL_TENSOR_TILE, LAYOUT_PACKED, LAYOUT_RECORDS, N,
                    RECORD_BYTES, IdashB200Error)
 

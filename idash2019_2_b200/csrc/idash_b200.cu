@@ -361,6 +361,7 @@ __global__ void __launch_bounds__(128) decrypt_kernel(CtView in, uint64_t n_ct, 
 }
 
 #include "decrypt_tc.cuh"
+#include "decrypt_pair.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -454,6 +455,10 @@ extern "C" int idash_b200_init(idash_b200_ctx **out, int device) {
     CUDA_TRY(cudaFuncSetAttribute(decrypt_tc_kernel<IDASH_B200_CT_BYTES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) RG_SMEM_MAX));
     CUDA_TRY(cudaFuncSetAttribute(decrypt_tc_kernel<IDASH_B200_RECORD_BYTES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) RG_SMEM_MAX));
     CUDA_TRY(cudaFuncSetAttribute(decrypt_tc_kernel<IDASH_B200_RECORD_BYTES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) RG_SMEM_MAX));
+    CUDA_TRY(cudaFuncSetAttribute(decrypt_pair_kernel<IDASH_B200_CT_BYTES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) RG_SMEM_MAX));
+    CUDA_TRY(cudaFuncSetAttribute(decrypt_pair_kernel<IDASH_B200_CT_BYTES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) RG_SMEM_MAX));
+    CUDA_TRY(cudaFuncSetAttribute(decrypt_pair_kernel<IDASH_B200_RECORD_BYTES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) RG_SMEM_MAX));
+    CUDA_TRY(cudaFuncSetAttribute(decrypt_pair_kernel<IDASH_B200_RECORD_BYTES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) RG_SMEM_MAX));
     for (int rot = 0; rot < 2; ++rot)
         for (int bat = 0; bat < 2; ++bat)
             for (int epi = 0; epi < RG_EPI_VARIANTS; ++epi)
@@ -527,7 +532,7 @@ extern "C" int idash_b200_last_kernel(const idash_b200_ctx *c) { return c ? c->l
 
 extern "C" int idash_b200_set_decrypt_kernel(idash_b200_ctx *c, int which) {
     clear_error();
-    if (!c || which < IDASH_B200_DECRYPT_AUTO || which > IDASH_B200_DECRYPT_TENSOR) return set_error(IDASH_B200_ERR_INVALID, "set_decrypt_kernel: bad argument");
+    if (!c || which < IDASH_B200_DECRYPT_AUTO || which > IDASH_B200_DECRYPT_TENSOR_PAIR) return set_error(IDASH_B200_ERR_INVALID, "set_decrypt_kernel: bad argument");
     c->decrypt_choice = which;
     return IDASH_B200_OK;
 }
@@ -1492,7 +1497,43 @@ static int launch_decrypt(idash_b200_ctx *c, const KeyBits &kb, uint32_t S, cons
     if (in.count == 0) return IDASH_B200_OK;
     const bool timed = c->t_used < (int) c->t_begin.size();
     if (timed) CUDA_TRY(cudaEventRecord(c->t_begin[c->t_used], st));
-    if (c->decrypt_choice != IDASH_B200_DECRYPT_IADD) {
+    bool pair_launched = false;
+    if (c->decrypt_choice == IDASH_B200_DECRYPT_TENSOR_PAIR || (c->decrypt_choice == IDASH_B200_DECRYPT_AUTO && c->sm_count >= 2)) {
+        // K4p: CTA pairs (tcgen05.mma.cta_group::2), two groups of operand slots resident per CTA
+        DecTcParams p;
+        memset(&p, 0, sizeof(p));
+        p.in = in;
+        p.n_ct = in.count;
+        p.n_groups = (in.count + DT_CTS - 1) / DT_CTS;
+        p.S = S;
+        p.n_slots = 16u;
+        p.n_bstages = 3u;
+        p.scores = d_scores;
+        p.phase = d_phase;
+        p.key = kb;
+        uint64_t grid = std::min<uint64_t>(2 * p.n_groups, (uint64_t) c->sm_count) & ~1ull;
+        if (const char *gs = debug_env("IDASH_B200_DECRYPT_GRID")) grid = std::max<uint64_t>(2, std::min<uint64_t>(grid, (uint64_t) atoi(gs)) & ~1ull);
+        if (const char *ns = debug_env("IDASH_B200_DECRYPT_SLOTS")) p.n_slots = std::max<uint32_t>(DT_GROUP_SLOTS, std::min<uint32_t>(DP_MAX_SLOTS, (uint32_t) atoi(ns)));
+        if (const char *bs = debug_env("IDASH_B200_DECRYPT_BSTAGES")) p.n_bstages = std::max<uint32_t>(2u, std::min<uint32_t>(DT_MAX_BSTAGES, (uint32_t) atoi(bs)));
+        if (const char *ko = debug_env("IDASH_B200_DECRYPT_KNOCKOUT")) p.knockout = (uint32_t) atoi(ko);
+        while (dec_pair_smem_bytes(p.n_slots, p.n_bstages) > RG_SMEM_MAX && p.n_slots > DT_GROUP_SLOTS) --p.n_slots;
+        const size_t smem = dec_pair_smem_bytes(p.n_slots, p.n_bstages);
+        CUtensorMap bmap;
+        if (int rc = make_b_map(in, &bmap)) return rc;
+        if (in.stride == IDASH_B200_RECORD_BYTES) {
+            if (d_phase) decrypt_pair_kernel<IDASH_B200_RECORD_BYTES, true><<<(unsigned) grid, DT_THREADS, smem, st>>>(p, bmap);
+            else decrypt_pair_kernel<IDASH_B200_RECORD_BYTES, false><<<(unsigned) grid, DT_THREADS, smem, st>>>(p, bmap);
+        } else {
+            if (d_phase) decrypt_pair_kernel<IDASH_B200_CT_BYTES, true><<<(unsigned) grid, DT_THREADS, smem, st>>>(p, bmap);
+            else decrypt_pair_kernel<IDASH_B200_CT_BYTES, false><<<(unsigned) grid, DT_THREADS, smem, st>>>(p, bmap);
+        }
+        // a device that cannot place the pairs (a cluster launch needs both SMs of a TPC): AUTO falls back to one CTA per SM
+        const cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) { pair_launched = true; c->last_decrypt_kernel = IDASH_B200_DECRYPT_TENSOR_PAIR; }
+        else if (c->decrypt_choice == IDASH_B200_DECRYPT_TENSOR_PAIR) return set_error(IDASH_B200_ERR_CUDA, "decrypt: cluster launch failed: %s", cudaGetErrorString(e));
+    }
+    if (pair_launched) {
+    } else if (c->decrypt_choice != IDASH_B200_DECRYPT_IADD) {
         DecTcParams p;
         memset(&p, 0, sizeof(p));
         p.in = in;

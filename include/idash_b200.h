@@ -204,10 +204,12 @@ int idash_b200_decrypt_host(idash_b200_ctx *ctx, const int32_t *key, uint32_t nu
                             float *scores, uint32_t *phase);
 int idash_b200_decrypt_device(idash_b200_ctx *ctx, const int32_t *key_host, uint32_t num_samples,
                               const idash_b200_cts *in, float *scores, uint32_t *phase, void *cuda_stream);
-/* Which kernel idash_b200_decrypt_* launches. AUTO = TENSOR: the negacyclic product as a tcgen05 int8 GEMM of the
- * key's 1024 x 1024 Toeplitz matrix against the byte planes of a (32 ciphertexts per group). IADD = the CUDA-core
- * kernel (one CTA per ciphertext, ~512 integer adds per phase coefficient). Both are exact and bit-identical. */
-enum { IDASH_B200_DECRYPT_AUTO = 0, IDASH_B200_DECRYPT_IADD = 1, IDASH_B200_DECRYPT_TENSOR = 2 };
+/* Which kernel idash_b200_decrypt_* launches. TENSOR: the negacyclic product as a tcgen05 int8 GEMM of the key's
+ * 1024 x 1024 Toeplitz matrix against the byte planes of a (32 ciphertexts per group), one CTA per SM. TENSOR_PAIR
+ * (= AUTO): the same GEMM on CTA pairs (tcgen05.mma.cta_group::2, M = 256; each CTA holds half of a group's planes, two
+ * groups resident). IADD = the CUDA-core kernel (one CTA per ciphertext, ~512 integer adds per phase coefficient).
+ * All three are exact and bit-identical. */
+enum { IDASH_B200_DECRYPT_AUTO = 0, IDASH_B200_DECRYPT_IADD = 1, IDASH_B200_DECRYPT_TENSOR = 2, IDASH_B200_DECRYPT_TENSOR_PAIR = 3 };
 int idash_b200_set_decrypt_kernel(idash_b200_ctx *ctx, int which);
 int idash_b200_last_decrypt_kernel(const idash_b200_ctx *ctx);
 

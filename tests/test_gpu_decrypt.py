@@ -10,10 +10,10 @@ from helpers import GOLDEN_CASES, load_golden
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["tensor", "iadd"], autouse=True)
+@pytest.fixture(params=["pair", "tensor", "iadd"], autouse=True)
 def decrypt_kernel(request, gpu_ctx):
-    """Every test runs on both decrypt kernels (tcgen05 Toeplitz GEMM and the CUDA-core kernel)."""
-    which = {"tensor": api.DECRYPT_TENSOR, "iadd": api.DECRYPT_IADD}[request.param]
+    """Every test runs on all decrypt kernels (tcgen05 Toeplitz GEMM on CTA pairs and on single CTAs, and the CUDA-core kernel)."""
+    which = {"pair": api.DECRYPT_TENSOR_PAIR, "tensor": api.DECRYPT_TENSOR, "iadd": api.DECRYPT_IADD}[request.param]
     gpu_ctx.set_decrypt_kernel(which)
     yield which
     gpu_ctx.set_decrypt_kernel(api.DECRYPT_AUTO)

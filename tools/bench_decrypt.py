@@ -27,7 +27,9 @@ def main():
     line = {"ciphertexts": n, "S": S, "algorithmic_bytes": n * (8192 + 4 * S), "kernels": {}}
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     quick = bool(os.environ.get("DEC_QUICK"))       # tensor kernel only, no CPU leg (knock-out / tuning runs)
-    kernels = (("decrypt_tc_kernel", api.DECRYPT_TENSOR), ("decrypt_kernel", api.DECRYPT_IADD))
+    kernels = (("decrypt_pair_kernel", api.DECRYPT_TENSOR_PAIR), ("decrypt_tc_kernel", api.DECRYPT_TENSOR), ("decrypt_kernel", api.DECRYPT_IADD))
+    if os.environ.get("DEC_KERNELS"):      # e.g. DEC_KERNELS=decrypt_tc_kernel
+        kernels = tuple(k for k in kernels if k[0] in os.environ["DEC_KERNELS"].split(","))
     for name, which in kernels[:1] if quick else kernels:
         ctx.set_decrypt_kernel(which)
         scores.zero_()
@@ -47,7 +49,7 @@ def main():
         gbs = n * (8192 + 4 * S) / (k_ms * 1e-3) * 1e-9
         line["kernels"][name] = {"kernel_ms": k_ms, "min_ms": float(np.min(ms)), "ct_per_s": n / (k_ms * 1e-3), "achieved_GBps": gbs,
                                  "frac_of_measured_hbm_peak": gbs / peaks["hbm_gbs"] if "hbm_gbs" in peaks else None,
-                                 "int8_mac_per_s": n * 4 * 1024 * 1024 / (k_ms * 1e-3) if which == api.DECRYPT_TENSOR else None,
+                                 "int8_mac_per_s": n * 4 * 1024 * 1024 / (k_ms * 1e-3) if which != api.DECRYPT_IADD else None,
                                  "sample_matches_exact_oracle": ok}
     ctx.set_decrypt_kernel(api.DECRYPT_AUTO)
     if po.have_ref() and not quick:

@@ -1,0 +1,10 @@
+set -u
+OUT=gpurun_out/r3n; mkdir -p $OUT
+for rep in 1 2; do for k in decrypt_pair_kernel decrypt_tc_kernel; do
+  DEC_KERNELS=$k DEC_QUICK=1 timeout 120 python tools/bench_decrypt.py 2>>$OUT/err.log | python -c "
+import json,sys; r=json.loads(sys.stdin.read()); k=list(r['kernels'].values())[0]; print('$k', round(k['kernel_ms'],4), round(k['min_ms'],4), k['sample_matches_exact_oracle'])"
+done; done
+for cfg in "IDASH_B200_DECRYPT_SLOTS=20" "IDASH_B200_DECRYPT_SLOTS=12" "IDASH_B200_DECRYPT_SLOTS=16 IDASH_B200_DECRYPT_BSTAGES=5" "IDASH_B200_DECRYPT_KNOCKOUT=1" "IDASH_B200_DECRYPT_KNOCKOUT=38" "IDASH_B200_DECRYPT_KNOCKOUT=25"; do
+  env IDASH_B200_USE_PROFILE_LIB=1 $cfg DEC_KERNELS=decrypt_pair_kernel DEC_QUICK=1 timeout 120 python tools/bench_decrypt.py 2>>$OUT/err.log | python -c "
+import json,sys; r=json.loads(sys.stdin.read()); k=list(r['kernels'].values())[0]; print('$cfg', round(k['kernel_ms'],4), k['sample_matches_exact_oracle'])"
+done
