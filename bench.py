@@ -149,6 +149,13 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
 
 
+def measured_peaks() -> dict:
+    try:
+        return json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        return {}
+
+
 def ncu_traffic(kernel: str, args, world: int):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture
     of this same workload (profiles/traffic.json, written from the .ncu-rep by tools/ncu_summary.py), or None."""
@@ -306,8 +313,16 @@ def bench_decrypt(args, api, ctx, out_ct, n_rows, peak):
     kname = {api.DECRYPT_TENSOR_PAIR: "decrypt_pair_kernel", api.DECRYPT_TENSOR: "decrypt_tc_kernel"}.get(ctx.last_decrypt_kernel(), "decrypt_kernel")
     rec = {"metric": "decrypted output ciphertexts/sec", "value": n_rows / (d_ms * 1e-3), "unit": "ct/s", "ciphertexts": n_rows,
            "roofline": {"bound": "hbm", "achieved": d_bytes / (d_ms * 1e-3) * 1e-9, "peak": peak, "unit": "GB/s",
-                        "frac": d_bytes / (d_ms * 1e-3) * 1e-9 / peak, "traffic": None, "kernel": kname, "kernel_ms": d_ms,
+                        "frac": d_bytes / (d_ms * 1e-3) * 1e-9 / peak, "traffic": (json.loads((ROOT / "profiles" / "traffic.json").read_text()).get(kname, {}).get(str(n_rows), {}).get("dram_bytes_per_launch") if (ROOT / "profiles" / "traffic.json").exists() else None), "kernel": kname, "kernel_ms": d_ms,
                         "algorithmic_bytes": d_bytes, "int8_mac_per_s": n_rows * 4 * 1024 * 1024 / (d_ms * 1e-3)}}
+    # the other roofline of this kernel: the phase is a GEMM (1024 x 1024 Toeplitz matrix x 4 byte planes per ciphertext), and on CTA
+    # pairs it runs the int8 tensor pipe at 97 % active cycles (profiles/r02_ncu_decrypt_pair.txt). Peak: int8 dense = 2 x the bf16
+    # figure MEASURED_PEAKS.json holds (the profiling recipe's table: fp8 / int8 dense = 2 x bf16 dense)
+    bf16 = measured_peaks().get("bf16_tflops")
+    if bf16 and kname != "decrypt_kernel":
+        tops = 2 * n_rows * 4 * 1024 * 1024 / (d_ms * 1e-3) * 1e-12
+        rec["roofline"]["tensor"] = {"achieved": tops, "peak": 2 * bf16, "unit": "TOP/s (int8)", "frac": tops / (2 * bf16),
+                                     "peak_source": "2 x measured bf16 TFLOP/s (MEASURED_PEAKS.json bf16_tflops)"}
     # end to end: pinned host ciphertexts in, pinned host scores out
     try:
         h_ct = torch.empty((n_rows, 2048), dtype=torch.int32, pin_memory=True)
