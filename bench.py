@@ -294,6 +294,25 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------
+def decrypt_sharded_ms(args, api, ctx, outs, n_rows):
+    """N > 1: every rank decrypts its own rows of every batch (the stage shards by ciphertext, nothing is exchanged). Milliseconds
+    for all batches of this rank, CUDA events around the back-to-back launches, mean of 5."""
+    import torch
+    key = np.random.default_rng(5).integers(0, 2, 1024).astype(np.int32)
+    scores = torch.empty((n_rows, args.samples), dtype=torch.float32, device="cuda")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for o in outs:
+        api.decrypt_predictions_device(ctx, key, args.samples, o, scores)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        for o in outs:
+            api.decrypt_predictions_device(ctx, key, args.samples, o, scores)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / 5
+
+
 def bench_decrypt(args, api, ctx, out_ct, n_rows, peak):
     """The decrypt stage (decrypt_predictions, eval/idash.cpp:681-761) on the step's own output ciphertexts: kernel roofline,
     end to end through the host-buffer entry point, and the reference's decrypt_predictions on a bounded sample."""
@@ -603,20 +622,22 @@ def run_b200(args):
         parity, ref_secs, ref_kind, ref_cores = parity_gate(args, api, ctx, m, sub, ins[0], NR, RS, world)
 
     # ---- the decrypt stage on the step's own output ciphertexts (secondary record beside the headline)
-    decrypt = None
+    decrypt, dec_ms = None, 0.0
+    if world > 1 and not args.no_decrypt:
+        dec_ms = decrypt_sharded_ms(args, api, ctx, outs, n_rows)
     if rank == 0 and not args.no_decrypt:
         decrypt = bench_decrypt(args, api, ctx, outs[0], n_rows, measured_peak_gbs()[0])
 
     par_ok = 1.0 if (parity is None or parity["equal"]) else 0.0
     par_words = float(parity["checked_words"]) if parity else 0.0
-    t = torch.tensor([ms_total, t_e2e * 1e3, bare_d2h_ms, sustained["ms_per_step"] if sustained else 0.0], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms_total, t_e2e * 1e3, bare_d2h_ms, sustained["ms_per_step"] if sustained else 0.0, dec_ms], dtype=torch.float64, device="cuda")
     pt = torch.tensor([par_ok, 1.0 if h_out_host_path else 0.0], dtype=torch.float64, device="cuda")
     ps = torch.tensor([par_words], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(pt, op=dist.ReduceOp.MIN)
         dist.all_reduce(ps, op=dist.ReduceOp.SUM)
-    ms_total, ms_e2e, bare_d2h_ms, sus_ms_step = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+    ms_total, ms_e2e, bare_d2h_ms, sus_ms_step, dec_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3]), float(t[4])
     all_equal, host_same = bool(pt[0] > 0.5), bool(pt[1] > 0.5)
 
     rc = 0
@@ -679,6 +700,12 @@ def run_b200(args):
             sustained["vs_burst"] = (ms_total / args.steps) / sus_ms_step
             line["sustained"] = sustained
         if decrypt:
+            if world > 1 and dec_ms > 0:
+                # the whole job's decrypt: every rank its own rows of every batch, max over ranks
+                n_all = n_rows * n_batches * world
+                decrypt["sharded"] = {"n_gpus": world, "ciphertexts": n_all, "ms": dec_ms, "value": n_all / (dec_ms * 1e-3), "unit": "ct/s",
+                                      "how": "every rank decrypts its rows of every batch (no exchange), CUDA events, max over ranks",
+                                      "hbm_frac_per_gpu": n_rows * n_batches * (CT_BYTES + 4 * args.samples) / (dec_ms * 1e-3) * 1e-9 / measured_peak_gbs()[0]}
             line["decrypt"] = decrypt
         if nvlink:
             nvlink["job_ms_gpu0_resident"] = nvlink["scatter_ms"] + ms_total / args.steps + nvlink["gather_ms"]

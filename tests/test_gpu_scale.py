@@ -197,15 +197,16 @@ def test_config0_full_pipeline_keygen_encrypt_cloud_decrypt(built_lib, tmp_path)
     shutil.rmtree(tmp_path / "model", ignore_errors=True)
 
 
-@pytest.mark.parametrize("n_gpus", [2, 4, 8])
-def test_cloud_sharded_over_gpus_equals_unsharded_equals_reference(built_lib, n_gpus):
+@pytest.mark.parametrize("n_gpus,S", [(2, 1004), (2, 335), (4, 1004), (8, 1004)])
+def test_cloud_sharded_over_gpus_equals_unsharded_equals_reference(built_lib, n_gpus, S):
     """SURVEY 8e on real GPUs: the target range cut over n GPUs of one process (idash_b200_cloud_eval_multi_device: peer-copied input
     slabs, rows stored straight into GPU 0's output array through the peer mapping) == the unsharded evaluation on GPU 0 == the
-    reference, every word, index and variance; full iDASH size, neighbors = 20 (BASELINE configs[4] geometry)."""
+    reference, every word, index and variance; full iDASH size, neighbors = 20 (BASELINE configs[4] geometry). 335 samples
+    (NUM_REGIONS = 3): the rotated staging and the zero tail (bulk stores through the peer mapping) on the other GPU."""
     import torch
     if torch.cuda.device_count() < n_gpus:
         pytest.skip(f"needs {n_gpus} GPUs")
-    S, n = 1004, 20
+    n = 20
     geo = synth.Geometry(S, T_FULL, G_FULL)
     tag, tgt = synth.make_positions(T_FULL, G_FULL, SEED)
     model = synth.make_model(tag, tgt, n, SEED)
