@@ -1,0 +1,6 @@
+set -u
+OUT=gpurun_out/r3t; mkdir -p $OUT
+for tune in 456 459 1483 457 458; do
+  IDASH_B200_USE_PROFILE_LIB=1 IDASH_B200_TUNE=$tune timeout 300 python bench.py --neighbors 5 --no-cpu-baseline --no-parity --no-decrypt --sustain 3 --e2e-steps 1 2>>$OUT/err.log | python -c "
+import json,sys; r=json.loads(sys.stdin.read()); s=r['sustained']; print('n5 tune=$tune burst', round(r['roofline']['kernel_ms'],4), 'sustained', round(s['ms_per_step'],4), s['clocks'])"
+done
