@@ -100,7 +100,9 @@ struct RingParams {
                                    // coefficient chunk of a K step is read from shared memory once, tcgen05.mma.ws + collector buffer); host side: 256 / 512 pick
                                    // the kernel's EPI template parameter (x16 loads / burst epilogue)
     uint32_t knockout;             // profiling aid (IDASH_B200_KNOCKOUT, results are wrong when non-zero):
-                                   // 1 no MMAs, 2 no output stores, 4 no epilogue TMEM loads, 8 no input loads, 16 no zero fill, 32 no bias / mask
+                                   // 1 no MMAs, 2 no output stores, 4 no epilogue TMEM loads, 8 no input loads, 16 no zero fill, 32 no bias / mask,
+                                   // 64 producers sleep 20 us before every block (results stay right: tests/test_gpu_cloud.py), 128 without the gate of the
+                                   // MMA warps' slot waits (with 64: the stale-slot race the gate closes shows)
 };
 
 #define RG_ZERO_BYTES 4096u                      // NUM_REGIONS > 1: a block of zeros, the source of the bulk stores that fill b[RS'..N) of every output row
@@ -188,6 +190,10 @@ __device__ __forceinline__ void tc_mma_kstep_ws_p(uint32_t d0, uint64_t da, uint
 // monotonic progress counters in shared memory
 __device__ __forceinline__ void progress_publish(uint32_t *ctr, uint32_t v) {
     asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(ctr)), "r"(v) : "memory");
+}
+// ... advanced by several threads in no fixed order (release: what the publishing warp has observed is visible to whoever reads the value)
+__device__ __forceinline__ void progress_publish_max(uint32_t *ctr, uint32_t v) {
+    asm volatile("fence.acq_rel.cta;\n\tred.relaxed.cta.shared::cta.max.u32 [%0], %1;" ::"r"(smem_u32(ctr)), "r"(v) : "memory");
 }
 __device__ __forceinline__ void progress_wait(const uint32_t *ctr, uint32_t at_least) {
     uint32_t v;
@@ -485,6 +491,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
     __shared__ uint32_t tiles_done_s;       // tiles of this CTA whose MMAs are complete
     __shared__ uint32_t blocks_freed_s;     // input blocks (in staging order) that no pending MMA reads any more
     __shared__ uint32_t mma_issued_s;       // tiles of this CTA whose MMAs have all been handed to the tensor pipe (tune & 32)
+    __shared__ uint32_t waits_done_s;       // tiles of this CTA whose input-block waits have all been satisfied (see the MMA issuers)
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // CTAs [0, n_slices * n_chunks) are the (slice, chunk) pairs that fill the GPU. The SMs that division leaves over (148 = 16 x 9 + 4)
@@ -529,6 +536,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
         tiles_done_s = 0;
         blocks_freed_s = 0;
         mma_issued_s = 0;
+        waits_done_s = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == RG_WARP_MMA) {
@@ -683,6 +691,27 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                     if (s >= n_slots) { s -= n_slots; par ^= 1u; }
                     bar = &a_full[s];
                 }
+                // The a_full waits are PARITY waits on ring slots that are reused every n_slots blocks, and a parity wait is only
+                // meaningful when the slot's previous use is known to be complete: test_wait(parity of use k) is also true while
+                // the barrier is still in use k - 1. One warp waiting for its tiles in order would guarantee that; two warps on
+                // alternating tiles do not -- this warp may get here before the blocks of the OTHER warp's previous tile (whose slots
+                // this tile's new blocks may reuse when the band moves by several blocks per tile) have been staged at all, and in
+                // particular at kernel start, when nothing has (found by running the 9-set NUM_REGIONS = 2 test under
+                // compute-sanitizer: with the producers slowed down, the last rows of a chunk were computed from a stale slot).
+                // Gate: the input-block lanes start polling only when the previous tile's input waits are all satisfied (waits_done_s);
+                // then every block staged before this tile's is in place, i.e. the previous use of every slot this tile adds to.
+                // It is needed only when a slot's previous occupant (n_slots blocks earlier in staging order) is not below what this
+                // warp has itself seen staged, i.e. when the new blocks of this tile and the previous one together wrap the ring --
+                // never on the iDASH geometry (less than one new block per tile), and then neither the gate nor the publication
+                // costs an instruction in the polling loop (gating / publishing every tile cost 1.7 % at neighbors = 5 and 4.3 %
+                // at 50, A/B on one box).
+                // waits_done_s is published as soon as the INPUT lanes are through -- the other warp's input polling need not wait for this
+                // tile's TMEM stage or coefficients.
+                // gate(it) <=> the new blocks of tiles it - 1 and it together wrap the ring; then (and only then) tile it - 1 publishes
+                const uint32_t st_after = max(walk.staged_upto, bt);
+                const uint32_t n_new_next = has_next ? Tn.a + Tn.nb - max(Tn.a, st_after) : 0u;
+                const bool need_gate = (prev_bt - prev_fn) + n_new > n_slots && !(k_knockout & 128u), need_pub = n_new + n_new_next > n_slots;     // knock-out 128: no gate
+                bool gate_open = !need_gate, published = !need_pub;
                 // warp-uniform polling loop: lanes without a barrier count as done
                 const uint32_t bar_addr = bar ? smem_u32(bar) : 0u;
                 // lane 31 (tune & 32): the other warp has handed ALL MMAs of the previous tile to the tensor pipe. The pipe executes
@@ -694,7 +723,12 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                 if (k_tune & 1024u) {
                     // every lane blocks on its own barrier with try_wait (the hardware suspends the thread until the phase completes or a
                     // time limit expires): no polling granularity between "TMEM stage released" and the first MMA of the next tile
-                    if (bar) mbar_wait(bar, par);
+                    if (need_gate) progress_wait(&waits_done_s, it);
+                    if (lane >= 2u && bar) mbar_wait(bar, par);
+                    __syncwarp();
+                    if (need_pub && lane == 0) progress_publish_max(&waits_done_s, it + 1u);
+                    published = true;
+                    if (lane < 2u && bar) mbar_wait(bar, par);
                     if (order_lane) {
                         uint32_t v;
                         do asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(&mma_issued_s)) : "memory");
@@ -704,17 +738,28 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
                     __syncwarp();
                 } else
                 for (;;) {
+                    if (!gate_open) {
+                        uint32_t v;
+                        asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(&waits_done_s)) : "memory");
+                        gate_open = (int32_t) (v - it) >= 0;
+                    }
                     if (!done) {
                         if (order_lane) {
                             uint32_t v;
                             asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(&mma_issued_s)) : "memory");
                             done = (int32_t) (v - it) >= 0 ? 1u : 0u;
-                        } else {
+                        } else if (lane < 2u || gate_open) {
                             done = mbar_test(bar_addr, par);
                         }
                         if (done && k_trace) t_done = clock64();
                     }
-                    if (__all_sync(0xFFFFFFFFu, done)) break;
+                    // (published with a max: a tile that needed no gate may get here before the other warp's previous tile, and a plain
+                    // store of that tile's `it` would then overwrite `it + 2` -- the first version of this gate hung on exactly that)
+                    if (!published && gate_open && __all_sync(0xFFFFFFFFu, done || lane < 2u)) {
+                        if (lane == 0) progress_publish_max(&waits_done_s, it + 1u);      // opens the other warp's gate for tile it + 1
+                        published = true;
+                    }
+                    if (published && gate_open && __all_sync(0xFFFFFFFFu, done)) break;
                     if (!(k_tune & 4u)) __nanosleep(40);      // polling hot next to running MMAs slows them down (measured)
                 }
                 if (k_trace) {
@@ -943,6 +988,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) cloud_ring_kernel(const RingPar
         // split into byte planes and store into the ring slot, once the slot's previous block has been released
         auto store_block = [&](uint32_t kbv, const uint4 (&w)[2][NW]) {
             const uint32_t kb = batched ? kbv & ((1u << RG_BATCH_SHIFT) - 1u) : kbv;
+            if (k_knockout & 64u) __nanosleep(20000);      // profiling build: slow producers (the timing compute-sanitizer produces; results stay right)
             if (seq >= p.n_slots) progress_wait(&blocks_freed_s, seq - p.n_slots + 1u);
             uint8_t *blk = sA + slot * RG_BLOCK_BYTES;
 #pragma unroll

@@ -396,3 +396,23 @@ def test_cloud_host_path_pipelined_pieces(gpu_ctx, n, monkeypatch):
     out3, _, _ = api.cloud_compute_score(gpu_ctx, m, cts, in_var=var)     # the context stays usable
     assert np.array_equal(out3, ref_out)
     m.free()
+
+
+@pytest.mark.parametrize("S", [400, 1004])
+def test_ring_slot_reuse_with_slow_producers(S):
+    """Two MMA warps wait for ring slots by parity; a slot that is reused within two tiles (the band moves by several blocks per tile:
+    500 tag x 300 target SNPs) must not be taken for staged while its previous use is still pending. Found under compute-sanitizer,
+    whose instrumentation slows the producers; the profiling build reproduces that timing (knock-out 64: producers sleep before every
+    block). Runs tools/race_probe2.py in its own process (the profiling library is chosen at import): every launch == the oracle."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    if not (root / "idash2019_2_b200" / "lib" / "libidash_b200_prof.so").exists():
+        pytest.skip("profiling build of the library not present")
+    env = dict(os.environ, IDASH_B200_USE_PROFILE_LIB="1", IDASH_B200_KNOCKOUT="64")
+    r = subprocess.run([sys.executable, str(root / "tools" / "race_probe2.py"), str(S), "300", "3"], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("rep")]
+    assert len(lines) == 3 and all(ln.endswith("bad rows []") for ln in lines), r.stdout[-2000:]
