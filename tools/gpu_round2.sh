@@ -33,7 +33,7 @@ for spec in "n5:--neighbors 5" "n50:--neighbors 50" "s335:--samples 335 --neighb
       python bench.py $args --steps 2 --warmup 1 --e2e-steps 1 --no-cpu-baseline --no-parity --no-decrypt --sustain 0 > "$OUT/ncu_full_$tag.log" 2>&1; echo "ncu full $tag rc=$?"
 done
 timeout 300 python tools/bench_decrypt.py > "$OUT/decrypt.json" 2> "$OUT/decrypt.err"; echo "bench_decrypt rc=$?"; cat "$OUT/decrypt.json"
-DEC_QUICK=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:decrypt_tc -s 3 -c 1 -f -o "$OUT/prof_decrypt_tc" \
+DEC_QUICK=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:decrypt_pair -s 3 -c 1 -f -o "$OUT/prof_decrypt_pair" \
     python tools/bench_decrypt.py > "$OUT/ncu_full_decrypt.log" 2>&1; echo "ncu decrypt rc=$?"
 timeout 600 python tools/population_bench.py > "$OUT/populations.json" 2> "$OUT/populations.err"; echo "population bench rc=$?"; tail -3 "$OUT/populations.json"
 ls -la "$OUT"
