@@ -4,14 +4,18 @@
 //   * grid = 16 slices x C chunks (C = SMs / 16): CTA (slice, chunk) walks the tiles of its chunk in order
 //     for ONE 128-word slice of the ciphertext axis. The 16 CTAs of a chunk advance together, so whole
 //     8 KB ciphertexts are read / written at about the same time and a tile's coefficient image is
-//     fetched from HBM once and served to the other 15 CTAs by L2.
+//     fetched from HBM once and served to the other 15 CTAs by L2. The SMs that division leaves over (148 = 16 x 9 + 4)
+//     run one more, short chunk in waves (RingParams::extra_tiles): the kernel's time follows the number of SMs it uses.
 //   * the limb planes of the input blocks (32 features x 128 words x 4 planes = 18 KB) live in a
 //     shared-memory RING: consecutive tiles share most of their band, so every (block, slice) is loaded
 //     from global memory, split into byte planes and stored ONCE per CTA -- the north-star's "stage each
 //     overlapping tag window once and reuse it across consecutive target SNPs".
 //   * roles: warps 0-7 epilogue (TMEM lane quadrant = warp id % 4, rows 32 (warp id / 4) .. +31 of the tile),
-//     warp 8 MMA issuer (+ TMEM owner), warp 9 coefficient loader (one cp.async.bulk per tile into a ring of
-//     tile-sized stages), warps 10-13 block producers, warp 14 progress publisher.
+//     warps 8 and 15 MMA issuers (even / odd tiles = TMEM stage 0 / 1; warp 8 owns the TMEM allocation), warp 9 coefficient
+//     loader (cp.async.bulk copies of a tile's image into a ring of 4 KB chunks, of its metadata record into a ring of 8),
+//     warps 10-13 block producers, warp 14 progress publisher.
+//   * the MMA warps wait for input blocks by PARITY on reused ring slots; two warps on alternating tiles can be a whole use
+//     early where one warp could not, hence the gate on waits_done_s (see the MMA issuers).
 //   * synchronisation is built so that the MMA warp -- the one serial instruction stream every tile passes
 //     through -- does as little as possible per tile: its waits (TMEM stage free, coefficient stage full, new
 //     input blocks full) are taken by different lanes at the same time, and it issues ONE tcgen05.commit per
