@@ -24,16 +24,19 @@
 //     lanes that hold one 16-coefficient block split their words into byte planes (PRMT, reversed order), transpose
 //     4 x 4 with 4 shuffles, and each stores one 16-byte row. The operand lives in a shared-memory ring of slots
 //     (128 k' x 128 n, 16.5 KB with the bank-conflict pad).
-//   * TMEM: 4 stages x 128 columns = all 512 columns, one j block each. A group of 32 ciphertexts takes 8 passes
-//     (one j block each) over its 8 ring slots: 256 MMAs ~ 16 k cycles, the same order as the HBM time of the
-//     group's 384 KB (a, b in; scores out), so the kernel sits near both rooflines; measured numbers in DESIGN.md.
-//     The MMA warp may run three j blocks ahead of the epilogue (with 2 stages of 2 j blocks it stalled 22 % of the
-//     time on a free stage: the epilogue needs ~3650 of the 4096 cycles a pass gives it, and any jitter showed).
-//   * roles (416 threads, 128 registers per thread; one persistent CTA per SM, groups strided over the grid):
-//     warps 0-3 epilogue (warp = TMEM lane quadrant; the b words of the next j block are prefetched into the registers
-//     just consumed), warp 4 MMA issuer + TMEM owner, warps 5-12 producers (six 4 x 16-byte units in flight per thread).
+//   * TMEM: 4 stages x 128 columns = all 512 columns, one j block each. A group of 32 ciphertexts takes 4 passes (PAIRS of j
+//     blocks: tcgen05.mma.ws keeps a K step's byte-plane chunk in the collector buffer for both j blocks, 6 instead of 8 KB of
+//     operand reads per MMA) over its 8 ring slots: 256 MMAs ~ 16 k cycles, the same order as the HBM time of the group's 384 KB
+//     (a, b in; scores out), so the kernel sits near both rooflines; measured numbers in DESIGN.md 3.4.
+//   * roles (448 threads, 128 registers per thread; one persistent CTA per SM, groups strided over the grid):
+//     warps 0-3 epilogue (warp = TMEM lane quadrant; TMEM loads double-buffered; the b words come from a shared-memory ring),
+//     warp 4 MMA issuer + TMEM owner, warps 5-12 producers (six 4 x 16-byte units in flight per thread; a unit is split and
+//     transposed two units ahead of its store, so a freed slot is refilled by a wait and four stores), warp 13 b loader
+//     (one thread: a tensor copy -- cp.async.bulk.tensor.2d -- of 128 words x 16 ciphertexts per half stage).
 //     The first version had 8 epilogue warps (544 threads, 96 registers): they idled 78 % of the time while the register
 //     cap limited the producers to 4 units.
+//   * decrypt_pair.cuh is this kernel on CTA pairs (cta_group::2) and the default; this one remains selectable
+//     (IDASH_B200_DECRYPT_TENSOR) and is what AUTO falls back to where a cluster launch is not possible.
 #pragma once
 
 #define DT_CTS 32u                        // ciphertexts per group
