@@ -20,6 +20,12 @@ ciphertexts. `value` is timed with the inputs resident in HBM; `e2e` goes throug
 call (H2D + kernels + D2H inside the timed region). The reference arm (--impl reference) and the
 `cpu_baseline` object time the reference's own cloud_compute_score (oracle/_ref, compiled from the
 unmodified reference) on this box's host cores.
+
+Further records of the line: `sustained` (seconds of back-to-back steps with their own clock / power samples),
+`decrypt` (the decrypt stage on the step's own outputs: `roofline` against HBM plus `roofline.tensor` against the
+int8 tensor rate, `e2e` through the host-buffer call, `parity` against the exact integer phase, the reference's
+decrypt_predictions as `cpu_baseline`; at N > 1 also `sharded`: every rank decrypts its own rows), `nvlink` (N > 1:
+the scatter of the input slabs from rank 0 and the gather of the rows back, and sharded == unsharded on the GPU).
 """
 from __future__ import annotations
 
